@@ -1,0 +1,51 @@
+'''Shared list of parity cases: (parameters, grid, state).  Used by make_golden.py (run once
+in the build container against the unmodified Python reference) and by the tests (which load
+the committed .npz files; nothing here touches /root/reference).'''
+import numpy
+
+LDC = {'Reynolds Number': 100}
+RB = {'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 1000.0, 'Prandtl Number': 10.0,
+      'Biot Number': 1.0, 'X-max': 10, 'Y-max': 10, 'Reynolds Number': 1}
+RBP = {'Problem Type': 'Rayleigh-Benard Perturbation', 'Rayleigh Number': 1500.0, 'Prandtl Number': 10.0,
+       'Biot Number': 1.0, 'X-max': 10, 'Asymmetry Parameter': 0.3}
+DHC = {'Problem Type': 'Differentially Heated Cavity', 'Rayleigh Number': 1e4, 'Prandtl Number': 1000.0,
+       'Reynolds Number': 1, 'X-max': 0.051, 'Y-max': 1}
+QG = {'Problem Type': 'Double Gyre', 'Reynolds Number': 16, 'Rossby Parameter': 1000,
+      'Wind Stress Parameter': 1000}
+AMOC = {'Problem Type': 'AMOC', 'Rayleigh Number': 4e4, 'Prandtl Number': 2.25, 'Lewis Number': 1,
+        'Freshwater Flux': 0.1, 'Temperature Forcing': 1, 'X-max': 5}
+STR = {'Grid Stretching Factor': 1.5}
+
+# name: (parameters, nx, ny, nz, dim, dof, state-kind)   state-kind: 'lin' | 'zero' | int seed
+CASES = {
+    'ldc3d_lin': (LDC, 4, 4, 4, None, None, 'lin'),
+    'ldc3d_rand': (LDC, 6, 5, 4, None, None, 0),
+    'ldc3d_zero': (LDC, 4, 4, 4, None, None, 'zero'),
+    'ldc3d_str_rand': ({**LDC, **STR, 'Lid Velocity': 2.5}, 5, 6, 7, None, None, 1),
+    'ldc3d_8_rand': (LDC, 8, 8, 8, None, None, 2),
+    'ldc3d_small': (LDC, 2, 3, 2, None, None, 3),
+    'stokes3d_rand': ({'Reynolds Number': 0}, 4, 4, 4, None, None, 4),
+    'ldc2d_rand': ({**LDC, **STR}, 8, 6, 1, None, None, 5),
+    'ldc2d_lin': (LDC, 4, 4, 1, None, None, 'lin'),
+    'ldc_semi2d_rand': (LDC, 6, 5, 1, 3, 4, 6),
+    'rb3d_rand': (RB, 4, 5, 6, None, None, 7),
+    'rb3d_str_lin': ({**RB, **STR}, 4, 4, 4, None, None, 'lin'),
+    'rb2d_rand': (RB, 8, 6, 1, None, None, 8),
+    'rbp3d_rand': (RBP, 5, 4, 6, None, None, 9),
+    'rbp2d_str_rand': ({**RBP, **STR}, 6, 8, 1, None, None, 10),
+    'rb_semi2d_rand': (RB, 6, 5, 1, 3, 5, 11),
+    'dhc2d_rand': (DHC, 8, 8, 1, None, None, 12),
+    'dhc3d_rand': (DHC, 4, 5, 4, None, None, 13),
+    'qg_rand': (QG, 8, 6, 1, None, None, 14),
+    'qg_zero': (QG, 6, 6, 1, None, None, 'zero'),
+    'amoc_rand': (AMOC, 8, 6, 1, None, None, 15),
+    'amoc_str_lin': ({**AMOC, **STR}, 6, 4, 1, None, None, 'lin'),
+}
+
+
+def make_state(kind, n):
+    if kind == 'lin':
+        return numpy.arange(1, n + 1, dtype=numpy.float64)
+    if kind == 'zero':
+        return numpy.zeros(n)
+    return numpy.random.default_rng(kind).uniform(-0.5, 0.5, n)
