@@ -1,0 +1,204 @@
+'''Host-side preparation for the B200 assembly kernels (numpy only).
+
+Everything that involves transcendentals (grid stretching, wind / AMOC forcing profiles,
+sqrt of the Grashof number) or the mutable parameter dictionary is evaluated here, on the
+host, with the same numpy expressions the reference uses, and handed to the kernels as
+1-D metric arrays and a small struct of scalars.  File:line citations are to
+/root/reference/transiflow/.
+'''
+import ctypes
+
+import numpy
+
+from . import recipes
+
+TFB_MAX_FORCE = 8
+TFB_NMET = 8
+
+
+class TfbParams(ctypes.Structure):
+    '''Mirror of ``struct TfbParams`` (csrc/tfb_rows_common.h).'''
+    _fields_ = [
+        ('c_visc', ctypes.c_double), ('c_T', ctypes.c_double), ('c_S', ctypes.c_double),
+        ('c_pert', ctypes.c_double), ('beta', ctypes.c_double),
+        ('bc_cf', ctypes.c_double * TFB_MAX_FORCE), ('bc_ca', ctypes.c_double * TFB_MAX_FORCE),
+        ('nl', ctypes.c_int), ('has_beta', ctypes.c_int), ('pert', ctypes.c_int), ('pad_', ctypes.c_int),
+    ]
+
+
+# ---------------------------------------------------------------------------------------
+# coordinate vectors (utils.py:175-267): length n+3, x[i] = east face of cell i, the two
+# trailing entries are the faces at and before the domain start (Python wrap-around).
+# ---------------------------------------------------------------------------------------
+
+def uniform_vector(start, end, n):
+    h = (end - start) / n
+    faces = start + numpy.arange(-1, n + 2) * h
+    return numpy.roll(faces, -2)
+
+
+def _mirror_ghost_cells(x, start, end):
+    h = x[0] - x[-1]
+    if start == 0:
+        x[-2] = x[-1] - h
+    if end == 1:
+        x[-3] = x[-4] + h
+    return x
+
+
+def stretched_vector(start, end, n, sigma, method='tanh'):
+    x = uniform_vector(0, 1, n)
+    if method == 'sin':
+        x = x - sigma * numpy.sin(2 * numpy.pi * x)
+    else:
+        x = 0.5 * (1 + numpy.tanh(2 * sigma * (x - 0.5)) / numpy.tanh(sigma))
+    x = start + x * (end - start)
+    return _mirror_ghost_cells(x, start, end)
+
+
+def coordinate_vector(parameters, start, end, n):
+    '''Discretization.get_coordinate_vector (Discretization.py:186-208).'''
+    if parameters.get('Grid Stretching', False) or 'Grid Stretching Factor' in parameters:
+        if parameters.get('Grid Stretching Method', 'tanh') == 'sin':
+            return stretched_vector(start, end, n, parameters.get('Grid Stretching Factor', 0.1), 'sin')
+        return stretched_vector(start, end, n, parameters.get('Grid Stretching Factor', 1.5), 'tanh')
+    return uniform_vector(start, end, n)
+
+
+def cell_centers(vec):
+    '''utils.compute_coordinate_vector_centers (utils.py:269-288): centre of cell i at [i],
+    ghost cell before the domain at [-1].'''
+    n = len(vec) - 1
+    idx = numpy.arange(-1, n - 1)
+    out = numpy.zeros(n)
+    out[idx] = (vec[idx] + vec[idx - 1]) / 2
+    return out
+
+
+def axis_metrics(X, n):
+    '''The TFB_NMET 1-D arrays of one axis, shape (8, n), C order:
+    hc, hu, 1/hc, 1/hp, 1/hm, 1/hu, wm, wp with Python wrap-around indexing of X.'''
+    X = numpy.asarray(X, dtype=numpy.float64)
+    i = numpy.arange(n)
+    hc = X[i] - X[i - 1]                    # cell width                (Discretization.py:743)
+    hp = X[i + 1] - X[i]                    # next cell width           (:745)
+    hu = (X[i + 1] - X[i - 1]) / 2          # staggered width           (:784)
+    hm = (X[i] - X[i - 2]) / 2              # centre distance i-1 -> i  (:780)
+    wm = 1 / 2 * hc / hu                    # _weighted_average         (:1220)
+    wp = 1 / 2 * hp / hu                    #                           (:1221)
+    return numpy.ascontiguousarray(numpy.stack([hc, hu, 1 / hc, 1 / hp, 1 / hm, 1 / hu, wm, wp]))
+
+
+def coriolis_metrics(Y, ny):
+    j = numpy.arange(ny)
+    Y = numpy.asarray(Y, dtype=numpy.float64)
+    return numpy.ascontiguousarray(numpy.stack([Y[j] / 2, -(Y[j] + Y[j - 1]) / 4]))
+
+
+def _get(parameters, name, default=0):
+    '''Discretization.get_parameter (Discretization.py:164-184).'''
+    return parameters.get(name, default) if name in parameters else default
+
+
+def _robin_constants(X, m, far, Q, Bi):
+    '''heat_flux_<face> (BoundaryConditions.py:339-421).'''
+    if far:
+        h = (X[m] - X[m - 2]) / 2
+        return h * Q / (1 + h * Bi / 2), (1 - h * Bi / 2) / (1 + h * Bi / 2)
+    h = (X[0] - X[-2]) / 2
+    return -h * Q / (1 - h * Bi / 2), (1 + h * Bi / 2) / (1 - h * Bi / 2)
+
+
+def wind_stress(parameters, nx, ny, nz, dof, x, y, z):
+    '''Discretization.wind_stress (Discretization.py:1101-1118) as a state-ordered vector.'''
+    alpha = _get(parameters, 'Wind Stress Parameter')
+    asym = _get(parameters, 'Asymmetry Parameter')
+    i, j, k = numpy.arange(nx - 1), numpy.arange(ny), numpy.arange(nz)
+    dx = ((x[i + 1] - x[i - 1]) / 2)[:, None, None]
+    dy = (y[j] - y[j - 1])[None, :, None]
+    dz = (z[k] - z[k - 1])[None, None, :]
+    yc = ((y[j] + y[j - 1]) / 2)[None, :, None]
+    val = - (1 - asym) * numpy.cos(2 * numpy.pi * yc) - asym * numpy.cos(numpy.pi * yc)
+    val = val * (alpha / (2 * numpy.pi) * dx * dy * dz)
+    frc = numpy.zeros((nz, ny, nx, dof))
+    frc[:, :, :nx - 1, 0] = numpy.transpose(val, (2, 1, 0))
+    return frc.ravel()
+
+
+def amoc_face_values(parameters, nx, ny, nz, x, y):
+    '''Value arrays of temperature_north(theta*T_S) and salinity_flux_north(sigma*Q_S)
+    (Discretization.py:670-686; BoundaryConditions.py:316,445,472), reduced to the in-plane
+    centre entries the kernels need: shape (nz, nx), first in-plane axis (x) fastest.'''
+    xc = cell_centers(x)
+    theta = _get(parameters, 'Temperature Forcing')
+    asym = _get(parameters, 'Asymmetry Parameter')
+    A = parameters.get('X-max', 1.0)
+    T_S = numpy.zeros((nx + 2, nz + 2))
+    T_S[:, 0] = 1 / 2 * ((1 - asym) * numpy.cos(2 * numpy.pi * (xc / A - 1 / 2))
+                         + asym * numpy.cos(numpy.pi * xc / A) + 1)
+    tval = numpy.ones((nx + 2, nz + 2)) * (2 * (theta * T_S))
+    sigma = _get(parameters, 'Freshwater Flux')
+    p = 2
+    Q_S = numpy.zeros((nx + 2, nz + 2))
+    Q_S[:, 0] = 3 * numpy.cos(p * numpy.pi * (xc / A - 1 / 2)) - 6 / (p * numpy.pi) * numpy.sin(p * numpy.pi / 2)
+    h = (y[ny] - y[ny - 2]) / 2
+    sval = numpy.ones((nx + 2, nz + 2)) * (h * (sigma * Q_S))
+    return (numpy.ascontiguousarray(tval[:nx, :nz].T), numpy.ascontiguousarray(sval[:nx, :nz].T))
+
+
+def make_params(cfg, problem, parameters, nx, ny, nz, x, y, z):
+    '''Evaluate the per-call scalars from the (mutable, shared) parameter dict.  Returns
+    (TfbParams, {force op index: face value array}).'''
+    prm = TfbParams()
+    Re = _get(parameters, 'Reynolds Number', 1.0)       # Discretization.py:236,278
+    Ra = _get(parameters, 'Rayleigh Number', 1.0)
+    Pr = _get(parameters, 'Prandtl Number', 1.0)
+    Gr = _get(parameters, 'Grashof Number', Ra / Pr)
+    Le = _get(parameters, 'Lewis Number', 1.0)
+    if Re == 0:
+        Re = 1
+    if Gr == 0:
+        Gr = 1 / Pr
+    prm.c_visc = 1 / (Re * numpy.sqrt(Gr))
+    prm.c_T = 1 / (Pr * numpy.sqrt(Gr))
+    prm.c_S = 1 / (Le * Pr * numpy.sqrt(Gr))
+    Bi = _get(parameters, 'Biot Number')
+    prm.pert = int(problem == recipes.RBP)
+    prm.c_pert = Bi / (Bi + 1) if prm.pert else 0.0
+    beta = _get(parameters, 'Rossby Parameter')
+    prm.beta = beta
+    prm.has_beta = int(bool(beta) and cfg.dim == 2)
+    Re_nl = _get(parameters, 'Reynolds Number')         # default 0 here, Discretization.py:333
+    prm.nl = int(not (Re_nl == 0 and not cfg.dof > cfg.dim + 1))
+    X = (x, y, z)
+    m = (nx, ny, nz)
+    arrays = {}
+    fidx = 0
+    for op in cfg.recipe:
+        if op[0] != 'force':
+            continue
+        _, axis, far, var, kind, arg = op
+        if kind == 'lid':
+            cf, ca = 2 * _get(parameters, 'Lid Velocity', 1), -1
+        elif kind == 'temp':
+            Tb = (1 if problem == recipes.RB else 0) if arg == 'bottom' else arg
+            cf, ca = 2 * Tb, -1
+        elif kind == 'hflux':
+            Q = _get(parameters, 'Asymmetry Parameter') if arg[0] == 'asym' else arg[0]
+            b = Bi if arg[1] == 'Bi' else 0.0
+            cf, ca = _robin_constants(X[axis], m[axis], far, Q, b)
+        elif kind == 'sflux':
+            Xa = X[axis]
+            h = (Xa[m[axis]] - Xa[m[axis] - 2]) / 2 if far else (Xa[0] - Xa[-2]) / 2
+            cf, ca = (h * arg, 1) if far else (-h * arg, 1)
+        elif kind in ('tarr', 'sarr'):
+            if 'amoc' not in arrays:
+                arrays['amoc'] = amoc_face_values(parameters, nx, ny, nz, x, y)
+            arrays[fidx] = arrays['amoc'][0 if kind == 'tarr' else 1]
+            cf, ca = 0.0, (-1 if kind == 'tarr' else 1)
+        else:
+            raise ValueError(kind)
+        prm.bc_cf[fidx], prm.bc_ca[fidx] = cf, ca
+        fidx += 1
+    arrays.pop('amoc', None)
+    return prm, arrays
