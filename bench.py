@@ -1,0 +1,255 @@
+#!/usr/bin/env python3
+'''Benchmark of the B200 TransiFlow backend's hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 128] [--impl reference]
+
+Workload (BASELINE.json north_star / SURVEY.md section 8d): 3D lid-driven cavity, Re = 100,
+grid^3 cells (default 128^3, n = 8.4 M unknowns, nnz = 118 M), synthetic state
+uniform(-0.5, 0.5) seed 0.  One "step" = one fused Jacobian+RHS assembly on the fixed
+sparsity pattern.  `value` = cells/s with the state resident in HBM; `e2e` = the same through
+Interface.jacobian_rhs() with host buffers (H2D state + D2H F(x) inside the timed region).
+With N > 1 (torchrun, one process per GPU) the grid is split into z-slabs, weak scaling:
+every rank owns grid/1 planes of a (grid x grid x N*grid) domain... see --scaling.
+
+`--impl reference` times the CPU implementation of the same path (the C port of the
+reference in oracle/, all host threads) on a bounded sample of the workload.
+'''
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PARAMS = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    '''nvidia-smi clocks / throttle reasons during the timed region.'''
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([s.strip() for s in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()]
+        reasons = []
+        for idx, name in ((2, 'hw_slowdown'), (3, 'hw_thermal_slowdown'), (4, 'sw_thermal_slowdown'), (5, 'sw_power_cap')):
+            if any(len(s) > idx and s[idx].lower().startswith('active') for s in self.samples):
+                reasons.append(name)
+        return {'sm_mhz': float(numpy.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_port_cells_per_s(grid, planes, repeats=1):
+    '''Jacobian+RHS with the oracle C port (all OpenMP threads) on a (grid x grid x planes) sample.'''
+    from oracle.tf_oracle import Oracle, lib
+    orc = Oracle(dict(PARAMS), grid, grid, planes)
+    state = numpy.random.default_rng(0).uniform(-0.5, 0.5, orc.n)
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        orc.jacobian(state)
+        orc.rhs(state)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return grid * grid * planes / best, lib().tfo_num_threads(), best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    grid = args.grid
+    planes = max(2, min(grid, 16))
+    sample = '3D LDC %dx%dx%d slab of the %d^3 grid (Jacobian+RHS, C port of the reference, OpenMP)' % (grid, grid, planes, grid)
+    for _ in range(args.warmup):
+        cpu_port_cells_per_s(grid, planes)
+    times = []
+    cores = 1
+    for _ in range(args.steps):
+        v, cores, dt = cpu_port_cells_per_s(grid, planes)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = grid * grid * planes / (ms * 1e-3)
+    out = {
+        'impl': 'reference', 'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': '3D lid-driven cavity %d^3, Re=100, fused Jacobian+RHS assembly' % grid},
+        'cpu_baseline': {'value': value, 'unit': 'cells/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--grid', type=int, default=128)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import ctypes
+    from transiflow_b200 import Interface, _lib
+    from transiflow_b200._lib import check, ptr
+    L = _lib.lib()
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('gloo')     # plumbing only: id broadcast, barrier, max-reduce
+
+    grid = args.grid
+    # weak scaling: every rank owns `grid` planes of a (grid x grid x world*grid) domain
+    nz = grid * world
+    it = Interface(dict(PARAMS), grid, grid, nz, device=local_rank, slab=(rank * grid, (rank + 1) * grid)) \
+        if world > 1 else Interface(dict(PARAMS), grid, grid, grid, device=local_rank)
+    if world > 1:
+        import torch
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (ctypes.c_uint8 * 128)()
+            check(L.tfb_nccl_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        dist.broadcast(idbuf, 0)
+        raw = (ctypes.c_uint8 * 128)(*idbuf.tolist())
+        check(L.tfb_comm_init(it._ctx, world, rank, raw))
+
+    n_local = it.n_local
+    cells_local = n_local // it.dof
+    state = _lib.pinned_array(n_local)
+    state[:] = numpy.random.default_rng(rank).uniform(-0.5, 0.5, n_local)
+    out = _lib.pinned_array(n_local)
+    it._sync_params()
+    from transiflow_b200 import DeviceMatrix
+    mat = DeviceMatrix(it)
+
+    def barrier():
+        check(L.tfb_sync(it._ctx))
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    launches0 = L.tfb_launch_count()
+    # ---- kernel-only: state resident in HBM; L2 flushed between iterations ----
+    check(L.tfb_state_upload(it._ctx, ptr(state)))
+    for _ in range(args.warmup):
+        check(L.tfb_assemble_resident(it._ctx, mat._h, 1, 1))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kern_ms = []
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        check(L.tfb_flush_l2(it._ctx))
+        check(L.tfb_event_record(it._ctx, 0))
+        check(L.tfb_assemble_resident(it._ctx, mat._h, 1, 1))
+        check(L.tfb_event_record(it._ctx, 1))
+        ms = ctypes.c_float()
+        check(L.tfb_event_elapsed_ms(it._ctx, 0, 1, ctypes.byref(ms)))
+        kern_ms.append(ms.value)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.tfb_launch_count() - launches0
+    step_ms = max_over_ranks(sum(kern_ms) / len(kern_ms))
+    # ---- e2e: host buffers through the public API, copies inside the timed region ----
+    for _ in range(3):
+        it.jacobian_rhs_into(state, mat, out)
+    barrier()
+    t0 = time.perf_counter()
+    check(L.tfb_event_record(it._ctx, 2))
+    for s in range(args.steps):
+        it.jacobian_rhs_into(state, mat, out)
+    check(L.tfb_event_record(it._ctx, 3))
+    ms = ctypes.c_float()
+    check(L.tfb_event_elapsed_ms(it._ctx, 2, 3, ctypes.byref(ms)))
+    barrier()
+    e2e_ms = max_over_ranks(ms.value / args.steps)
+
+    if rank != 0:
+        return
+    total_cells = cells_local * world
+    value = total_cells / (step_ms * 1e-3)
+    nnz = it.nnz
+    alg_bytes = 8 * nnz + 16 * n_local       # CSR values written + state read + RHS written
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    line = {
+        'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': '3D lid-driven cavity %d^3 per GPU, Re=100, fused Jacobian+RHS assembly' % grid,
+                   'grid': [grid, grid, nz], 'unknowns': n_local * world, 'nnz_per_gpu': nnz,
+                   'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': None, 'peak_source': peak_src, 'kernel': 'tfb_assemble_kernel<Cfg_ldc3d,J,F>',
+                     'algorithmic_bytes_per_launch': alg_bytes},
+        'e2e': {'value': total_cells / (e2e_ms * 1e-3), 'unit': 'cells/s', 'ms_per_step': e2e_ms,
+                'h2d_bytes_per_step': 8 * n_local, 'd2h_bytes_per_step': 8 * n_local},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        planes = max(2, min(grid, 32))
+        v, cores, dt = cpu_port_cells_per_s(grid, planes, repeats=2)
+        line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
+                                'sample': '%dx%dx%d slab of the workload, Jacobian+RHS, oracle C port with OpenMP' % (grid, grid, planes)}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,128 @@
+/*
+ * tfb200.h -- C ABI of the B200-native TransiFlow backend (libtfb200.so).
+ *
+ * The reference (BIMAU/transiflow) is pure Python and has no FFI; this ABI is the boundary a
+ * `transiflow/interface/<Backend>.py` module binds with ctypes.  Each entry
+ * point names the reference method it replaces (paths relative to /root/reference/transiflow).
+ *
+ * Conventions: every function returns 0 on success, <0 on error (message via
+ * tfb_last_error()), >0 for "did not converge" style soft statuses.  All vectors are
+ * contiguous fp64 in the reference's state ordering [u,v,(w),p,(T),(S)] per cell, cells
+ * i-fastest then j, k (Discretization.py:20-26).  With z-slab partitioning every rank passes
+ * only the planes it owns; halos are exchanged inside the library.
+ */
+#ifndef TFB200_H
+#define TFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFB_MAX_FORCE 8
+#define TFB_NMET 8
+
+typedef struct tfb_ctx tfb_ctx; /* one discretised problem (or one z-slab of it) on one GPU */
+typedef struct tfb_mat tfb_mat; /* CSR values on the ctx's fixed sparsity pattern */
+
+/* Per-call scalars; layout identical to struct TfbParams in csrc/tfb_rows_common.h.
+ * Evaluated by the host exactly like Discretization._linear_part_2D/3D (Discretization.py:229-317)
+ * and BoundaryConditions.heat_flux_* etc. (BoundaryConditions.py:339-469). */
+typedef struct {
+    double c_visc, c_T, c_S, c_pert, beta;
+    double bc_cf[TFB_MAX_FORCE], bc_ca[TFB_MAX_FORCE];
+    int32_t nl, has_beta, pert, pad_;
+} tfb_params;
+
+/* Problem descriptor: replaces the constructor arguments of Discretization
+ * (Discretization.py:106-143).  Coordinate vectors enter as the per-axis metric arrays of
+ * hostprep.axis_metrics (shape (TFB_NMET, n_axis), host memory, copied). */
+typedef struct {
+    int32_t config;          /* generated kernel family, recipes.Config.cid */
+    int32_t nx, ny, nz, dim, dof;
+    int32_t device;          /* CUDA device ordinal */
+    int32_t k0, k1;          /* owned z-planes [k0,k1); single GPU: 0, nz */
+    const double* met[3];
+    const double* cor;       /* (2, ny) Coriolis metrics */
+} tfb_desc;
+
+int tfb_device_count(void);
+const char* tfb_last_error(void);
+const char* tfb_config_name(int config);
+
+int tfb_create(const tfb_desc* desc, tfb_ctx** out);
+void tfb_destroy(tfb_ctx* ctx);
+
+/* Discretization.set_parameter / the shared parameter dict: scalars for the next calls.
+ * fval[f]: optional host array of face values for 'force' op f (AMOC), in-plane order;
+ * frc_static: optional host vector (local rows) added to the RHS (wind stress). */
+int tfb_set_params(tfb_ctx* ctx, const tfb_params* prm, const double* const* fval,
+                   const int8_t* fdir, const double* frc_static);
+
+/* sizes of the local slab: rows, structural non-zeros, first global row */
+int tfb_sizes(tfb_ctx* ctx, int64_t* n_local, int64_t* nnz_local, int64_t* n_global, int64_t* row0);
+/* CrsMatrix.begA / jcoA of the fixed structural pattern (int64 like the reference), host out.
+ * row_ptr has n_local+1 entries starting at 0; col_idx holds GLOBAL column indices. */
+int tfb_get_pattern(tfb_ctx* ctx, int64_t* row_ptr, int64_t* col_idx);
+
+int tfb_mat_create(tfb_ctx* ctx, tfb_mat** out);
+void tfb_mat_destroy(tfb_mat* mat);
+int tfb_mat_get_values(tfb_mat* mat, double* vals_out);        /* D2H, nnz_local doubles */
+int tfb_mat_set_values(tfb_mat* mat, const double* vals_in);   /* H2D */
+
+/* Interface.rhs -> Discretization.rhs (Discretization.py:367-390); host in, host out. */
+int tfb_rhs(tfb_ctx* ctx, const double* state, double* out);
+/* Interface.jacobian -> Discretization.jacobian (:392-415) into `mat`; if rhs_out != NULL the
+ * same launch also produces F(x) (fused Jacobian+RHS). */
+int tfb_jacobian(tfb_ctx* ctx, const double* state, tfb_mat* mat, double* rhs_out);
+/* Interface.mass_matrix -> Discretization.mass_matrix (:417-437): the diagonal, one value per
+ * local row (0 for pressure rows). */
+int tfb_mass_diag(tfb_ctx* ctx, double* diag_out);
+
+/* Device-resident variants used for kernel-only timing: state already uploaded. */
+int tfb_state_upload(tfb_ctx* ctx, const double* state);
+int tfb_assemble_resident(tfb_ctx* ctx, tfb_mat* mat, int do_jacobian, int do_rhs);
+int tfb_rhs_download(tfb_ctx* ctx, double* out);
+int tfb_sync(tfb_ctx* ctx);
+
+/* CUDA-event timers on the ctx's stream. slot in [0,16). */
+int tfb_event_record(tfb_ctx* ctx, int slot);
+int tfb_event_elapsed_ms(tfb_ctx* ctx, int slot_a, int slot_b, float* ms);
+/* write `bytes` of device memory (> L2) to evict the L2 between timed iterations */
+int tfb_flush_l2(tfb_ctx* ctx);
+/* page-locked host buffers for the host<->device legs of the e2e path */
+int tfb_pinned_alloc(size_t bytes, void** out);
+int tfb_pinned_free(void* p);
+/* number of kernel launches issued by this library since load */
+int64_t tfb_launch_count(void);
+
+/* y = A x with host vectors (CrsMatrix.matvec / `jac @ x` of the SciPy backend) */
+int tfb_spmv(tfb_mat* mat, const double* x, double* y);
+
+/* Interface.solve (interface/SciPy.py:204-315): solve mat * x = b with the pressure pinned at
+ * local row `pressure_row` (<0: no pin) by preconditioned FGMRES to ||r||/||b|| <= tol.
+ * Returns 0 converged, 1 not converged (x holds the best iterate). */
+typedef struct {
+    double tol;
+    int32_t maxit, restart;
+    int32_t pressure_row;
+    int32_t precond;        /* TFB_PREC_* */
+    int32_t verbose;
+    int32_t reserved[3];
+} tfb_solve_opts;
+typedef struct {
+    int32_t iters, converged;
+    double relres;
+    float setup_ms, solve_ms;
+} tfb_solve_info;
+int tfb_solve(tfb_mat* mat, const double* b, double* x, const tfb_solve_opts* opts, tfb_solve_info* info);
+
+/* NCCL plumbing for z-slab runs (one process per GPU). */
+int tfb_nccl_unique_id(uint8_t id[128]);
+int tfb_comm_init(tfb_ctx* ctx, int nranks, int rank, const uint8_t id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

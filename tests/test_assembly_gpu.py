@@ -1,0 +1,151 @@
+'''Parity of the CUDA assembly path (through the Interface / C ABI) against the committed golden
+vectors, the reference's own golden files and the CPU oracle.  Bit-exact for the integer
+pattern; fp64 values are required to be within 1e-12 relative (north_star) and are in fact
+compared bit-for-bit (the kernels are built with -fmad=false and keep the reference's
+operation order).'''
+import numpy
+import pytest
+
+from cases import CASES, make_state
+from golden_io import assert_csr_equal, compress, load_case, read_ref_matrix, read_ref_vector
+
+pytestmark = pytest.mark.gpu
+
+SUPPORTED = sorted(CASES)
+
+
+def _iface(params, nx, ny, nz, dim, dof, x=None, y=None, z=None):
+    from transiflow_b200 import Interface
+    return Interface(dict(params), nx, ny, nz, dim, dof, x, y, z)
+
+
+def _rhs_close(f, want, exact):
+    if exact:
+        assert numpy.array_equal(f, want), 'rhs not bit-identical, max abs diff %.3e' % numpy.abs(f - want).max()
+    else:
+        assert numpy.allclose(f, want, rtol=1e-12, atol=1e-12 * numpy.abs(want).max())
+
+
+@pytest.mark.parametrize('name', SUPPORTED)
+def test_gpu_matches_reference_generated_golden(name):
+    params, nx, ny, nz, dim, dof, kind = CASES[name]
+    g = load_case(name)
+    it = _iface(params, nx, ny, nz, int(g['dim']), int(g['dof']), g['x'], g['y'], g['z'])
+    state = g['state']
+    jac = it.jacobian(state)
+    row_ptr, col = it.pattern()
+    got = compress(jac.values(), col, row_ptr)
+    assert_csr_equal(got, (g['coA'], g['jcoA'], g['begA']), 0.0, name)
+    exact = params.get('Problem Type') not in ('Double Gyre', 'AMOC')   # host cos() may differ by an ulp
+    _rhs_close(it.rhs(state), g['rhs'], exact)
+    # fused Jacobian+RHS launch gives the same bits as the separate launches
+    jac2, f2 = it.jacobian_rhs(state)
+    assert numpy.array_equal(jac2.values(), jac.values())
+    assert numpy.array_equal(f2, it.rhs(state))
+    # scipy export == reference CrsMatrix
+    csr = jac.tocsr()
+    assert numpy.array_equal(csr.indptr, g['begA']) and numpy.array_equal(csr.indices, g['jcoA'])
+    assert numpy.array_equal(csr.data, g['coA'])
+    M = it.mass_matrix().tocsr()
+    assert numpy.array_equal(M.indptr, g['mbegA']) and numpy.array_equal(M.indices, g['mjcoA'])
+    assert numpy.array_equal(M.data, g['mcoA'])
+
+
+REF_FILES = [
+    ('ldc', {'Reynolds Number': 100}, 3, 4, 4),
+    ('ldc_stretched', {'Reynolds Number': 100, 'Grid Stretching': True}, 3, 4, 4),
+    ('bous', {'Reynolds Number': 1, 'Rayleigh Number': 100, 'Prandtl Number': 100,
+              'Problem Type': 'Rayleigh-Benard'}, 3, 5, 4),
+    ('bous_stretched', {'Reynolds Number': 1, 'Rayleigh Number': 100, 'Prandtl Number': 100,
+                        'Problem Type': 'Rayleigh-Benard', 'Grid Stretching': True}, 3, 5, 4),
+    ('dhc', {'Reynolds Number': 1, 'Rayleigh Number': 100, 'Prandtl Number': 100,
+             'Problem Type': 'Differentially Heated Cavity'}, 3, 5, 4),
+    ('amoc', {'Reynolds Number': 16, 'Rayleigh Number': 4e4, 'Prandtl Number': 2.25, 'Lewis Number': 1,
+              'Temperature Forcing': 1, 'Freshwater Flux': 1, 'Problem Type': 'AMOC'}, 2, 5, 1),
+]
+
+
+@pytest.mark.parametrize('stem,params,dim,dof,nz', REF_FILES, ids=[r[0] for r in REF_FILES])
+def test_gpu_matches_reference_golden_files(stem, params, dim, dof, nz):
+    '''The reference's own fixtures (tests/test_fvm.py:843-1257), state[i] = i+1 on 4x4x{4,1}.'''
+    nx = ny = 4
+    it = _iface(params, nx, ny, nz, dim, dof)
+    state = make_state('lin', it.n)
+    want = read_ref_matrix('%s_%dx%dx%d.txt' % (stem, nx, ny, nz), it.n)
+    row_ptr, col = it.pattern()
+    assert_csr_equal(compress(it.jacobian(state).values(), col, row_ptr), want, 1e-12, stem)
+    want_rhs = read_ref_vector('%s_rhs_%dx%dx%d.txt' % (stem, nx, ny, nz))
+    f = it.rhs(state)
+    assert numpy.all(numpy.abs(f - want_rhs) <= 1e-12 * numpy.maximum(numpy.abs(want_rhs), numpy.abs(f).max() * 1e-3))
+
+
+BIG = [
+    ('ldc3d_32', {'Reynolds Number': 100}, 32, 32, 32),
+    ('ldc3d_ragged', {'Reynolds Number': 100, 'Grid Stretching Factor': 1.5}, 37, 13, 9),
+    ('ldc3d_wide', {'Reynolds Number': 100}, 70, 5, 6),
+    ('rb3d_20', {'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 2000.0, 'Prandtl Number': 10.0,
+                 'Biot Number': 1.0, 'X-max': 10, 'Y-max': 10}, 20, 21, 22),
+    ('dhc2d_64', {'Problem Type': 'Differentially Heated Cavity', 'Rayleigh Number': 1e4, 'Prandtl Number': 1000.0,
+                  'Reynolds Number': 1, 'X-max': 0.051, 'Y-max': 1}, 64, 64, 1),
+    ('ldc2d_32', {'Reynolds Number': 100, 'Grid Stretching Factor': 1.5}, 32, 32, 1),
+    ('qg_256', {'Problem Type': 'Double Gyre', 'Reynolds Number': 16, 'Rossby Parameter': 1000,
+                'Wind Stress Parameter': 1000}, 256, 128, 1),
+    ('amoc_256', {'Problem Type': 'AMOC', 'Rayleigh Number': 4e4, 'Prandtl Number': 2.25, 'Lewis Number': 1,
+                  'Freshwater Flux': 0.1, 'Temperature Forcing': 1, 'X-max': 5}, 256, 128, 1),
+]
+
+
+@pytest.mark.parametrize('name,params,nx,ny,nz', BIG, ids=[b[0] for b in BIG])
+def test_gpu_matches_oracle_at_scale(name, params, nx, ny, nz):
+    '''BASELINE config sizes (2D) and mid-size 3D grids, ragged tiles included, vs the C oracle.'''
+    from oracle.tf_oracle import Oracle
+    orc = Oracle(dict(params), nx, ny, nz)
+    it = _iface(params, nx, ny, nz, None, None)
+    assert numpy.array_equal(it.x, orc.x) and numpy.array_equal(it.y, orc.y) and numpy.array_equal(it.z, orc.z)
+    state = make_state(123, it.n)
+    row_ptr, col = it.pattern()
+    jac, f = it.jacobian_rhs(state)
+    assert_csr_equal(compress(jac.values(), col, row_ptr), orc.jacobian(state), 0.0, name)
+    exact = params.get('Problem Type') not in ('Double Gyre', 'AMOC')
+    _rhs_close(f, orc.rhs(state), exact)
+    # structural nnz formulas fitted on the reference
+    if name.startswith('ldc3d_32'):
+        N = 32
+        assert it.nnz == 57 * N**3 - 96 * N**2 + 36 * N
+
+
+def test_parameters_are_reread_on_every_call():
+    '''The parameter dict is shared and mutable (BaseInterface.py:65): continuation changes it
+    between calls.'''
+    from oracle.tf_oracle import Oracle
+    params = {'Reynolds Number': 10, 'Lid Velocity': 1}
+    it = _iface(params, 6, 6, 6, None, None)
+    it.parameters = params   # same dict object the caller mutates
+    state = make_state(5, it.n)
+    for Re, lid in ((10, 1), (200, 1), (200, 3.5), (0, 1)):
+        params['Reynolds Number'] = Re
+        it.set_parameter('Lid Velocity', lid)
+        orc = Oracle(dict(params), 6, 6, 6)
+        assert numpy.array_equal(it.rhs(state), orc.rhs(state))
+        row_ptr, col = it.pattern()
+        assert_csr_equal(compress(it.jacobian(state).values(), col, row_ptr), orc.jacobian(state), 0.0, 'Re=%s' % Re)
+
+
+def test_matvec_matches_scipy():
+    it = _iface({'Reynolds Number': 100}, 8, 7, 6, None, None)
+    state = make_state(1, it.n)
+    jac = it.jacobian(state)
+    v = make_state(2, it.n)
+    want = jac.tocsr() @ v
+    got = jac @ v
+    assert numpy.allclose(got, want, rtol=1e-13, atol=1e-13 * numpy.abs(want).max())
+
+
+def test_unsupported_configurations_fail_loudly():
+    from transiflow_b200 import Interface
+    with pytest.raises(NotImplementedError):
+        Interface({'Problem Type': 'Double Gyre'}, 4, 4, 1, 2, 4)      # QG with an extra scalar
+    with pytest.raises(NotImplementedError):
+        Interface({}, 4, 4, 4, boundary_conditions=lambda bc, atom: None)
+    with pytest.raises(Exception):
+        Interface({'Problem Type': 'nonsense'}, 4, 4, 4)

@@ -1,0 +1,98 @@
+'''ctypes binding of libtfb200.so (the C ABI declared in include/tfb200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or no device is
+visible, constructing an Interface raises.'''
+import ctypes
+import os
+
+import numpy
+
+from .hostprep import TFB_MAX_FORCE, TfbParams
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, 'lib', 'libtfb200.so')
+_LIB = None
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class TfbDesc(ctypes.Structure):
+    _fields_ = [
+        ('config', ctypes.c_int32), ('nx', ctypes.c_int32), ('ny', ctypes.c_int32), ('nz', ctypes.c_int32),
+        ('dim', ctypes.c_int32), ('dof', ctypes.c_int32), ('device', ctypes.c_int32),
+        ('k0', ctypes.c_int32), ('k1', ctypes.c_int32),
+        ('met', ctypes.c_void_p * 3), ('cor', ctypes.c_void_p),
+    ]
+
+
+class TfbSolveOpts(ctypes.Structure):
+    _fields_ = [
+        ('tol', ctypes.c_double), ('maxit', ctypes.c_int32), ('restart', ctypes.c_int32),
+        ('pressure_row', ctypes.c_int32), ('precond', ctypes.c_int32), ('verbose', ctypes.c_int32),
+        ('reserved', ctypes.c_int32 * 3),
+    ]
+
+
+class TfbSolveInfo(ctypes.Structure):
+    _fields_ = [
+        ('iters', ctypes.c_int32), ('converged', ctypes.c_int32), ('relres', ctypes.c_double),
+        ('setup_ms', ctypes.c_float), ('solve_ms', ctypes.c_float),
+    ]
+
+
+EXPORTS = [
+    'tfb_device_count', 'tfb_last_error', 'tfb_config_name', 'tfb_create', 'tfb_destroy', 'tfb_set_params',
+    'tfb_sizes', 'tfb_get_pattern', 'tfb_mat_create', 'tfb_mat_destroy', 'tfb_mat_get_values',
+    'tfb_mat_set_values', 'tfb_rhs', 'tfb_jacobian', 'tfb_mass_diag', 'tfb_state_upload',
+    'tfb_assemble_resident', 'tfb_rhs_download', 'tfb_sync', 'tfb_event_record', 'tfb_event_elapsed_ms',
+    'tfb_flush_l2', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_solve', 'tfb_nccl_unique_id', 'tfb_comm_init',
+]
+
+
+def lib():
+    '''Load libtfb200.so (built in-tree by ``python -m transiflow_b200.build``).'''
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO):
+            raise RuntimeError('libtfb200.so is missing: run `python -m transiflow_b200.build` '
+                               '(there is no CPU fallback for the B200 backend)')
+        L = ctypes.CDLL(SO)
+        L.tfb_last_error.restype = ctypes.c_char_p
+        L.tfb_config_name.restype = ctypes.c_char_p
+        L.tfb_launch_count.restype = ctypes.c_int64
+        for name in EXPORTS:
+            if name not in ('tfb_last_error', 'tfb_config_name', 'tfb_launch_count', 'tfb_destroy', 'tfb_mat_destroy'):
+                getattr(L, name).restype = ctypes.c_int
+        L.tfb_destroy.restype = None
+        L.tfb_mat_destroy.restype = None
+        L.tfb_destroy.argtypes = [ctypes.c_void_p]
+        L.tfb_mat_destroy.argtypes = [ctypes.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def device_count():
+    return lib().tfb_device_count()
+
+
+def check(rc):
+    if rc < 0:
+        raise RuntimeError('libtfb200: ' + lib().tfb_last_error().decode())
+    return rc
+
+
+def ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(None)
+
+
+def as_f64(a):
+    return numpy.ascontiguousarray(a, dtype=numpy.float64)
+
+
+def pinned_array(n):
+    """fp64 numpy array of length n backed by page-locked host memory."""
+    p = ctypes.c_void_p()
+    check(lib().tfb_pinned_alloc(ctypes.c_size_t(8 * n), ctypes.byref(p)))
+    buf = (ctypes.c_double * n).from_address(p.value)
+    arr = numpy.frombuffer(buf, dtype=numpy.float64)
+    return arr

@@ -499,7 +499,7 @@ class RowEmitter:
         w = out.append
         name = '%s_row%d' % (cfg.name, d1)
         w('template <bool DO_J, bool DO_F, class Cell, class State>')
-        w('TFB_HD inline void %s(const TfbParams& prm, const Cell& c, const State& P, double* __restrict__ Jout, double& rhs_out) {' % name)
+        w('TFB_HD void %s(const TfbParams& prm, const Cell& c, const State& P, double* __restrict__ Jout, double& rhs_out) {' % name)
         # make sure every state value the RHS product needs is loaded
         for k in self.fkeys:
             row.P(k[0], (k[1] - 1, k[2] - 1, k[3] - 1))
@@ -580,7 +580,7 @@ class RowEmitter:
         w('')
         # mask function
         w('template <class Cell>')
-        w('TFB_HD inline unsigned %s_mask%d(const Cell& c) {' % (cfg.name, d1))
+        w('TFB_HD unsigned %s_mask%d(const Cell& c) {' % (cfg.name, d1))
         for ln in self.mask_lines():
             w('    ' + ln)
         w('    return m;')
@@ -605,8 +605,9 @@ def emit_config(cfg):
     w('struct Cfg_%s {' % cfg.name)
     w('    static constexpr int ID = %d, DIM = %d, DOF = %d, FLAT = %d, FOLD = %d, MAXSLOT = %d, NFORCE = %d;' % (
         cfg.cid, cfg.dim, cfg.dof, int(cfg.flat), int(cfg.fold), maxs, cfg.nforce))
+    w('    static constexpr int CELL_SLOTS = %d;' % sum(len(em.cols) for em in ems))
     w('    static constexpr const char* NAME = "%s";' % cfg.name)
-    w('    TFB_HD static int nslot(int d1) {')
+    w('    TFB_HD static constexpr int nslot(int d1) {')
     w('        switch (d1) { %s default: return 0; }' % ' '.join('case %d: return %d;' % (d, len(em.cols)) for d, em in enumerate(ems)))
     w('    }')
     # slot table: for each row and output column: d2, dx, dy, dz (dz = 0 for folded columns)

@@ -37,10 +37,10 @@ struct TfbCell {
     C.rhm##ax = g.met[A][4 * (n) + (idx)]; C.rhu##ax = g.met[A][5 * (n) + (idx)];  \
     C.wm##ax = g.met[A][6 * (n) + (idx)]; C.wp##ax = g.met[A][7 * (n) + (idx)];
 
-TFB_HD inline int tfb_far2_index(int m) { return m >= 2 ? m - 2 : 2 * m - 2; }  // Python index m-2 with wrap
+TFB_HD int tfb_far2_index(int m) { return m >= 2 ? m - 2 : 2 * m - 2; }  // Python index m-2 with wrap
 
 template <int NFORCE>
-TFB_HD inline void tfb_make_cell(const TfbGrid& g, int i, int j, int k, TfbCell& c) {
+TFB_HD void tfb_make_cell(const TfbGrid& g, int i, int j, int k, TfbCell& c) {
     { constexpr int A = 0; TFB_LOADMET(x, g.nx, i, c) }
     { constexpr int A = 1; TFB_LOADMET(y, g.ny, j, c) }
     { constexpr int A = 2; TFB_LOADMET(z, g.nz, k, c) }
@@ -67,7 +67,7 @@ TFB_HD inline void tfb_make_cell(const TfbGrid& g, int i, int j, int k, TfbCell&
 // non-periodic x/y directions and the (periodic iff nz == 1) z direction: zero outside the
 // domain, wall-normal velocity on the far walls forced to zero, z-fold onto the single plane.
 // `kofs` maps a global k to the plane index of `state` (slab-local storage has ghost planes).
-TFB_HD inline double tfb_padded_load(const TfbGrid& g, const double* __restrict__ state, int kofs,
+TFB_HD double tfb_padded_load(const TfbGrid& g, const double* __restrict__ state, int kofs,
                                      int ii, int jj, int kk, int d) {
     if (g.zfold) kk = 0;
     else if (kk < 0 || kk >= g.nz) return 0.0;
@@ -77,7 +77,7 @@ TFB_HD inline double tfb_padded_load(const TfbGrid& g, const double* __restrict_
 }
 
 // Global column of slot (d2, dx, dy, dz) of cell (i,j,k), Discretization.py:516-518.
-TFB_HD inline long long tfb_column(const TfbGrid& g, int i, int j, int k, int d2, int dx, int dy, int dz) {
+TFB_HD long long tfb_column(const TfbGrid& g, int i, int j, int k, int d2, int dx, int dy, int dz) {
     int a = (i + dx + g.nx) % g.nx, b = (j + dy + g.ny) % g.ny, cc = (k + dz + g.nz) % g.nz;
     return (((long long)cc * g.ny + b) * g.nx + a) * g.dof + d2;
 }

@@ -1,0 +1,99 @@
+// NCCL plumbing for z-slab partitioned runs (one process per GPU).  libnccl is loaded with
+// dlopen so that single-GPU use has no NCCL dependency at all.
+#include <dlfcn.h>
+#include <string.h>
+#include "tfb_internal.h"
+
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void* ncclComm_t_;
+enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+static struct {
+    void* handle;
+    int (*GetUniqueId)(ncclUniqueId_t*);
+    int (*CommInitRank)(ncclComm_t_*, int, ncclUniqueId_t, int);
+    int (*CommDestroy)(ncclComm_t_);
+    int (*Send)(const void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
+    const char* (*GetErrorString)(int);
+} nccl;
+
+static int load_nccl() {
+    if (nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (nccl.handle) break;
+    }
+    if (!nccl.handle) return tfb_fail(__FILE__, __LINE__, "dlopen(libnccl.so.2)", dlerror());
+#define SYM(f) *(void**)(&nccl.f) = dlsym(nccl.handle, "nccl" #f); if (!nccl.f) return tfb_fail(__FILE__, __LINE__, "dlsym", "nccl" #f);
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    return 0;
+}
+
+#define TFB_NCCL(call)                                                                     \
+    do {                                                                                   \
+        int r_ = (call);                                                                   \
+        if (r_ != 0) return tfb_fail(__FILE__, __LINE__, #call, nccl.GetErrorString(r_));  \
+    } while (0)
+
+extern "C" int tfb_nccl_unique_id(uint8_t id[128]) {
+    if (load_nccl()) return -1;
+    ncclUniqueId_t u;
+    TFB_NCCL(nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+extern "C" int tfb_comm_init(tfb_ctx* c, int nranks, int rank, const uint8_t id[128]) {
+    TFB_CHECK(c && nranks >= 1 && rank >= 0 && rank < nranks, "bad arguments");
+    c->nranks = nranks;
+    c->rank = rank;
+    if (nranks == 1) return 0;
+    if (load_nccl()) return -1;
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    ncclUniqueId_t u;
+    memcpy(u.internal, id, 128);
+    ncclComm_t_ comm;
+    TFB_NCCL(nccl.CommInitRank(&comm, nranks, u, rank));
+    c->nccl_comm = comm;
+    return 0;
+}
+
+// One-layer halo exchange of a slab vector stored with ghost planes:
+// [ghost below | owned planes | ghost above], plane = nx*ny*dof doubles.
+// Rank r owns planes directly above rank r-1 (z-slab order = rank order).
+int tfb_halo_exchange(tfb_ctx* c, double* v) {
+    if (c->nranks <= 1) return 0;
+    TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    const size_t pl = (size_t)c->plane_rows;
+    double* first_owned = v + pl;
+    double* last_owned = v + pl * c->nzl;
+    double* ghost_lo = v;
+    double* ghost_hi = v + pl * (c->nzl + 1);
+    TFB_NCCL(nccl.GroupStart());
+    if (c->rank > 0) {
+        TFB_NCCL(nccl.Send(first_owned, pl, NCCL_FLOAT64, c->rank - 1, comm, c->stream));
+        TFB_NCCL(nccl.Recv(ghost_lo, pl, NCCL_FLOAT64, c->rank - 1, comm, c->stream));
+    }
+    if (c->rank < c->nranks - 1) {
+        TFB_NCCL(nccl.Send(last_owned, pl, NCCL_FLOAT64, c->rank + 1, comm, c->stream));
+        TFB_NCCL(nccl.Recv(ghost_hi, pl, NCCL_FLOAT64, c->rank + 1, comm, c->stream));
+    }
+    TFB_NCCL(nccl.GroupEnd());
+    TFB_LAUNCHED();
+    return 0;
+}
+
+int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count) {
+    if (c->nranks <= 1) return 0;
+    TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    TFB_NCCL(nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t_)c->nccl_comm, c->stream));
+    TFB_LAUNCHED();
+    return 0;
+}

@@ -1,0 +1,383 @@
+// libtfb200 core: context management, fixed-pattern construction, assembly launches.
+#include <cub/device/device_scan.cuh>
+#include <string.h>
+#include "tfb_assemble.cuh"
+
+thread_local std::string g_tfb_err;
+int64_t g_tfb_launches = 0;
+
+int tfb_fail(const char* file, int line, const char* what, const char* detail) {
+    char buf[1024];
+    snprintf(buf, sizeof buf, "%s:%d: %s: %s", file, line, what, detail ? detail : "");
+    g_tfb_err = buf;
+    return -1;
+}
+
+extern "C" const char* tfb_last_error(void) { return g_tfb_err.c_str(); }
+extern "C" int64_t tfb_launch_count(void) { return g_tfb_launches; }
+
+extern "C" int tfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* tfb_config_name(int config) {
+#define X(C) if (config == C::ID) return C::NAME;
+    TFB_FOR_EACH_CONFIG(X)
+#undef X
+    return nullptr;
+}
+
+TfbGrid tfb_ctx::grid() const {
+    TfbGrid g;
+    g.nx = desc.nx; g.ny = desc.ny; g.nz = desc.nz; g.dim = desc.dim; g.dof = desc.dof;
+    g.zfold = desc.nz == 1;
+    for (int a = 0; a < 3; a++) g.met[a] = d_met[a];
+    g.cor = d_cor;
+    for (int f = 0; f < TFB_MAX_FORCE; f++) { g.fval[f] = d_fval[f]; g.fdir[f] = fdir[f]; }
+    return g;
+}
+
+static int config_dof(int config) {
+#define X(C) if (config == C::ID) return C::DOF;
+    TFB_FOR_EACH_CONFIG(X)
+#undef X
+    return -1;
+}
+
+extern "C" int tfb_create(const tfb_desc* d, tfb_ctx** out) {
+    TFB_CHECK(d && out, "null argument");
+    TFB_CHECK(tfb_config_name(d->config) != nullptr, "unknown kernel config");
+    TFB_CHECK(config_dof(d->config) == d->dof, "dof does not match the kernel config");
+    TFB_CHECK(d->nx >= 2 && d->ny >= 2 && d->nz >= 1, "grid must be at least 2x2x1");
+    TFB_CHECK(d->k0 >= 0 && d->k1 <= d->nz && d->k0 < d->k1, "bad z-slab");
+    TFB_CHECK((int64_t)d->nx * d->ny * d->nz * d->dof < (int64_t)INT32_MAX, "more than 2^31 unknowns");
+    TFB_CUDA(cudaSetDevice(d->device));
+    tfb_ctx* c = new tfb_ctx();
+    c->desc = *d;
+    c->nzl = d->k1 - d->k0;
+    c->plane_rows = (int64_t)d->nx * d->ny * d->dof;
+    c->n_local = c->plane_rows * c->nzl;
+    c->n_global = c->plane_rows * d->nz;
+    c->row0 = c->plane_rows * d->k0;
+    TFB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const int n[3] = {d->nx, d->ny, d->nz};
+    for (int a = 0; a < 3; a++) {
+        TFB_CUDA(cudaMalloc(&c->d_met[a], sizeof(double) * TFB_NMET * n[a]));
+        TFB_CUDA(cudaMemcpy(c->d_met[a], d->met[a], sizeof(double) * TFB_NMET * n[a], cudaMemcpyHostToDevice));
+    }
+    TFB_CUDA(cudaMalloc(&c->d_cor, sizeof(double) * 2 * d->ny));
+    TFB_CUDA(cudaMemcpy(c->d_cor, d->cor, sizeof(double) * 2 * d->ny, cudaMemcpyHostToDevice));
+    TFB_CUDA(cudaMalloc(&c->d_state, sizeof(double) * c->plane_rows * (c->nzl + 2)));
+    TFB_CUDA(cudaMemset(c->d_state, 0, sizeof(double) * c->plane_rows * (c->nzl + 2)));
+    TFB_CUDA(cudaMalloc(&c->d_rhs, sizeof(double) * c->n_local));
+    TFB_CUDA(cudaMalloc(&c->d_frc_static, sizeof(double) * c->n_local));
+    for (int e = 0; e < 16; e++) TFB_CUDA(cudaEventCreate(&c->ev[e]));
+    memset(&c->prm, 0, sizeof c->prm);
+    c->desc.met[0] = c->desc.met[1] = c->desc.met[2] = nullptr;
+    c->desc.cor = nullptr;
+    *out = c;
+    int rc = tfb_build_pattern(c);
+    if (rc != 0) { tfb_destroy(c); *out = nullptr; return rc; }
+    return 0;
+}
+
+extern "C" void tfb_destroy(tfb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->desc.device);
+    for (int a = 0; a < 3; a++) cudaFree(c->d_met[a]);
+    cudaFree(c->d_cor);
+    for (int f = 0; f < TFB_MAX_FORCE; f++) cudaFree(c->d_fval[f]);
+    cudaFree(c->d_frc_static);
+    cudaFree(c->d_state);
+    cudaFree(c->d_rhs);
+    cudaFree(c->d_row_ptr);
+    cudaFree(c->d_col);
+    cudaFree(c->d_flush);
+    for (int e = 0; e < 16; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int tfb_set_params(tfb_ctx* c, const tfb_params* prm, const double* const* fval,
+                              const int8_t* fdir, const double* frc_static) {
+    TFB_CHECK(c && prm, "null argument");
+    static_assert(sizeof(tfb_params) == sizeof(TfbParams), "ABI struct mismatch");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    memcpy(&c->prm, prm, sizeof(TfbParams));
+    c->have_params = true;
+    for (int f = 0; f < TFB_MAX_FORCE; f++) {
+        c->fdir[f] = fdir ? fdir[f] : 0;
+        const double* src = fval ? fval[f] : nullptr;
+        if (src) {
+            int a = c->fdir[f];
+            // in-plane extent of the face, restricted to the owned planes where z is in-plane
+            size_t n1 = a == 0 ? c->desc.ny : c->desc.nx;
+            size_t n2 = a == 2 ? c->desc.ny : c->desc.nz;
+            if (!c->d_fval[f]) TFB_CUDA(cudaMalloc(&c->d_fval[f], sizeof(double) * n1 * n2));
+            TFB_CUDA(cudaMemcpyAsync(c->d_fval[f], src, sizeof(double) * n1 * n2, cudaMemcpyHostToDevice, c->stream));
+        } else if (c->d_fval[f]) {
+            cudaFree(c->d_fval[f]);
+            c->d_fval[f] = nullptr;
+        }
+    }
+    c->has_frc_static = frc_static != nullptr;
+    if (frc_static)
+        TFB_CUDA(cudaMemcpyAsync(c->d_frc_static, frc_static, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int tfb_sizes(tfb_ctx* c, int64_t* n_local, int64_t* nnz_local, int64_t* n_global, int64_t* row0) {
+    TFB_CHECK(c, "null ctx");
+    if (n_local) *n_local = c->n_local;
+    if (nnz_local) *nnz_local = c->nnz;
+    if (n_global) *n_global = c->n_global;
+    if (row0) *row0 = c->row0;
+    return 0;
+}
+
+template <class Cfg>
+static int build_pattern_t(tfb_ctx* c) {
+    const long long nrows = c->n_local;
+    TfbGrid g = c->grid();
+    int* d_counts = nullptr;
+    TFB_CUDA(cudaMalloc(&d_counts, sizeof(int) * (nrows + 1)));
+    TFB_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * (nrows + 1), c->stream));
+    const int bs = 256;
+    const unsigned nb = (unsigned)((nrows + bs - 1) / bs);
+    tfb_count_kernel<Cfg><<<nb, bs, 0, c->stream>>>(g, c->desc.k0, nrows, d_counts);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    TFB_CUDA(cudaMalloc(&c->d_row_ptr, sizeof(int) * (nrows + 1)));
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    TFB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, c->d_row_ptr, nrows + 1, c->stream));
+    TFB_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    TFB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_counts, c->d_row_ptr, nrows + 1, c->stream));
+    TFB_LAUNCHED();
+    int nnz = 0;
+    TFB_CUDA(cudaMemcpyAsync(&nnz, c->d_row_ptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+    cudaFree(d_counts);
+    TFB_CHECK(nnz > 0, "empty pattern");
+    c->nnz = nnz;
+    TFB_CUDA(cudaMalloc(&c->d_col, sizeof(int) * (size_t)nnz));
+    tfb_fill_cols_kernel<Cfg><<<nb, bs, 0, c->stream>>>(g, c->desc.k0, nrows, c->d_row_ptr, c->d_col);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_pattern = true;
+    return 0;
+}
+
+int tfb_build_pattern(tfb_ctx* c) {
+    // nnz per slab can be counted in 64 bits on the host side later; the device pattern uses int32.
+#define X(C) if (c->desc.config == C::ID) return build_pattern_t<C>(c);
+    TFB_FOR_EACH_CONFIG(X)
+#undef X
+    return tfb_fail(__FILE__, __LINE__, "tfb_build_pattern", "unknown config");
+}
+
+extern "C" int tfb_get_pattern(tfb_ctx* c, int64_t* row_ptr, int64_t* col_idx) {
+    TFB_CHECK(c && c->have_pattern, "no pattern");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    std::vector<int> tmp((size_t)std::max<int64_t>(c->n_local + 1, c->nnz));
+    if (row_ptr) {
+        TFB_CUDA(cudaMemcpy(tmp.data(), c->d_row_ptr, sizeof(int) * (c->n_local + 1), cudaMemcpyDeviceToHost));
+        for (int64_t r = 0; r <= c->n_local; r++) row_ptr[r] = tmp[r];
+    }
+    if (col_idx) {
+        TFB_CUDA(cudaMemcpy(tmp.data(), c->d_col, sizeof(int) * c->nnz, cudaMemcpyDeviceToHost));
+        for (int64_t e = 0; e < c->nnz; e++) col_idx[e] = tmp[e];
+    }
+    return 0;
+}
+
+extern "C" int tfb_mat_create(tfb_ctx* c, tfb_mat** out) {
+    TFB_CHECK(c && out && c->have_pattern, "no pattern");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    tfb_mat* m = new tfb_mat();
+    m->ctx = c;
+    TFB_CUDA(cudaMalloc(&m->d_vals, sizeof(double) * (size_t)c->nnz));
+    TFB_CUDA(cudaMemset(m->d_vals, 0, sizeof(double) * (size_t)c->nnz));
+    *out = m;
+    return 0;
+}
+
+extern "C" void tfb_mat_destroy(tfb_mat* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->desc.device);
+    tfb_solver_free(m->solver);
+    cudaFree(m->d_vals);
+    delete m;
+}
+
+extern "C" int tfb_mat_get_values(tfb_mat* m, double* out) {
+    TFB_CHECK(m && out, "null argument");
+    TFB_CUDA(cudaSetDevice(m->ctx->desc.device));
+    TFB_CUDA(cudaMemcpyAsync(out, m->d_vals, sizeof(double) * (size_t)m->ctx->nnz, cudaMemcpyDeviceToHost, m->ctx->stream));
+    TFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return 0;
+}
+
+extern "C" int tfb_mat_set_values(tfb_mat* m, const double* in) {
+    TFB_CHECK(m && in, "null argument");
+    TFB_CUDA(cudaSetDevice(m->ctx->desc.device));
+    TFB_CUDA(cudaMemcpyAsync(m->d_vals, in, sizeof(double) * (size_t)m->ctx->nnz, cudaMemcpyHostToDevice, m->ctx->stream));
+    TFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    m->version++;
+    return 0;
+}
+
+// ------------------------------- assembly launches -------------------------------
+template <class Cfg, bool DO_J, bool DO_F>
+static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
+    constexpr int TJ = Cfg::DOF >= 5 ? 3 : 4;
+    TfbAsmArgs a;
+    a.g = c->grid();
+    a.prm = c->prm;
+    a.state = c->d_state;
+    a.frc_static = c->has_frc_static ? c->d_frc_static : nullptr;
+    a.row_ptr = c->d_row_ptr;
+    a.vals = m ? m->d_vals : nullptr;
+    a.rhs = c->d_rhs;
+    a.k0 = c->desc.k0;
+    a.nzl = c->nzl;
+    constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
+    size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
+    auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ>;
+    static bool configured = false;
+    if (!configured) {
+        TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 block(32, Cfg::DOF, TJ);
+    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, c->nzl);
+    kern<<<grid, block, smem, c->stream>>>(a);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <class Cfg>
+static int launch_assemble(tfb_ctx* c, tfb_mat* m, bool do_j, bool do_f) {
+    if (do_j && do_f) return launch_assemble_t<Cfg, true, true>(c, m);
+    if (do_j) return launch_assemble_t<Cfg, true, false>(c, m);
+    return launch_assemble_t<Cfg, false, true>(c, m);
+}
+
+extern "C" int tfb_state_upload(tfb_ctx* c, const double* state) {
+    TFB_CHECK(c && state, "null argument");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    TFB_CUDA(cudaMemcpyAsync(c->d_state + c->plane_rows, state, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f) {
+    TFB_CHECK(c && c->have_params, "tfb_set_params has not been called");
+    TFB_CHECK(do_j || do_f, "nothing to do");
+    TFB_CHECK(!do_j || (m && m->ctx == c), "matrix does not belong to this context");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    if (c->nranks > 1) {
+        int rc = tfb_halo_exchange(c, c->d_state);
+        if (rc) return rc;
+    }
+    if (do_j) m->version++;
+#define X(C) if (c->desc.config == C::ID) return launch_assemble<C>(c, m, do_j != 0, do_f != 0);
+    TFB_FOR_EACH_CONFIG(X)
+#undef X
+    return tfb_fail(__FILE__, __LINE__, "tfb_assemble_resident", "unknown config");
+}
+
+extern "C" int tfb_rhs_download(tfb_ctx* c, double* out) {
+    TFB_CHECK(c && out, "null argument");
+    TFB_CUDA(cudaMemcpyAsync(out, c->d_rhs, sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int tfb_sync(tfb_ctx* c) {
+    TFB_CHECK(c, "null ctx");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int tfb_rhs(tfb_ctx* c, const double* state, double* out) {
+    int rc = tfb_state_upload(c, state);
+    if (rc) return rc;
+    rc = tfb_assemble_resident(c, nullptr, 0, 1);
+    if (rc) return rc;
+    return tfb_rhs_download(c, out);
+}
+
+extern "C" int tfb_jacobian(tfb_ctx* c, const double* state, tfb_mat* m, double* rhs_out) {
+    int rc = tfb_state_upload(c, state);
+    if (rc) return rc;
+    rc = tfb_assemble_resident(c, m, 1, rhs_out != nullptr);
+    if (rc) return rc;
+    if (rhs_out) return tfb_rhs_download(c, rhs_out);
+    return tfb_sync(c);
+}
+
+extern "C" int tfb_mass_diag(tfb_ctx* c, double* diag_out) {
+    TFB_CHECK(c && diag_out, "null argument");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    double* d = nullptr;
+    TFB_CUDA(cudaMalloc(&d, sizeof(double) * c->n_local));
+    const int bs = 256;
+    tfb_mass_kernel<<<(unsigned)((c->n_local + bs - 1) / bs), bs, 0, c->stream>>>(c->grid(), c->desc.k0, c->n_local, d);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    TFB_CUDA(cudaMemcpyAsync(diag_out, d, sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return 0;
+}
+
+// ------------------------------- timing helpers -------------------------------
+extern "C" int tfb_event_record(tfb_ctx* c, int slot) {
+    TFB_CHECK(c && slot >= 0 && slot < 16, "bad slot");
+    TFB_CUDA(cudaEventRecord(c->ev[slot], c->stream));
+    return 0;
+}
+
+extern "C" int tfb_event_elapsed_ms(tfb_ctx* c, int a, int b, float* ms) {
+    TFB_CHECK(c && ms && a >= 0 && a < 16 && b >= 0 && b < 16, "bad slot");
+    TFB_CUDA(cudaEventSynchronize(c->ev[b]));
+    TFB_CUDA(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
+    return 0;
+}
+
+__global__ void tfb_flush_kernel(double4* p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_double4(1.0, 2.0, 3.0, 4.0);
+}
+
+extern "C" int tfb_flush_l2(tfb_ctx* c) {
+    TFB_CHECK(c, "null ctx");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    if (!c->d_flush) {
+        c->flush_bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+        TFB_CUDA(cudaMalloc(&c->d_flush, c->flush_bytes));
+    }
+    tfb_flush_kernel<<<148 * 8, 256, 0, c->stream>>>((double4*)c->d_flush, c->flush_bytes / sizeof(double4));
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int tfb_pinned_alloc(size_t bytes, void** out) {
+    TFB_CHECK(out, "null argument");
+    TFB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return 0;
+}
+
+extern "C" int tfb_pinned_free(void* p) {
+    if (p) TFB_CUDA(cudaFreeHost(p));
+    return 0;
+}

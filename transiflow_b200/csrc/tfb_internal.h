@@ -1,0 +1,71 @@
+// Internal definitions of libtfb200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/tfb200.h"
+#include "tfb_cell.h"
+
+extern thread_local std::string g_tfb_err;
+extern int64_t g_tfb_launches;
+
+int tfb_fail(const char* file, int line, const char* what, const char* detail);
+
+#define TFB_CUDA(call)                                                                 \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) return tfb_fail(__FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define TFB_CHECK(cond, msg)                                                           \
+    do {                                                                               \
+        if (!(cond)) return tfb_fail(__FILE__, __LINE__, #cond, msg);                  \
+    } while (0)
+#define TFB_LAUNCHED() (g_tfb_launches++)
+
+struct tfb_solver_state;  // tfb_solver.cu
+
+struct tfb_ctx {
+    tfb_desc desc;
+    int nzl;                    // owned planes
+    int64_t plane_rows;         // nx*ny*dof
+    int64_t n_local, n_global, row0;
+    int64_t nnz = 0;
+    cudaStream_t stream = nullptr;
+    // geometry on the device
+    double* d_met[3] = {nullptr, nullptr, nullptr};
+    double* d_cor = nullptr;
+    double* d_fval[TFB_MAX_FORCE] = {};
+    int8_t fdir[TFB_MAX_FORCE] = {};
+    double* d_frc_static = nullptr;
+    bool has_frc_static = false;
+    TfbParams prm;
+    bool have_params = false;
+    // state with one ghost plane below and above: (nzl+2) planes
+    double* d_state = nullptr;
+    double* d_rhs = nullptr;
+    // fixed pattern
+    int* d_row_ptr = nullptr;   // n_local+1
+    int* d_col = nullptr;       // nnz, GLOBAL columns
+    bool have_pattern = false;
+    // scratch for L2 flush
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+    cudaEvent_t ev[16] = {};
+    // multi-GPU
+    int nranks = 1, rank = 0;
+    void* nccl_comm = nullptr;
+    TfbGrid grid() const;
+};
+
+struct tfb_mat {
+    tfb_ctx* ctx;
+    double* d_vals = nullptr;
+    tfb_solver_state* solver = nullptr;
+    uint64_t version = 0;       // bumped whenever values change (invalidates the preconditioner)
+};
+
+int tfb_build_pattern(tfb_ctx* ctx);
+int tfb_halo_exchange(tfb_ctx* ctx, double* d_vec_with_ghosts);
+void tfb_solver_free(tfb_solver_state* s);

@@ -7,7 +7,7 @@
 #if defined(__CUDACC__)
 #define TFB_HD __host__ __device__ __forceinline__
 #else
-#define TFB_HD
+#define TFB_HD inline
 #endif
 
 #define TFB_MAX_FORCE 8
@@ -30,4 +30,4 @@ struct TfbParams {
 
 // assemble_jacobian only emits |a| > 1e-14 (Discretization.py:515); needed where duplicate
 // columns are merged afterwards (z-fold of semi-2D grids).
-TFB_HD inline double tfb_keep(double a) { return fabs(a) > 1e-14 ? a : 0.0; }
+TFB_HD double tfb_keep(double a) { return fabs(a) > 1e-14 ? a : 0.0; }

@@ -1,0 +1,334 @@
+'''``transiflow.interface`` backend for NVIDIA B200 (sm_100a).
+
+``Interface`` keeps the API surface of the reference's backends (``vector, rhs, jacobian,
+mass_matrix, solve, eigs`` plus the inherited parameter / save / load helpers of
+``transiflow/interface/BaseInterface.py:30-215`` and the constructor signature of
+``transiflow/interface/SciPy.py:25-26``), so ``Continuation`` and ``TimeIntegration`` drive
+it unchanged, while assembly and the linear solve run as CUDA kernels behind the C ABI in
+``include/tfb200.h``.  The host side is numpy + ctypes only.
+
+Vectors are plain ``numpy.ndarray`` (like the SciPy backend, SciPy.py:37-38).  Matrices are
+``DeviceMatrix`` handles whose values live in HBM on a fixed structural sparsity pattern.
+'''
+import ctypes
+import json
+import os
+
+import numpy
+
+from . import _lib, hostprep, recipes
+from ._lib import as_f64, check, ptr
+
+
+class DeviceMatrix:
+    '''Jacobian on the device: CSR values on the Interface's fixed structural pattern.
+
+    Behaves like the ``scipy.sparse`` matrix the SciPy backend returns for what the callers
+    use (``J @ x``, ``shape``, ``dtype``; arithmetic such as ``J - M / s`` goes through a lazy
+    ``tocsc()`` copy).  ``tocsr()/tocsc()`` drop entries with ``|v| <= 1e-14`` exactly like
+    ``CrsMatrix.compress`` (CrsMatrix.py:52-71) so the result is identical to the reference's
+    value-dependent pattern.'''
+
+    def __init__(self, interface):
+        self.interface = interface
+        h = ctypes.c_void_p()
+        check(_lib.lib().tfb_mat_create(interface._ctx, ctypes.byref(h)))
+        self._h = h
+        self.shape = (interface.n, interface.n)
+        self.dtype = numpy.dtype(numpy.float64)
+        self._host = None
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h and _lib._LIB is not None:
+            _lib._LIB.tfb_mat_destroy(h)
+
+    def values(self):
+        '''CSR values of the full structural pattern (explicit zeros included), D2H copy.'''
+        out = numpy.empty(self.interface.nnz)
+        check(_lib.lib().tfb_mat_get_values(self._h, ptr(out)))
+        return out
+
+    def structural_csr(self):
+        from scipy import sparse
+        row_ptr, col = self.interface.pattern()
+        return sparse.csr_matrix((self.values(), col, row_ptr), self.shape)
+
+    def tocsr(self):
+        if self._host is None:
+            from scipy import sparse
+            row_ptr, col = self.interface.pattern()
+            vals = self.values()
+            keep = numpy.abs(vals) > 1e-14
+            counts = numpy.zeros(self.shape[0] + 1, dtype=numpy.int64)
+            numpy.add.at(counts, numpy.repeat(numpy.arange(self.shape[0]), numpy.diff(row_ptr))[keep] + 1, 1)
+            self._host = sparse.csr_matrix((vals[keep], col[keep], numpy.cumsum(counts)), self.shape)
+        return self._host
+
+    def tocsc(self):
+        return self.tocsr().tocsc()
+
+    def __matmul__(self, x):
+        x = as_f64(x)
+        if x.ndim != 1 or numpy.iscomplexobj(x):
+            return self.tocsr() @ x
+        y = numpy.empty_like(x)
+        check(_lib.lib().tfb_spmv(self._h, ptr(x), ptr(y)))
+        return y
+
+    def __mul__(self, other):
+        if numpy.isscalar(other):
+            return self.tocsc() * other
+        return self @ other
+
+    def __rmul__(self, other):
+        return self.tocsc() * other
+
+    def __neg__(self):
+        return -self.tocsc()
+
+    def __add__(self, other):
+        return self.tocsc() + _host_matrix(other)
+
+    def __radd__(self, other):
+        return _host_matrix(other) + self.tocsc()
+
+    def __sub__(self, other):
+        return self.tocsc() - _host_matrix(other)
+
+    def __rsub__(self, other):
+        return _host_matrix(other) - self.tocsc()
+
+    def __truediv__(self, other):
+        return self.tocsc() / other
+
+
+def _host_matrix(m):
+    return m.tocsc() if isinstance(m, DeviceMatrix) else m
+
+
+class Interface:
+    '''B200 backend.  Constructor arguments as ``transiflow.interface.SciPy.Interface``
+    (SciPy.py:25-26) plus ``device``.'''
+
+    def __init__(self, parameters, nx, ny, nz=1, dim=None, dof=None,
+                 x=None, y=None, z=None, boundary_conditions=None, device=0, slab=None):
+        if boundary_conditions is not None:
+            raise NotImplementedError('user-supplied boundary_conditions callbacks cannot run on the device')
+        self.parameters = parameters
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.dim = dim if dim is not None else (3 if nz > 1 else 2)       # Discretization.py:115-117
+        ptype = parameters.get('Problem Type', 'Lid-driven Cavity').lower()  # :550-557
+        if ptype not in recipes.PROBLEM_IDS:
+            raise Exception('Invalid problem type %s' % parameters.get('Problem Type'))  # :733
+        self.problem = recipes.PROBLEM_IDS[ptype]
+        if dof is None:                                                    # set_dof, :559-573
+            dof = self.dim + 1
+            if self.problem in (recipes.RB, recipes.RBP, recipes.DHC):
+                dof = self.dim + 2
+            elif self.problem == recipes.AMOC:
+                dof = self.dim + 3
+        self.dof = dof
+        self.config = recipes.find_config(self.problem, self.dim, nz, dof)
+        if self.config is None:
+            raise NotImplementedError('no B200 kernel family for problem=%r dim=%d nz=%d dof=%d'
+                                      % (ptype, self.dim, nz, dof))
+        p = parameters
+        cv = hostprep.coordinate_vector
+        self.x = cv(p, p.get('X-min', 0.0), p.get('X-max', 1.0), nx) if x is None else x
+        self.y = cv(p, p.get('Y-min', 0.0), p.get('Y-max', 1.0), ny) if y is None else y
+        self.z = cv(p, p.get('Z-min', 0.0), p.get('Z-max', 1.0), nz) if z is None else z
+        self.n = nx * ny * nz * dof
+        self.pressure_row = self.dim                                       # SciPy.py:30
+        self.border_scaling = 1e-3                                         # SciPy.py:33
+        self.device = device
+        self._subspaces = None
+
+        L = _lib.lib()
+        if L.tfb_device_count() <= 0:
+            raise RuntimeError('transiflow_b200 needs a CUDA device (no CPU fallback)')
+        self._mets = [hostprep.axis_metrics(v, m) for v, m in ((self.x, nx), (self.y, ny), (self.z, nz))]
+        self._cor = hostprep.coriolis_metrics(self.y, ny)
+        d = _lib.TfbDesc()
+        d.config, d.nx, d.ny, d.nz, d.dim, d.dof = self.config.cid, nx, ny, nz, self.dim, dof
+        self.slab = (0, nz) if slab is None else (int(slab[0]), int(slab[1]))
+        d.device, d.k0, d.k1 = device, self.slab[0], self.slab[1]
+        for a in range(3):
+            d.met[a] = self._mets[a].ctypes.data
+        d.cor = self._cor.ctypes.data
+        self._ctx = ctypes.c_void_p()
+        check(L.tfb_create(ctypes.byref(d), ctypes.byref(self._ctx)))
+        nnz, nloc, row0 = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(L.tfb_sizes(self._ctx, ctypes.byref(nloc), ctypes.byref(nnz), None, ctypes.byref(row0)))
+        self.nnz, self.n_local, self.row0 = nnz.value, nloc.value, row0.value
+        self._pattern = None
+        self._param_key = None
+        self.last_solve = None
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, '_ctx', None), None
+        if ctx and _lib._LIB is not None:
+            _lib._LIB.tfb_destroy(ctx)
+
+    # ---- parameters (BaseInterface.py:84-104; Discretization.py:145-184) ----
+    def _debug_print(self, *args):
+        if self.parameters.get('Verbose', False):
+            print('Debug:', *args, flush=True)
+
+    def set_parameter(self, name, value):
+        self.parameters[name] = value
+
+    def get_parameter(self, name, default=0):
+        return self.parameters.get(name, default) if name in self.parameters else default
+
+    def _sync_params(self):
+        '''Re-evaluate the kernel scalars whenever the shared, mutable parameter dict changed.'''
+        key = json.dumps(self.parameters, sort_keys=True, default=repr)
+        if key == self._param_key:
+            return
+        prm, arrays = hostprep.make_params(self.config, self.problem, self.parameters,
+                                           self.nx, self.ny, self.nz, self.x, self.y, self.z)
+        fval = (ctypes.c_void_p * hostprep.TFB_MAX_FORCE)()
+        fdir = (ctypes.c_int8 * hostprep.TFB_MAX_FORCE)()
+        fi = 0
+        for op in self.config.recipe:
+            if op[0] == 'force':
+                fdir[fi] = op[1]
+                if fi in arrays:
+                    fval[fi] = arrays[fi].ctypes.data
+                fi += 1
+        wind = None
+        if self.problem == recipes.QG:
+            wind = as_f64(hostprep.wind_stress(self.parameters, self.nx, self.ny, self.nz, self.dof,
+                                               self.x, self.y, self.z))
+        check(_lib.lib().tfb_set_params(self._ctx, ctypes.byref(prm), fval, fdir, ptr(wind)))
+        self._param_key = key
+
+    # ---- vectors (SciPy.py:37-38; BaseInterface.py:84-92) ----
+    def vector(self):
+        return numpy.zeros(self.n)
+
+    def vector_from_array(self, array):
+        return array
+
+    def array_from_vector(self, vector):
+        return vector
+
+    # ---- assembly ----
+    def pattern(self):
+        '''(row_ptr, col_idx) of the fixed structural pattern, int64 like CrsMatrix.begA/jcoA.'''
+        if self._pattern is None:
+            row_ptr = numpy.empty(self.n_local + 1, dtype=numpy.int64)
+            col = numpy.empty(self.nnz, dtype=numpy.int64)
+            check(_lib.lib().tfb_get_pattern(self._ctx, ptr(row_ptr), ptr(col)))
+            self._pattern = (row_ptr, col)
+        return self._pattern
+
+    def rhs(self, state):
+        '''F(x); replaces Discretization.rhs (Discretization.py:367-390).'''
+        self._sync_params()
+        state = as_f64(state)
+        out = numpy.empty(self.n)
+        check(_lib.lib().tfb_rhs(self._ctx, ptr(state), ptr(out)))
+        return out
+
+    def jacobian(self, state):
+        '''J(x) as a DeviceMatrix; replaces Discretization.jacobian (:392-415).'''
+        self._sync_params()
+        state = as_f64(state)
+        mat = DeviceMatrix(self)
+        check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, None))
+        return mat
+
+    def jacobian_rhs(self, state):
+        '''Fused J(x), F(x) in one kernel launch (the state is staged once).'''
+        self._sync_params()
+        state = as_f64(state)
+        mat = DeviceMatrix(self)
+        out = numpy.empty(self.n)
+        check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
+        return mat, out
+
+    def jacobian_rhs_into(self, state, mat, out):
+        '''Fused J(x), F(x) into an existing DeviceMatrix / host buffer (no allocations).'''
+        self._sync_params()
+        check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
+        mat._host = None
+        return mat, out
+
+    def mass_matrix(self):
+        '''M as scipy csc (diagonal; pressure rows empty); replaces Discretization.mass_matrix
+        (:417-437) + SciPy.Interface.mass_matrix (SciPy.py:47-49).'''
+        from scipy import sparse
+        diag = numpy.empty(self.n)
+        check(_lib.lib().tfb_mass_diag(self._ctx, ptr(diag)))
+        keep = numpy.abs(diag) > 1e-14                      # Discretization.py:541
+        rows = numpy.nonzero(keep)[0]
+        begA = numpy.zeros(self.n + 1, dtype=numpy.int64)
+        begA[1:] = numpy.cumsum(keep)
+        return sparse.csr_matrix((diag[keep], rows, begA), (self.n, self.n)).tocsc()
+
+    # ---- linear solve (SciPy.py:204-315) ----
+    def solve(self, jac, rhs, rhs2=None, V=None, W=None, C=None):
+        '''Solve ``J y = rhs`` (pressure pinned at row ``dim`` when dof > dim, SciPy.py:212-216)
+        with the preconditioned FGMRES on the device.  With a border (``rhs2, V, W, C``) the
+        bordered system is reduced to two solves with J and a 1x1 Schur complement.'''
+        if not isinstance(jac, DeviceMatrix):
+            raise NotImplementedError('solve() needs a matrix produced by this backend')
+        if V is not None:
+            return self._bordered_solve(jac, rhs, rhs2, V, W, C)
+        return self._solve1(jac, rhs)
+
+    def _solve1(self, jac, rhs):
+        b = as_f64(rhs).copy()
+        prow = -1
+        if self.dof > self.dim:
+            prow = self.pressure_row
+            b[prow] = 0
+        its = self.parameters.get('Iterative Solver', {})
+        o = _lib.TfbSolveOpts()
+        o.tol = its.get('Convergence Tolerance', 1e-10)
+        o.maxit = its.get('Maximum Iterations', 1000)
+        o.restart = its.get('Restart', 100)
+        o.pressure_row = prow
+        o.precond = its.get('Preconditioner Id', 0)
+        o.verbose = int(bool(self.parameters.get('Verbose', False)))
+        info = _lib.TfbSolveInfo()
+        y = numpy.zeros(self.n)
+        rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
+        self.last_solve = {'iterations': info.iters, 'relres': info.relres, 'converged': rc == 0,
+                           'setup_ms': info.setup_ms, 'solve_ms': info.solve_ms}
+        self._debug_print('FGMRES: %d iterations, relres %.3e' % (info.iters, info.relres))
+        return y
+
+    def _bordered_solve(self, jac, rhs, rhs2, V, W, C):
+        # [J V; W^T C] [y1; y2] = [rhs; rhs2]  ->  block elimination with two solves with J
+        if W is None:
+            W = V
+        if C is None:
+            C = 0.0
+        a = self._solve1(jac, rhs)
+        b = self._solve1(jac, as_f64(V))
+        y2 = (rhs2 - W @ a) / (C - W @ b)
+        y1 = a - b * y2
+        return y1, (y2.item() if numpy.ndim(y2) else y2)
+
+    def eigs(self, state, return_eigenvectors=False, enable_recycling=False):
+        raise NotImplementedError('eigs needs jadapy (absent in this environment)')
+
+    # ---- save / load (BaseInterface.py:106-215) ----
+    def save_state(self, name, x):
+        if not name.endswith('.npy'):
+            name += '.npy'
+        numpy.save(name, x)
+        with open(os.path.splitext(name)[0] + '.params', 'w') as f:
+            json.dump(self.parameters, f, default=float)
+
+    def load_state(self, name):
+        if not name.endswith('.npy'):
+            name += '.npy'
+        pname = os.path.splitext(name)[0] + '.params'
+        if os.path.exists(pname):
+            with open(pname) as f:
+                self.parameters.update(json.load(f))
+        return numpy.load(name)
