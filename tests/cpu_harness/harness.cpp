@@ -22,7 +22,12 @@ static int run(const TfbGrid& g, const TfbParams& prm, const double* state, cons
         HostState P{&g, state, i, j, k};
         for (int d1 = 0; d1 < Cfg::DOF; d1++, row++) {
             double J[32]; double f = 0.0;
-            Cfg::template row<true, true>(d1, prm, c, P, J, f);
+            for (int s = 0; s < 32; s++) J[s] = 0.0;
+            TfbArraySink sink{J};
+            const bool interior = !(c.near[0] || c.far[0] || c.far2[0] || c.near[1] || c.far[1] || c.far2[1] ||
+                                    (!Cfg::FLAT && (c.near[2] || c.far[2] || c.far2[2])) || (Cfg::ID == 7 && i <= 1 && j <= 1));
+            if (interior) Cfg::template row<true, true, false>(d1, prm, c, P, sink, f);   // BC-free fast path
+            else Cfg::template row<true, true, true>(d1, prm, c, P, sink, f);
             unsigned m = Cfg::mask(d1, c);
             int ns = Cfg::nslot(d1);
             for (int s = 0; s < ns; s++) if (m >> s & 1u) {

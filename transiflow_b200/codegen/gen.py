@@ -498,8 +498,8 @@ class RowEmitter:
         out = []
         w = out.append
         name = '%s_row%d' % (cfg.name, d1)
-        w('template <bool DO_J, bool DO_F, class Cell, class State>')
-        w('TFB_HD void %s(const TfbParams& prm, const Cell& c, const State& P, double* __restrict__ Jout, double& rhs_out) {' % name)
+        w('template <bool DO_J, bool DO_F, bool BC, class Cell, class State, class Sink>')
+        w('TFB_HD void %s(const TfbParams& prm, const Cell& c, const State& P, Sink& Jout, double& rhs_out) {' % name)
         # make sure every state value the RHS product needs is loaded
         for k in self.fkeys:
             row.P(k[0], (k[1] - 1, k[2] - 1, k[3] - 1))
@@ -544,8 +544,10 @@ class RowEmitter:
             else:
                 e = cname('l', k)
             w('        double %s = %s;' % (cname('F', k), e))
+        w('        if (BC) {')
         for ln in self.bc_lines('F', self.fkeys, True):
-            w('        ' + ln)
+            w('            ' + ln)
+        w('        }')
         terms = ['(%s * %s)' % (cname('F', k), row.P(k[0], (k[1] - 1, k[2] - 1, k[3] - 1))) for k in self.fkeys]
         e = terms[0]
         for t in terms[1:]:
@@ -563,18 +565,20 @@ class RowEmitter:
             if k in L:
                 parts = cname('l', k) if parts is None else '%s + %s' % (parts, cname('l', k))
             w('        double %s = %s;' % (cname('J', k), parts))
+        w('        if (BC) {')
         for ln in self.bc_lines('J', self.jkeys, False):
-            w('        ' + ln)
+            w('            ' + ln)
+        w('        }')
         for ci, (col, ckeys) in enumerate(self.cols):
             if len(ckeys) == 1:
-                w('        Jout[%d] = %s;' % (ci, cname('J', ckeys[0])))
+                w('        Jout.put(%d, %s);' % (ci, cname('J', ckeys[0])))
             else:
                 # z-fold: CrsMatrix.compress merges duplicates in emission order (z = 0,1,2) after
                 # assemble_jacobian dropped entries with |a| <= 1e-14 (Discretization.py:515)
                 e = '0.0'
                 for k in ckeys:
                     e = '(%s + tfb_keep(%s))' % (e, cname('J', k))
-                w('        Jout[%d] = %s;' % (ci, e))
+                w('        Jout.put(%d, %s);' % (ci, e))
         w('    }')
         w('}')
         w('')
@@ -624,11 +628,11 @@ def emit_config(cfg):
     w('        }')
     w('        d2 = code & 15; dx = ((code >> 4) & 3) - 1; dy = ((code >> 6) & 3) - 1; dz = ((code >> 8) & 3) - 1;')
     w('    }')
-    w('    template <bool DO_J, bool DO_F, class Cell, class State>')
-    w('    TFB_HD static void row(int d1, const TfbParams& prm, const Cell& c, const State& P, double* __restrict__ Jout, double& rhs_out) {')
+    w('    template <bool DO_J, bool DO_F, bool BC, class Cell, class State, class Sink>')
+    w('    TFB_HD static void row(int d1, const TfbParams& prm, const Cell& c, const State& P, Sink& Jout, double& rhs_out) {')
     w('        switch (d1) {')
     for d in range(cfg.dof):
-        w('        case %d: %s_row%d<DO_J, DO_F>(prm, c, P, Jout, rhs_out); break;' % (d, cfg.name, d))
+        w('        case %d: %s_row%d<DO_J, DO_F, BC>(prm, c, P, Jout, rhs_out); break;' % (d, cfg.name, d))
     w('        }')
     w('    }')
     w('    template <class Cell>')

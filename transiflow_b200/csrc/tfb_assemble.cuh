@@ -28,7 +28,12 @@ struct TfbAsmArgs {
 template <class Cfg>
 struct TfbTile {
     static constexpr int NZP = Cfg::FLAT ? 1 : 3;
-    template <int TJ> __host__ __device__ static constexpr int state_doubles() { return Cfg::DOF * NZP * (TJ + 2) * (TFB_TI + 2); }
+    // doubles per variable of the SoA tile, padded to 4 (mod 16) so that the AoS->SoA transpose
+    // stores of a half-warp (4 cells x DOF) hit distinct shared-memory banks
+    template <int TJ> __host__ __device__ static constexpr int dstride() {
+        return NZP * (TJ + 2) * (TFB_TI + 2) + ((4 - NZP * (TJ + 2) * (TFB_TI + 2) % 16) + 16) % 16;
+    }
+    template <int TJ> __host__ __device__ static constexpr int state_doubles() { return Cfg::DOF * dstride<TJ>(); }
     // per line: 32 cells * (sum of slots over the rows of a cell) + 2 (alignment slack)
     __host__ __device__ static constexpr int cell_slots() { return Cfg::CELL_SLOTS; }
 };
@@ -40,7 +45,7 @@ struct SmemState {
     __device__ __forceinline__ double operator()(int d, int ox, int oy, int oz) const {
         constexpr int NZP = TfbTile<Cfg>::NZP;
         const int zp = NZP == 1 ? 0 : oz + 1;
-        return base[((d * NZP + zp) * (TJ + 2) + (jl + 1 + oy)) * (TFB_TI + 2) + (il + 1 + ox)];
+        return base[d * TfbTile<Cfg>::template dstride<TJ>() + (zp * (TJ + 2) + (jl + 1 + oy)) * (TFB_TI + 2) + (il + 1 + ox)];
     }
 };
 
@@ -56,8 +61,15 @@ __device__ __forceinline__ bool tfb_is_interior(const TfbCell& c) {
     return !b;
 }
 
-template <class Cfg, bool DO_J, bool DO_F, int TJ>
-__global__ void __launch_bounds__(32 * Cfg::DOF * TJ)
+// Interior rows have the full slot set: slot s lands at a compile-time offset of the row start,
+// so every value is stored the moment it is computed (short register live ranges).
+struct TfbSmemSink {
+    double* row;   // smem position of this row's first slot
+    __device__ __forceinline__ void put(int s, double x) { row[s] = x; }
+};
+
+template <class Cfg, bool DO_J, bool DO_F, int TJ, int MINB>
+__global__ void __launch_bounds__(32 * Cfg::DOF * TJ, MINB)
 tfb_assemble_kernel(const TfbAsmArgs a) {
     constexpr int DOF = Cfg::DOF;
     constexpr int NZP = TfbTile<Cfg>::NZP;
@@ -67,6 +79,7 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
     double* sm_state = smem;
     double* sm_out = smem + ((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1);
     __shared__ int sm_span[TJ][2];
+    __shared__ double sm_mx[TFB_NMET][TFB_TI], sm_my[TFB_NMET + 2][TJ], sm_mz[TFB_NMET];
 
     const TfbGrid& g = a.g;
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
@@ -77,18 +90,47 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
     const int kofs = 1 - a.k0;           // global k -> plane index of the slab storage
 
     // ---- stage the state tile (+halo) in shared memory, SoA, padded-state semantics ----
+    // One warp per (z,y) row of the tile: W cells x DOF doubles are contiguous in global memory
+    // (AoS), so the reads are fully coalesced; the transpose to SoA happens in the smem store.
+    // Padded-state rules (utils.py:62-133): zero outside the domain, wall-normal velocity on the
+    // far walls forced to zero, all three z-planes fold onto the single plane when nz == 1.
     {
-        constexpr int W = TFB_TI + 2, H = TJ + 2;
-        constexpr int NCELL = NZP * H * W;
-        for (int e = tid; e < NCELL * DOF; e += NTHREADS) {
-            const int d = e % DOF;           // AoS order in global memory -> coalesced reads
-            const int cidx = e / DOF;
-            const int xx = cidx % W, yy = (cidx / W) % H, zz = cidx / (W * H);
-            const int oz = NZP == 1 ? 0 : zz - 1;
-            const double v = tfb_padded_load(g, a.state, kofs, i0 + xx - 1, j0 + yy - 1, k + oz, d);
-            sm_state[((d * NZP + zz) * H + yy) * W + xx] = v;
+        constexpr int W = TFB_TI + 2, H = TJ + 2, ROWS = NZP * H, ROWLEN = W * DOF;
+        constexpr int NWARPS = NTHREADS / 32;
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int r = warp; r < ROWS; r += NWARPS) {
+            const int zz = r / H, yy = r - zz * H;
+            const int jj = j0 + yy - 1;
+            const int kk = (NZP == 1) ? (g.zfold ? 0 : k) : k + zz - 1;
+            const bool rowvalid = jj >= 0 && jj < g.ny && kk >= 0 && kk < g.nz;
+            const double* src = a.state + (((long long)(kk + kofs) * g.ny + jj) * g.nx + (i0 - 1)) * DOF;
+            const bool zero_v = jj == g.ny - 1, zero_w = !g.zfold && kk == g.nz - 1;
+            double* dst = sm_state + (zz * H + yy) * W;
+#pragma unroll
+            for (int e = lane; e < ROWLEN; e += 32) {
+                const int xx = e / DOF, d = e - xx * DOF;
+                const int ii = i0 - 1 + xx;
+                double v = 0.0;
+                if (rowvalid && ii >= 0 && ii < g.nx) {
+                    v = src[e];
+                    if ((d == 0 && ii == g.nx - 1) || (d == 1 && zero_v) || (d == 2 && zero_w)) v = 0.0;
+                }
+                dst[d * TfbTile<Cfg>::template dstride<TJ>() + xx] = v;
+            }
         }
     }
+    // grid metrics of the tile: 1-D arrays, staged once per CTA
+    for (int e = tid; e < TFB_NMET * TFB_TI; e += NTHREADS) {
+        const int mm = e / TFB_TI, xx = e % TFB_TI;
+        sm_mx[mm][xx] = (i0 + xx < g.nx) ? g.met[0][mm * g.nx + i0 + xx] : 0.0;
+    }
+    for (int e = tid; e < (TFB_NMET + 2) * TJ; e += NTHREADS) {
+        const int mm = e / TJ, yy = e % TJ;
+        double v = 0.0;
+        if (j0 + yy < g.ny) v = mm < TFB_NMET ? g.met[1][mm * g.ny + j0 + yy] : g.cor[(mm - TFB_NMET) * g.ny + j0 + yy];
+        sm_my[mm][yy] = v;
+    }
+    if (tid < TFB_NMET) sm_mz[tid] = g.met[2][tid * g.nz + k];
     const int i = i0 + il, j = j0 + jl;
     const bool valid = i < g.nx && j < g.ny;
     const long long cell_local = ((long long)kl * g.ny + j) * g.nx + i;
@@ -102,19 +144,37 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
     }
     __syncthreads();
 
-    double J[Cfg::MAXSLOT];
-    double f = 0.0;
-    unsigned m = 0u;
-    int rp = 0;
+    // ---- per-row work: values go to this line's staging area in shared memory ----
+    double* out = sm_out + jl * LINE_CAP;
+    const int gbase = DO_J ? sm_span[jl][0] : 0, gend = DO_J ? sm_span[jl][1] : 0;
+    const int galign = gbase & ~1;
     if (valid) {
         TfbCell c;
-        tfb_make_cell<Cfg::NFORCE>(g, i, j, k, c);
+        c.hcx = sm_mx[0][il]; c.hux = sm_mx[1][il]; c.rhcx = sm_mx[2][il]; c.rhpx = sm_mx[3][il];
+        c.rhmx = sm_mx[4][il]; c.rhux = sm_mx[5][il]; c.wmx = sm_mx[6][il]; c.wpx = sm_mx[7][il];
+        c.hcy = sm_my[0][jl]; c.huy = sm_my[1][jl]; c.rhcy = sm_my[2][jl]; c.rhpy = sm_my[3][jl];
+        c.rhmy = sm_my[4][jl]; c.rhuy = sm_my[5][jl]; c.wmy = sm_my[6][jl]; c.wpy = sm_my[7][jl];
+        c.cor1 = sm_my[8][jl]; c.cor2 = sm_my[9][jl];
+        c.hcz = sm_mz[0]; c.huz = sm_mz[1]; c.rhcz = sm_mz[2]; c.rhpz = sm_mz[3];
+        c.rhmz = sm_mz[4]; c.rhuz = sm_mz[5]; c.wmz = sm_mz[6]; c.wpz = sm_mz[7];
+        tfb_cell_flags<Cfg::NFORCE>(g, i, j, k, c);
         SmemState<Cfg, TJ> P{sm_state, il, jl};
-        Cfg::template row<DO_J, DO_F>(d1, a.prm, c, P, J, f);
-        if (DO_J) {
-            const int ns = Cfg::nslot(d1);
-            m = tfb_is_interior<Cfg>(c) ? ((1u << ns) - 1u) : Cfg::mask(d1, c);
-            rp = a.row_ptr[row];
+        double f = 0.0;
+        const int rp = DO_J ? a.row_ptr[row] : 0;
+        if (tfb_is_interior<Cfg>(c)) {
+            TfbSmemSink sink{out + (rp - galign)};
+            Cfg::template row<DO_J, DO_F, false>(d1, a.prm, c, P, sink, f);
+        } else {
+            double J[Cfg::MAXSLOT];
+            TfbArraySink sink{J};
+            Cfg::template row<DO_J, DO_F, true>(d1, a.prm, c, P, sink, f);
+            if (DO_J) {
+                const unsigned m = Cfg::mask(d1, c);
+                int pos = rp - galign;
+#pragma unroll
+                for (int s = 0; s < Cfg::MAXSLOT; s++)
+                    if ((m >> s) & 1u) out[pos++] = J[s];
+            }
         }
         if (DO_F) {
             if (a.frc_static) f = f + a.frc_static[row];
@@ -122,31 +182,26 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
         }
     }
     if (DO_J) {
-        // ---- stage this line's CSR values, then write the contiguous span with 128-bit stores ----
-        double* out = sm_out + jl * LINE_CAP;
-        const int gbase = sm_span[jl][0], gend = sm_span[jl][1];
-        const int galign = gbase & ~1;
-        if (valid) {
-            int pos = rp - galign;
-#pragma unroll
-            for (int s = 0; s < Cfg::MAXSLOT; s++)
-                if ((m >> s) & 1u) out[pos++] = J[s];
-        }
+        // ---- write this line's contiguous CSR span: one TMA bulk store (smem -> global) ----
+        // writers fence generic-proxy smem stores towards the async proxy, then the line's warps meet
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tfb_bar_sync(1 + jl, 32 * DOF);
-        if (j < g.ny) {
+        if (j < g.ny && d1 == 0) {
+            const int head = gbase - galign;              // 0 or 1: first element not ours if 1
             const int cnt = gend - galign;
-            const int head = gbase - galign;    // 0 or 1
-            const int t = d1 * 32 + il;
-            double* gout = a.vals + galign;
-            for (int e = 2 * t; e < cnt; e += 2 * 32 * DOF) {
-                if (e >= head && e + 1 < cnt) {
-                    double2 v2 = *reinterpret_cast<const double2*>(out + e);
-                    *reinterpret_cast<double2*>(gout + e) = v2;
-                } else {
-                    if (e >= head) gout[e] = out[e];
-                    if (e + 1 < cnt) gout[e + 1] = out[e + 1];
-                }
+            const int body0 = head ? 2 : 0;               // first 16-byte aligned element we own
+            const int body1 = cnt & ~1;                   // end of the aligned body
+            if (il == 0 && body1 > body0) {
+                const unsigned src = (unsigned)__cvta_generic_to_shared(out + body0);
+                double* dstp = a.vals + galign + body0;
+                const unsigned bytes = (unsigned)(body1 - body0) * 8u;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(dstp), "r"(src), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            if (il == 1 && head && cnt > 1) a.vals[galign + 1] = out[1];
+            if (il == 2 && (cnt & 1) && cnt - 1 >= head) a.vals[galign + cnt - 1] = out[cnt - 1];
+            if (il == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
     }
 }

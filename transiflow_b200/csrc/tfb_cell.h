@@ -39,13 +39,9 @@ struct TfbCell {
 
 TFB_HD int tfb_far2_index(int m) { return m >= 2 ? m - 2 : 2 * m - 2; }  // Python index m-2 with wrap
 
+// everything of a TfbCell except the metrics: position, face flags, per-face forcing values
 template <int NFORCE>
-TFB_HD void tfb_make_cell(const TfbGrid& g, int i, int j, int k, TfbCell& c) {
-    { constexpr int A = 0; TFB_LOADMET(x, g.nx, i, c) }
-    { constexpr int A = 1; TFB_LOADMET(y, g.ny, j, c) }
-    { constexpr int A = 2; TFB_LOADMET(z, g.nz, k, c) }
-    c.cor1 = g.cor[j];
-    c.cor2 = g.cor[g.ny + j];
+TFB_HD void tfb_cell_flags(const TfbGrid& g, int i, int j, int k, TfbCell& c) {
     c.i = i; c.j = j; c.k = k; c.nx = g.nx; c.ny = g.ny; c.nz = g.nz;
     c.near[0] = i == 0; c.far[0] = i == g.nx - 1; c.far2[0] = i == tfb_far2_index(g.nx);
     c.near[1] = j == 0; c.far[1] = j == g.ny - 1; c.far2[1] = j == tfb_far2_index(g.ny);
@@ -61,6 +57,16 @@ TFB_HD void tfb_make_cell(const TfbGrid& g, int i, int j, int k, TfbCell& c) {
         }
         c.fval[f] = v;
     }
+}
+
+template <int NFORCE>
+TFB_HD void tfb_make_cell(const TfbGrid& g, int i, int j, int k, TfbCell& c) {
+    { constexpr int A = 0; TFB_LOADMET(x, g.nx, i, c) }
+    { constexpr int A = 1; TFB_LOADMET(y, g.ny, j, c) }
+    { constexpr int A = 2; TFB_LOADMET(z, g.nz, k, c) }
+    c.cor1 = g.cor[j];
+    c.cor2 = g.cor[g.ny + j];
+    tfb_cell_flags<NFORCE>(g, i, j, k, c);
 }
 
 // Padded-state semantics of utils.create_padded_state_mtx (utils.py:62-133) for the

@@ -1,5 +1,6 @@
 // libtfb200 core: context management, fixed-pattern construction, assembly launches.
 #include <cub/device/device_scan.cuh>
+#include <stdlib.h>
 #include <string.h>
 #include "tfb_assemble.cuh"
 
@@ -233,9 +234,8 @@ extern "C" int tfb_mat_set_values(tfb_mat* m, const double* in) {
 }
 
 // ------------------------------- assembly launches -------------------------------
-template <class Cfg, bool DO_J, bool DO_F>
-static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
-    constexpr int TJ = Cfg::DOF >= 5 ? 3 : 4;
+template <class Cfg, bool DO_J, bool DO_F, int TJ, int MINB>
+static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     TfbAsmArgs a;
     a.g = c->grid();
     a.prm = c->prm;
@@ -248,7 +248,7 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
     a.nzl = c->nzl;
     constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
     size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
-    auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ>;
+    auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ, MINB>;
     static bool configured = false;
     if (!configured) {
         TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -260,6 +260,31 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Tile shape / occupancy variant.  Default: TJ lines per CTA, MINB CTAs per SM (register cap).
+// TFB_ASM_VARIANT (env) selects alternatives for the headline 3D LDC kernel while tuning.
+template <class Cfg, bool DO_J, bool DO_F>
+static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("TFB_ASM_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    if constexpr (Cfg::ID == 1 && DO_J && DO_F) {   // Cfg_ldc3d
+        switch (variant) {
+        case 1: return launch_assemble_v<Cfg, DO_J, DO_F, 4, 1>(c, m);
+        case 2: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 2>(c, m);
+        case 3: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 3>(c, m);
+        case 4: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 4>(c, m);
+        case 5: return launch_assemble_v<Cfg, DO_J, DO_F, 1, 6>(c, m);
+        case 6: return launch_assemble_v<Cfg, DO_J, DO_F, 1, 8>(c, m);
+        case 7: return launch_assemble_v<Cfg, DO_J, DO_F, 4, 2>(c, m);
+        case 8: return launch_assemble_v<Cfg, DO_J, DO_F, 1, 4>(c, m);
+        default: break;
+        }
+    }
+    return launch_assemble_v<Cfg, DO_J, DO_F, (Cfg::DOF >= 5 ? 3 : 4), 1>(c, m);
 }
 
 template <class Cfg>

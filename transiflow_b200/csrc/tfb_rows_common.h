@@ -31,3 +31,10 @@ struct TfbParams {
 // assemble_jacobian only emits |a| > 1e-14 (Discretization.py:515); needed where duplicate
 // columns are merged afterwards (z-fold of semi-2D grids).
 TFB_HD double tfb_keep(double a) { return fabs(a) > 1e-14 ? a : 0.0; }
+
+// Where a row function delivers its Jacobian slot values (slot index s is a compile-time
+// constant at every call site after inlining).
+struct TfbArraySink {
+    double* v;
+    TFB_HD void put(int s, double x) { v[s] = x; }
+};
