@@ -206,6 +206,220 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
     }
 }
 
+// =====================================================================================
+// z-marching variant for true 3-D grids: a CTA owns a (TI x TJ) column of cells and sweeps KCH
+// planes.  The state planes live in a 4-slot shared-memory ring (k-1,k,k+1 in use, one slot
+// being refilled), so every plane is fetched from HBM/L2 once per column instead of three
+// times.  The loads of plane k+3 are issued BEFORE the rows of plane k are computed and wait
+// in registers (software prefetch) until they are deposited one step later; the CSR spans
+// leave through double-buffered TMA bulk stores.  One __syncthreads per plane.
+// =====================================================================================
+template <class Cfg, int TJ>
+struct TfbMarch {
+    static constexpr int W = TFB_TI + 2, H = TJ + 2, HW = H * W;
+    static constexpr int DSTR = HW + ((4 - HW % 16) + 16) % 16;   // = 4 (mod 16): conflict-free transpose stores
+    static constexpr int SLOT = Cfg::DOF * DSTR;                  // doubles per ring slot (one plane)
+    static constexpr int NSLOT = 4;
+    static constexpr int LINE_CAP = TFB_TI * Cfg::CELL_SLOTS + 2;
+    __host__ __device__ static constexpr int smem_doubles(bool do_j) { return NSLOT * SLOT + (do_j ? 2 * TJ * LINE_CAP : 0); }
+};
+
+template <class Cfg, int TJ>
+struct RingState {
+    const double* pl[3];   // planes k-1, k, k+1, already offset to this thread's cell
+    __device__ __forceinline__ double operator()(int d, int ox, int oy, int oz) const {
+        return pl[oz + 1][d * TfbMarch<Cfg, TJ>::DSTR + oy * TfbMarch<Cfg, TJ>::W + ox];
+    }
+};
+
+template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB>
+__global__ void __launch_bounds__(32 * Cfg::DOF * TJ, MINB)
+tfb_assemble_march_kernel(const TfbAsmArgs a) {
+    using M = TfbMarch<Cfg, TJ>;
+    constexpr int DOF = Cfg::DOF, W = M::W, H = M::H, DSTR = M::DSTR, SLOT = M::SLOT, LINE_CAP = M::LINE_CAP;
+    constexpr int NT = 32 * DOF * TJ;
+    constexpr int ROWLEN = W * DOF, NEL = H * ROWLEN, NPT = (NEL + NT - 1) / NT;
+    extern __shared__ __align__(16) double smem[];
+    double* ring = smem;
+    double* sm_out = smem + M::NSLOT * SLOT;   // SLOT is even (DSTR multiple of 4)
+    __shared__ int sm_span[2][TJ][2];
+    __shared__ double sm_mx[TFB_NMET][TFB_TI], sm_my[TFB_NMET + 2][TJ], sm_mz[TFB_NMET][KCH];
+
+    const TfbGrid& g = a.g;
+    const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
+    const int tid = (jl * DOF + d1) * 32 + il;
+    const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
+    const int kbeg = blockIdx.z * KCH, kend = min(kbeg + KCH, a.nzl);   // local planes
+    const int kofs = 1 - a.k0;
+    const long long plane = (long long)g.nx * g.ny * DOF;
+
+    // ---- k-invariant descriptors of the tile elements this thread moves for every plane ----
+    int l_src[NPT], l_dst[NPT];
+    unsigned l_flags = 0u;   // bit t: fetch from global; bit 8+t: w-component; bit 16+t: element exists
+#pragma unroll
+    for (int t = 0; t < NPT; t++) {
+        const int e = tid + t * NT;
+        const int yy = e / ROWLEN, cc = e - yy * ROWLEN;
+        const int xx = cc / DOF, d = cc - xx * DOF;
+        const int jj = j0 + yy - 1, ii = i0 - 1 + xx;
+        const bool exists = e < NEL;
+        const bool inside = exists && jj >= 0 && jj < g.ny && ii >= 0 && ii < g.nx;
+        // wall-normal velocities on the far x / y walls read as zero (utils.py:119,125)
+        const bool zeroed = (d == 0 && ii == g.nx - 1) || (d == 1 && jj == g.ny - 1);
+        l_src[t] = inside ? ((jj * g.nx + ii) * DOF + d) : 0;
+        l_dst[t] = d * DSTR + yy * W + xx;
+        if (inside && !zeroed) l_flags |= 1u << t;
+        if (d == 2) l_flags |= 1u << (8 + t);
+        if (exists) l_flags |= 1u << (16 + t);
+    }
+    auto fetch = [&](int kglob, double (&v)[NPT]) {
+        const double* pl = a.state + (long long)(kglob + kofs) * plane;   // ghost planes are zero at the domain ends
+#pragma unroll
+        for (int t = 0; t < NPT; t++) v[t] = ((l_flags >> t) & 1u) ? pl[l_src[t]] : 0.0;
+    };
+    auto deposit = [&](int kglob, int slot, const double (&v)[NPT]) {
+        const bool zero_w = !g.zfold && kglob == g.nz - 1;                // utils.py:131
+        double* dst = ring + slot * SLOT;
+#pragma unroll
+        for (int t = 0; t < NPT; t++)
+            if ((l_flags >> (16 + t)) & 1u) dst[l_dst[t]] = (zero_w && ((l_flags >> (8 + t)) & 1u)) ? 0.0 : v[t];
+    };
+
+    // ---- prologue: metrics of the column, first three planes, first CSR spans ----
+    for (int e = tid; e < TFB_NMET * TFB_TI; e += NT) {
+        const int mm = e / TFB_TI, xx = e % TFB_TI;
+        sm_mx[mm][xx] = (i0 + xx < g.nx) ? g.met[0][mm * g.nx + i0 + xx] : 0.0;
+    }
+    for (int e = tid; e < (TFB_NMET + 2) * TJ; e += NT) {
+        const int mm = e / TJ, yy = e % TJ;
+        double v = 0.0;
+        if (j0 + yy < g.ny) v = mm < TFB_NMET ? g.met[1][mm * g.ny + j0 + yy] : g.cor[(mm - TFB_NMET) * g.ny + j0 + yy];
+        sm_my[mm][yy] = v;
+    }
+    for (int e = tid; e < TFB_NMET * KCH; e += NT) {
+        const int mm = e / KCH, zz = e % KCH;
+        sm_mz[mm][zz] = (kbeg + zz < a.nzl) ? g.met[2][mm * g.nz + a.k0 + kbeg + zz] : 0.0;
+    }
+    double pre[NPT];   // plane in flight: fetched one step before it is deposited
+    {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            fetch(a.k0 + kbeg - 1 + p, pre);
+            deposit(a.k0 + kbeg - 1 + p, p, pre);
+        }
+        if (kbeg + 1 < kend) fetch(a.k0 + kbeg + 2, pre);
+    }
+    const int i = i0 + il, j = j0 + jl;
+    const bool valid = i < g.nx && j < g.ny;
+    const bool leader = DO_J && d1 == 0 && il == 0 && j < g.ny;
+    const int ilast = min(i0 + TFB_TI, g.nx);
+    long long row = (((long long)kbeg * g.ny + j) * g.nx + i) * DOF + d1;              // local row of this thread
+    long long r0 = (((long long)kbeg * g.ny + j) * g.nx + i0) * DOF;                  // span of this line
+    const long long rlen = (long long)(ilast - i0) * DOF;
+    int rp = (DO_J && valid) ? a.row_ptr[row] : 0;
+    if (leader) {
+        sm_span[0][jl][0] = a.row_ptr[r0];
+        sm_span[0][jl][1] = a.row_ptr[r0 + rlen];
+    }
+    // x/y part of the cell context is plane-invariant
+    TfbCell c;
+    tfb_cell_flags<Cfg::NFORCE>(g, i, j, a.k0 + kbeg, c);
+    const bool xy_interior = !(c.near[0] | c.far[0] | c.far2[0] | c.near[1] | c.far[1] | c.far2[1]) &&
+                             !(Cfg::ID == 7 && i <= 1 && j <= 1);
+    const int kfar2 = tfb_far2_index(g.nz);
+    const int cell_off = (jl + 1) * W + (il + 1);
+    int s0 = 0;   // ring slot of plane k-1
+    __syncthreads();
+
+    int step = 0;
+    for (int kl = kbeg; kl < kend; kl++, step++) {
+        const int k = a.k0 + kl;
+        const bool more = kl + 1 < kend;
+        const int s1 = (s0 + 1) & 3, s2 = (s0 + 2) & 3, s3 = (s0 + 3) & 3;
+        // ---- plane k+2 (in registers since the previous step) goes to the free slot; prefetch k+3 ----
+        int rp_next = 0, span_next0 = 0, span_next1 = 0;
+        if (more) {
+            deposit(k + 2, s3, pre);
+            if (kl + 2 < kend) fetch(k + 3, pre);
+            if (DO_J && valid) rp_next = a.row_ptr[row + plane];
+            if (leader) {
+                span_next0 = a.row_ptr[r0 + plane];
+                span_next1 = a.row_ptr[r0 + plane + rlen];
+            }
+        }
+        // ---- rows of plane k ----
+        double* out = sm_out + ((step & 1) * TJ + jl) * LINE_CAP;
+        const int gbase = DO_J ? sm_span[step & 1][jl][0] : 0, gend = DO_J ? sm_span[step & 1][jl][1] : 0;
+        const int galign = gbase & ~1;
+        if (valid) {
+            const int zz = kl - kbeg;
+            c.hcx = sm_mx[0][il]; c.hux = sm_mx[1][il]; c.rhcx = sm_mx[2][il]; c.rhpx = sm_mx[3][il];
+            c.rhmx = sm_mx[4][il]; c.rhux = sm_mx[5][il]; c.wmx = sm_mx[6][il]; c.wpx = sm_mx[7][il];
+            c.hcy = sm_my[0][jl]; c.huy = sm_my[1][jl]; c.rhcy = sm_my[2][jl]; c.rhpy = sm_my[3][jl];
+            c.rhmy = sm_my[4][jl]; c.rhuy = sm_my[5][jl]; c.wmy = sm_my[6][jl]; c.wpy = sm_my[7][jl];
+            c.cor1 = sm_my[8][jl]; c.cor2 = sm_my[9][jl];
+            c.hcz = sm_mz[0][zz]; c.huz = sm_mz[1][zz]; c.rhcz = sm_mz[2][zz]; c.rhpz = sm_mz[3][zz];
+            c.rhmz = sm_mz[4][zz]; c.rhuz = sm_mz[5][zz]; c.wmz = sm_mz[6][zz]; c.wpz = sm_mz[7][zz];
+            c.k = k;
+            c.near[2] = k == 0; c.far[2] = k == g.nz - 1; c.far2[2] = k == kfar2;
+            c.cell0 = (i == 0 && j == 0 && k == 0);
+            RingState<Cfg, TJ> P;
+            P.pl[0] = ring + s0 * SLOT + cell_off;
+            P.pl[1] = ring + s1 * SLOT + cell_off;
+            P.pl[2] = ring + s2 * SLOT + cell_off;
+            double f = 0.0;
+            if (xy_interior && !(c.near[2] | c.far[2] | c.far2[2])) {
+                TfbSmemSink sink{out + (rp - galign)};
+                Cfg::template row<DO_J, DO_F, false>(d1, a.prm, c, P, sink, f);
+            } else {
+                double J[Cfg::MAXSLOT];
+                TfbArraySink sink{J};
+                Cfg::template row<DO_J, DO_F, true>(d1, a.prm, c, P, sink, f);
+                if (DO_J) {
+                    const unsigned m = Cfg::mask(d1, c);
+                    int pos = rp - galign;
+#pragma unroll
+                    for (int s = 0; s < Cfg::MAXSLOT; s++)
+                        if ((m >> s) & 1u) out[pos++] = J[s];
+                }
+            }
+            if (DO_F) {
+                if (a.frc_static) f = f + a.frc_static[row];
+                a.rhs[row] = f;
+            }
+        }
+        if (leader && more) {
+            sm_span[(step + 1) & 1][jl][0] = span_next0;
+            sm_span[(step + 1) & 1][jl][1] = span_next1;
+        }
+        // staged CSR values -> async proxy; deposited plane + spans -> everyone.  The bulk store of
+        // the previous plane must have drained its staging buffer before anyone refills it.
+        if (DO_J) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        if (leader) {
+            // one TMA bulk store per line (smem -> global), double-buffered staging
+            const int head = gbase - galign, cnt = gend - galign;
+            const int body0 = head ? 2 : 0, body1 = cnt & ~1;
+            if (body1 > body0) {
+                const unsigned src = (unsigned)__cvta_generic_to_shared(out + body0);
+                double* dstp = a.vals + galign + body0;
+                const unsigned bytes = (unsigned)(body1 - body0) * 8u;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(dstp), "r"(src), "r"(bytes) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (head && cnt > 1) a.vals[galign + 1] = out[1];
+            if ((cnt & 1) && cnt - 1 >= head) a.vals[galign + cnt - 1] = out[cnt - 1];
+        }
+        rp = rp_next;
+        row += plane;
+        r0 += plane;
+        s0 = s1;
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- pattern discovery: structural row lengths, then global column indices ----
 template <class Cfg>
 __global__ void tfb_count_kernel(TfbGrid g, int k0, long long nrows, int* __restrict__ counts) {

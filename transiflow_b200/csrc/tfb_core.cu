@@ -262,6 +262,33 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     return 0;
 }
 
+template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB>
+static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
+    TfbAsmArgs a;
+    a.g = c->grid();
+    a.prm = c->prm;
+    a.state = c->d_state;
+    a.frc_static = c->has_frc_static ? c->d_frc_static : nullptr;
+    a.row_ptr = c->d_row_ptr;
+    a.vals = m ? m->d_vals : nullptr;
+    a.rhs = c->d_rhs;
+    a.k0 = c->desc.k0;
+    a.nzl = c->nzl;
+    size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
+    auto kern = tfb_assemble_march_kernel<Cfg, DO_J, DO_F, TJ, KCH, MINB>;
+    static bool configured = false;
+    if (!configured) {
+        TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 block(32, Cfg::DOF, TJ);
+    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (c->nzl + KCH - 1) / KCH);
+    kern<<<grid, block, smem, c->stream>>>(a);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Tile shape / occupancy variant.  Default: TJ lines per CTA, MINB CTAs per SM (register cap).
 // TFB_ASM_VARIANT (env) selects alternatives for the headline 3D LDC kernel while tuning.
 template <class Cfg, bool DO_J, bool DO_F>
@@ -277,14 +304,25 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
         case 2: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 2>(c, m);
         case 3: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 3>(c, m);
         case 4: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 4>(c, m);
-        case 5: return launch_assemble_v<Cfg, DO_J, DO_F, 1, 6>(c, m);
-        case 6: return launch_assemble_v<Cfg, DO_J, DO_F, 1, 8>(c, m);
         case 7: return launch_assemble_v<Cfg, DO_J, DO_F, 4, 2>(c, m);
-        case 8: return launch_assemble_v<Cfg, DO_J, DO_F, 1, 4>(c, m);
+        case 10: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 4>(c, m);
+        case 11: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 3>(c, m);
+        case 12: return launch_march_v<Cfg, DO_J, DO_F, 2, 8, 4>(c, m);
+        case 13: return launch_march_v<Cfg, DO_J, DO_F, 4, 16, 2>(c, m);
+        case 14: return launch_march_v<Cfg, DO_J, DO_F, 2, 32, 4>(c, m);
+        case 15: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 6>(c, m);
+        case 16: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);
+        case 17: return launch_march_v<Cfg, DO_J, DO_F, 4, 16, 1>(c, m);
         default: break;
         }
     }
-    return launch_assemble_v<Cfg, DO_J, DO_F, (Cfg::DOF >= 5 ? 3 : 4), 1>(c, m);
+    if constexpr (!Cfg::FLAT) {
+        // true 3-D grids: z-marching kernel (ring of state planes, software prefetch)
+        if constexpr (Cfg::DOF >= 5) return launch_march_v<Cfg, DO_J, DO_F, 3, 16, 1>(c, m);
+        else return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);
+    } else {
+        return launch_assemble_v<Cfg, DO_J, DO_F, (Cfg::DOF >= 5 ? 3 : 4), 1>(c, m);
+    }
 }
 
 template <class Cfg>
