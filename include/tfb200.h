@@ -118,6 +118,15 @@ typedef struct {
 } tfb_solve_info;
 int tfb_solve(tfb_mat* mat, const double* b, double* x, const tfb_solve_opts* opts, tfb_solve_info* info);
 
+/* Fast-diagonalisation data of the block preconditioner: for variable `var` and axis `axis`
+ * the m x m M-orthonormal eigenvector matrix Q (row-major) and eigenvalues lam of the 1-D pencil
+ * (K, M) of that variable's diffusion stencil incl. wall folds; coef = the operator's scalar
+ * (c_visc, c_T, c_S; -1 for the pressure Poisson operator D M^-1 G).  Computed by the host
+ * (hostprep.fdm_operators) whenever grid or parameters change. */
+int tfb_fdm_set(tfb_ctx* ctx, int var, int axis, int m, const double* Q, const double* lam, double coef);
+/* z = P^-1 r with host vectors (diagnostics / tests of the preconditioner alone) */
+int tfb_precond_apply(tfb_mat* mat, const double* r, double* z, int pressure_row);
+
 /* NCCL plumbing for z-slab runs (one process per GPU). */
 int tfb_nccl_unique_id(uint8_t id[128]);
 int tfb_comm_init(tfb_ctx* ctx, int nranks, int rank, const uint8_t id[128]);

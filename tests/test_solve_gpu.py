@@ -1,0 +1,104 @@
+'''Parity of the device linear solver / Newton step with the SciPy backend's spsolve path.
+Golden vectors were produced by the unmodified reference (tests/golden/make_golden_newton.py);
+the oracle's restatement of the pinned direct solve checks larger cases on the box.'''
+import os
+
+import numpy
+import pytest
+
+from cases_newton import NEWTON_CASES
+from golden_io import GEN
+
+pytestmark = pytest.mark.gpu
+
+
+def newton(it, x0, tol=1e-10, maxit=10):
+    '''Continuation.newton (Continuation.py:67-114), residual_check='F'.'''
+    x = x0
+    for k in range(maxit):
+        fval = it.rhs(x)
+        if numpy.linalg.norm(fval) < tol:
+            break
+        jac = it.jacobian(x)
+        x = x + it.solve(jac, -fval)
+    return x, k
+
+
+def _iface(params, nx, ny, nz):
+    from transiflow_b200 import Interface
+    return Interface(dict(params), nx, ny, nz)
+
+
+def test_solve_manufactured_solution():
+    '''reference tests/test_interface.py:17-50'''
+    nx = 4
+    it = _iface({}, nx, nx, nx)
+    A = it.jacobian(it.vector())
+    x = numpy.arange(1, it.n + 1, dtype=float)
+    x[3] = 0
+    b = A @ x
+    y = it.solve(A, b)
+    pressure = y[3] - x[3]
+    assert numpy.linalg.norm(y) > 0
+    assert (numpy.linalg.norm(y - x) - pressure * nx**3) / numpy.linalg.norm(b) < 1e-7
+    assert it.last_solve['converged']
+
+
+@pytest.mark.parametrize('name', ['ldc3d_8', 'ldc3d_12_str', 'ldc2d_24', 'dhc2d_16', 'rb3d_8', 'qg_16', 'amoc_16'])
+def test_linear_solve_matches_reference(name):
+    '''J(x*) y = b at the reference's converged state: y within 1e-8 of SuperLU's.'''
+    params, nx, ny, nz = NEWTON_CASES[name]
+    g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
+    it = _iface(params, nx, ny, nz)
+    jac = it.jacobian(g['x'])
+    y = it.solve(jac, g['b'])
+    assert it.last_solve['converged'], it.last_solve
+    scale = numpy.abs(g['y']).max()
+    assert numpy.abs(y - g['y']).max() <= 1e-8 * scale, (numpy.abs(y - g['y']).max() / scale, it.last_solve)
+
+
+@pytest.mark.parametrize('name', ['ldc3d_8', 'ldc3d_12_str', 'ldc2d_24', 'dhc2d_16', 'rb3d_8', 'qg_16'])
+def test_newton_converges_to_reference_state(name):
+    params, nx, ny, nz = NEWTON_CASES[name]
+    g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
+    it = _iface(params, nx, ny, nz)
+    x, k = newton(it, it.vector())
+    assert numpy.linalg.norm(it.rhs(x)) < 1e-9
+    scale = max(numpy.abs(g['x']).max(), 1e-300)
+    assert numpy.abs(x - g['x']).max() <= 1e-8 * scale, numpy.abs(x - g['x']).max() / scale
+
+
+def test_solve_against_oracle_direct_solve_32():
+    '''3-D LDC 20^3 (SuperLU still feasible): Newton update within 1e-8 of the spsolve path.'''
+    from oracle.tf_oracle import Oracle, direct_solve
+    params, N = {'Reynolds Number': 100}, 20
+    it = _iface(params, N, N, N)
+    orc = Oracle(dict(params), N, N, N)
+    x = numpy.zeros(it.n)
+    for _ in range(2):
+        f = it.rhs(x)
+        jac = it.jacobian(x)
+        dx = it.solve(jac, -f)
+        want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
+        assert numpy.abs(dx - want).max() <= 1e-8 * numpy.abs(want).max(), it.last_solve
+        x = x + dx
+
+
+def test_bordered_solve():
+    '''[J V; W^T C][y1; y2] = [b; b2] (SciPy.py:226-250) by block elimination.'''
+    it = _iface({'Reynolds Number': 50}, 6, 6, 6)
+    x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
+    jac = it.jacobian(x)
+    rng = numpy.random.default_rng(1)
+    V, W, b = rng.uniform(-1, 1, it.n), rng.uniform(-1, 1, it.n), rng.uniform(-1, 1, it.n)
+    V[3] = W[3] = b[3] = 0
+    C, b2 = 0.7, 0.3
+    y1, y2 = it.solve(jac, b, b2, V, W, C)
+    J = jac.tocsr().tolil()
+    J[3, :] = 0
+    J[:, 3] = 0
+    J[3, 3] = -1
+    J = J.tocsr()
+    r1 = J @ y1 + V * y2 - b
+    r2 = W @ y1 + C * y2 - b2
+    assert numpy.linalg.norm(r1) <= 1e-8 * numpy.linalg.norm(b) and abs(r2) < 1e-8

@@ -96,6 +96,7 @@ extern "C" void tfb_destroy(tfb_ctx* c) {
     cudaFree(c->d_row_ptr);
     cudaFree(c->d_col);
     cudaFree(c->d_flush);
+    tfb_solver_free(c->solver);
     for (int e = 0; e < 16; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -211,7 +212,6 @@ extern "C" int tfb_mat_create(tfb_ctx* c, tfb_mat** out) {
 extern "C" void tfb_mat_destroy(tfb_mat* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->desc.device);
-    tfb_solver_free(m->solver);
     cudaFree(m->d_vals);
     delete m;
 }

@@ -53,6 +53,7 @@ struct tfb_ctx {
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     cudaEvent_t ev[16] = {};
+    tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
     // multi-GPU
     int nranks = 1, rank = 0;
     void* nccl_comm = nullptr;
@@ -62,7 +63,6 @@ struct tfb_ctx {
 struct tfb_mat {
     tfb_ctx* ctx;
     double* d_vals = nullptr;
-    tfb_solver_state* solver = nullptr;
     uint64_t version = 0;       // bumped whenever values change (invalidates the preconditioner)
 };
 

@@ -202,3 +202,76 @@ def make_params(cfg, problem, parameters, nx, ny, nz, x, y, z):
         fidx += 1
     arrays.pop('amoc', None)
     return prm, arrays
+
+
+# ---------------------------------------------------------------------------------------
+# Fast-diagonalisation (FDM) data for the block preconditioner of the linear solver.
+# The diffusion part of every variable is a sum of Kronecker products of 1-D stencils
+# (Discretization.py:740-865 with the wall folds of BoundaryConditions.py:55-233,471-544):
+#     Op_v = coef_v * sum_a  K_a (x) prod_{b != a} M_b
+# with K_a symmetric tridiagonal and M_b diagonal.  With K q = lambda M q, Q^T M Q = I the
+# inverse is three dense transforms, a scaling by 1/(coef*(lx+ly+lz)) and three transforms back.
+# ---------------------------------------------------------------------------------------
+
+def fold_coefficients(cfg, prm):
+    '''(variable, axis, far) -> coefficient with which the recipe folds the ghost value into the
+    wall cell: -1 no-slip / Dirichlet, +1 free-slip / zero flux, Robin constants for heat flux.'''
+    out = {}
+    fidx = 0
+    for op in cfg.recipe:
+        if op[0] == 'wall':
+            _, axis, far, sign = op
+            for v in range(cfg.dof):
+                if v != cfg.p:
+                    out.setdefault((v, axis, far), float(sign))
+        elif op[0] == 'force':
+            _, axis, far, var, kind, arg = op
+            out[(cfg.var(var), axis, far)] = float(prm.bc_ca[fidx])
+            fidx += 1
+    return out
+
+
+def _pencil(kind, met, n, s_near, s_far):
+    hc, hu, rhc, rhp, rhm, rhu = met[0], met[1], met[2], met[3], met[4], met[5]
+    if kind == 'own':       # velocity along its own axis (_u_xx): faces 0..n-2, the wall face is not an unknown
+        m = n - 1
+        lower, upper, M = rhc[:m], rhp[:m], hu[:m]
+        diag = -(lower + upper)
+    else:                   # staggered direction of a velocity (_u_yy/_u_zz) or a cell-centred scalar (_C_xx)
+        m = n
+        lower, upper, M = rhm[:m], rhu[:m], hc[:m]
+        diag = -(lower + upper)
+        diag[0] += s_near * lower[0]
+        diag[m - 1] += s_far * upper[m - 1]
+    K = numpy.diag(diag)
+    if m > 1:
+        K += numpy.diag(upper[:m - 1], 1) + numpy.diag(lower[1:], -1)
+    K = (K + K.T) / 2       # symmetric by construction (1/hp[i] == 1/hc[i+1], 1/hu[i] == 1/hm[i+1])
+    ms = 1 / numpy.sqrt(M)
+    lam, Y = numpy.linalg.eigh(ms[:, None] * K * ms[None, :])
+    return numpy.ascontiguousarray(ms[:, None] * Y), numpy.ascontiguousarray(lam)
+
+
+def fdm_operators(cfg, prm, mets, nx, ny, nz):
+    '''[(var, axis, m, Q, lam, coef)] for tfb_fdm_set.'''
+    folds = fold_coefficients(cfg, prm)
+    n = (nx, ny, nz)
+    ndir = 3 if (cfg.dim == 3 and nz > 1) else 2
+    out = []
+    for v in range(cfg.dof):
+        if v == cfg.p:
+            coef = -1.0     # Lp = D M^-1 G = -(Neumann Laplacian)
+        elif v < cfg.dim:
+            coef = prm.c_visc
+        elif v == cfg.T:
+            coef = prm.c_T
+        else:
+            coef = prm.c_S
+        for a in range(ndir):
+            if v == cfg.p:
+                Q, lam = _pencil('cen', mets[a], n[a], 1.0, 1.0)
+            else:
+                kind = 'own' if (v < cfg.dim and a == v) else 'cen'
+                Q, lam = _pencil(kind, mets[a], n[a], folds.get((v, a, 0), 0.0), folds.get((v, a, 1), 0.0))
+            out.append((v, a, Q.shape[0], Q, lam, float(coef)))
+    return out

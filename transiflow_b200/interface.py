@@ -203,6 +203,19 @@ class Interface:
                                                self.x, self.y, self.z))
         check(_lib.lib().tfb_set_params(self._ctx, ctypes.byref(prm), fval, fdir, ptr(wind)))
         self._param_key = key
+        self._prm = prm
+        self._fdm_key = None
+
+    def _sync_solver(self):
+        '''Upload the fast-diagonalisation data of the preconditioner (grid + parameter dependent).'''
+        self._sync_params()
+        if self._fdm_key == self._param_key:
+            return
+        if self.config.fold:
+            raise NotImplementedError('solve() on semi-2D (dim=3, nz=1) grids')
+        for v, a, m, Q, lam, coef in hostprep.fdm_operators(self.config, self._prm, self._mets, self.nx, self.ny, self.nz):
+            check(_lib.lib().tfb_fdm_set(self._ctx, v, a, m, ptr(Q), ptr(lam), ctypes.c_double(coef)))
+        self._fdm_key = self._param_key
 
     # ---- vectors (SciPy.py:37-38; BaseInterface.py:84-92) ----
     def vector(self):
@@ -280,6 +293,7 @@ class Interface:
         return self._solve1(jac, rhs)
 
     def _solve1(self, jac, rhs):
+        self._sync_solver()
         b = as_f64(rhs).copy()
         prow = -1
         if self.dof > self.dim:
@@ -289,7 +303,7 @@ class Interface:
         o = _lib.TfbSolveOpts()
         o.tol = its.get('Convergence Tolerance', 1e-10)
         o.maxit = its.get('Maximum Iterations', 1000)
-        o.restart = its.get('Restart', 100)
+        o.restart = its.get('Restart', 300)
         o.pressure_row = prow
         o.precond = its.get('Preconditioner Id', 0)
         o.verbose = int(bool(self.parameters.get('Verbose', False)))
