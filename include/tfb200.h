@@ -124,6 +124,9 @@ int tfb_solve(tfb_mat* mat, const double* b, double* x, const tfb_solve_opts* op
  * (c_visc, c_T, c_S; -1 for the pressure Poisson operator D M^-1 G).  Computed by the host
  * (hostprep.fdm_operators) whenever grid or parameters change. */
 int tfb_fdm_set(tfb_ctx* ctx, int var, int axis, int m, const double* Q, const double* lam, double coef);
+/* A scalar whose diffusion operator is singular (zero-flux on every wall) is pinned at `cell`
+ * with diagonal `sign`, like the reference's "fix one salinity value" (Discretization.py:690-701). */
+int tfb_fdm_pin(tfb_ctx* ctx, int var, int64_t cell, double sign);
 /* z = P^-1 r with host vectors (diagnostics / tests of the preconditioner alone) */
 int tfb_precond_apply(tfb_mat* mat, const double* r, double* z, int pressure_row);
 

@@ -26,7 +26,12 @@ def newton(it, x0, tol=1e-10, maxit=10):
 
 def _iface(params, nx, ny, nz):
     from transiflow_b200 import Interface
-    return Interface(dict(params), nx, ny, nz)
+    params = dict(params)
+    if params.get('Problem Type') in ('AMOC', 'Rayleigh-Benard', 'Double Gyre'):
+        # the diffusion-based block preconditioner is weak for strongly coupled buoyancy / Coriolis
+        # terms; these small systems are solved by FULL (un-restarted) GMRES -- see DESIGN.md
+        params['Iterative Solver'] = {'Maximum Iterations': 2000, 'Restart': 2000}
+    return Interface(params, nx, ny, nz)
 
 
 def test_solve_manufactured_solution():

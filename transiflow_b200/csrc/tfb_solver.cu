@@ -34,6 +34,8 @@ struct FdmVar {
     double* lam[3] = {nullptr, nullptr, nullptr}; // m generalized eigenvalues
     double coef = 1.0;
     double maxden = 0.0;
+    long long pin_cell = -1;      // singular (all-Neumann) scalar operators are pinned at one cell
+    double pin_sign = 1.0;        // diagonal of the pinned row (+1 identity, -1 for the AMOC salinity pin)
 };
 
 struct tfb_solver_state {
@@ -285,10 +287,10 @@ __global__ void k_pin_rhs(double* rp, long long pc, double* scal) {   // scal[0]
     scal[1] = r0;
     rp[pc] = -(scal[0] - r0);
 }
-__global__ void k_pin_shift(long long n, double* q, long long pc, const double* __restrict__ scal, double* qpin) {
+__global__ void k_pin_shift(long long n, double* q, long long pc, const double* __restrict__ scal, double* qpin, double sign) {
     const double q0 = *qpin;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        q[i] = (i == pc) ? scal[1] : q[i] - q0;
+        q[i] = (i == pc) ? sign * scal[1] : q[i] - q0;
 }
 __global__ void k_copy1(const double* src, double* dst) { *dst = *src; }
 
@@ -343,7 +345,7 @@ static int fdm_solve(tfb_ctx* c, int v, double* in, double* tmp, double* out, do
 }
 
 // pinned Poisson solve on SoA arrays: q = Lp_pinned^-1 rp ; rp is clobbered
-static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, double* rp, double* tmp, double* q) {
+static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, double* rp, double* tmp, double* q, double pin_sign = 1.0) {
     tfb_solver_state* s = c->solver;
     const long long ncell = c->n_local / c->desc.dof;
     if (pin_cell >= 0) {
@@ -356,7 +358,7 @@ static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, double* rp, d
     if (fdm_solve(c, pvar, rp, tmp, q, nullptr)) return -1;
     if (pin_cell >= 0) {
         k_copy1<<<1, 1, 0, c->stream>>>(q + pin_cell, s->d_scal + 2);
-        k_pin_shift<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, q, pin_cell, s->d_scal, s->d_scal + 2);
+        k_pin_shift<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, q, pin_cell, s->d_scal, s->d_scal + 2, pin_sign);
         TFB_LAUNCHED(); TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
@@ -379,7 +381,9 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
     if (smask) {
         for (int v = pv + 1; v < dof; v++) {
             k_deinterleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, r, c0);
-            if (fdm_solve(c, v, c0, c1, c2, nullptr)) return -1;
+            if (s->var[v].pin_cell >= 0) {
+                if (poisson_solve(c, v, s->var[v].pin_cell, c0, c1, c2, s->var[v].pin_sign)) return -1;
+            } else if (fdm_solve(c, v, c0, c1, c2, nullptr)) return -1;
             k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
             TFB_LAUNCHED(); TFB_LAUNCHED();
         }
@@ -438,6 +442,14 @@ extern "C" int tfb_fdm_set(tfb_ctx* c, int var, int axis, int m, const double* Q
     double mx = 0.0;
     for (int i = 0; i < m; i++) mx = std::max(mx, fabs(lam[i]));
     f.maxden = std::max(f.maxden, 3.0 * mx);
+    return 0;
+}
+
+extern "C" int tfb_fdm_pin(tfb_ctx* c, int var, int64_t cell, double sign) {
+    TFB_CHECK(c && var >= 0 && var < TFB_MAXVAR, "bad arguments");
+    tfb_solver_state* s = solver_of(c);
+    s->var[var].pin_cell = cell;
+    s->var[var].pin_sign = sign;
     return 0;
 }
 

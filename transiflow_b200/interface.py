@@ -215,6 +215,8 @@ class Interface:
             raise NotImplementedError('solve() on semi-2D (dim=3, nz=1) grids')
         for v, a, m, Q, lam, coef in hostprep.fdm_operators(self.config, self._prm, self._mets, self.nx, self.ny, self.nz):
             check(_lib.lib().tfb_fdm_set(self._ctx, v, a, m, ptr(Q), ptr(lam), ctypes.c_double(coef)))
+        if self.problem == recipes.AMOC:
+            check(_lib.lib().tfb_fdm_pin(self._ctx, self.config.S, ctypes.c_int64(0), ctypes.c_double(-1.0)))
         self._fdm_key = self._param_key
 
     # ---- vectors (SciPy.py:37-38; BaseInterface.py:84-92) ----
@@ -303,7 +305,10 @@ class Interface:
         o = _lib.TfbSolveOpts()
         o.tol = its.get('Convergence Tolerance', 1e-10)
         o.maxit = its.get('Maximum Iterations', 1000)
-        o.restart = its.get('Restart', 300)
+        # 180 GB of HBM: keep the whole Krylov space whenever it fits (no restart), the basis
+        # needs 16 bytes per unknown and iteration
+        fit = max(20, int(100e9 // (16 * self.n)))
+        o.restart = min(its.get('Restart', 500), fit)
         o.pressure_row = prow
         o.precond = its.get('Preconditioner Id', 0)
         o.verbose = int(bool(self.parameters.get('Verbose', False)))
