@@ -18,6 +18,7 @@
 // The pressure is pinned at the reference's pressure row (SciPy.py:95-106,212-216): row -> -1
 // on the diagonal, column dropped; this is applied on the fly inside the SpMV kernels.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -38,8 +39,24 @@ struct FdmVar {
     double pin_sign = 1.0;        // diagonal of the pinned row (+1 identity, -1 for the AMOC salinity pin)
 };
 
+// Compact copy of the entries of J with (row variable, column variable) in given masks: the
+// gradient G, divergence D and buoyancy B blocks hold 2..6 entries per row, so multiplying with
+// them through the full 17-entries-per-row matrix would waste ~90 % of the traffic.
+struct SubCsr {
+    unsigned rowmask = 0, colmask = 0;
+    int* row_ptr = nullptr;   // n_local + 1
+    int* col = nullptr;
+    int* src = nullptr;       // position in the parent values array
+    double* vals = nullptr;
+    int nnz = 0;
+    uint64_t version = ~0ull; // matrix version the values were copied from
+    const tfb_mat* owner = nullptr;
+};
+
 struct tfb_solver_state {
     FdmVar var[TFB_MAXVAR];
+    SubCsr subG, subD, subB;
+    int sub_prow = -2;
     double* d_mass = nullptr;     // velocity mass diagonal (LSC scaling), n_local
     double* comp[3] = {};         // SoA work arrays, ncell each
     double* vec[6] = {};          // interleaved work vectors, n_local each
@@ -54,6 +71,7 @@ void tfb_solver_free(tfb_solver_state* s) {
     if (!s) return;
     for (auto& v : s->var)
         for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); }
+    for (SubCsr* q : {&s->subG, &s->subD, &s->subB}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
     cudaFree(s->d_mass);
     for (auto p : s->comp) cudaFree(p);
     for (auto p : s->vec) cudaFree(p);
@@ -118,6 +136,47 @@ static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, un
     return 0;
 }
 
+static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned colmask);
+// ---- sub-matrix extraction (structure once per pattern and pin; values once per Jacobian) ----
+__global__ void k_sub_count(long long nrows, int dof, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                            int prow, unsigned rowmask, unsigned colmask, int* __restrict__ counts) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int cnt = 0;
+    if (((rowmask >> (row % dof)) & 1u) && row != prow)
+        for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++) {
+            const int cidx = col[e];
+            if (cidx != prow && ((colmask >> (cidx % dof)) & 1u)) cnt++;
+        }
+    counts[row] = cnt;
+}
+__global__ void k_sub_fill(long long nrows, int dof, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                           int prow, unsigned rowmask, unsigned colmask, const int* __restrict__ sub_ptr,
+                           int* __restrict__ sub_col, int* __restrict__ sub_src) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    if (!(((rowmask >> (row % dof)) & 1u) && row != prow)) return;
+    int pos = sub_ptr[row];
+    for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++) {
+        const int cidx = col[e];
+        if (cidx != prow && ((colmask >> (cidx % dof)) & 1u)) { sub_col[pos] = cidx; sub_src[pos] = e; pos++; }
+    }
+}
+__global__ void k_sub_gather(int nnz, const int* __restrict__ src, const double* __restrict__ vals, double* __restrict__ out) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += gridDim.x * blockDim.x) out[e] = vals[src[e]];
+}
+// y = S x (optionally / rowscale) : one thread per row, rows are 0..6 entries long
+__global__ void k_sub_spmv(long long nrows, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                           const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                           const double* __restrict__ rowscale) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    double s = 0.0;
+    for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++) s += vals[e] * x[col[e]];
+    if (rowscale) s /= rowscale[row];
+    y[row] = s;
+}
+
 // ------------------------------------------------------------------------------------
 // vector kernels
 // ------------------------------------------------------------------------------------
@@ -175,6 +234,66 @@ __global__ void __launch_bounds__(256) k_multi_axpy(long long n, const double* _
             if (v < nv) a += hv[v] * V[v * ld + i];
         w[i] += sign * a;
     }
+}
+
+static inline unsigned vec_blocks(long long n);
+static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned colmask) {
+    const long long n = c->n_local;
+    S.rowmask = rowmask; S.colmask = colmask;
+    cudaFree(S.row_ptr); cudaFree(S.col); cudaFree(S.src); cudaFree(S.vals);
+    S.row_ptr = S.col = S.src = nullptr; S.vals = nullptr;
+    int* counts = nullptr;
+    TFB_CUDA(cudaMalloc(&counts, sizeof(int) * (n + 1)));
+    TFB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), c->stream));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    k_sub_count<<<nb, 256, 0, c->stream>>>(n, c->desc.dof, c->d_row_ptr, c->d_col, prow, rowmask, colmask, counts);
+    TFB_LAUNCHED();
+    // exclusive scan on the host side of a small int array is avoided: reuse CUB through a tiny kernel-free path
+    std::vector<int> h(n + 1);
+    TFB_CUDA(cudaMemcpyAsync(h.data(), counts, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    long long acc = 0;
+    for (long long r = 0; r <= n; r++) { const int v = h[r]; h[r] = (int)acc; acc += v; }
+    S.nnz = (int)acc;
+    TFB_CUDA(cudaMalloc(&S.row_ptr, sizeof(int) * (n + 1)));
+    TFB_CUDA(cudaMemcpyAsync(S.row_ptr, h.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+    const size_t cap = (size_t)std::max(S.nnz, 1);
+    TFB_CUDA(cudaMalloc(&S.col, sizeof(int) * cap));
+    TFB_CUDA(cudaMalloc(&S.src, sizeof(int) * cap));
+    TFB_CUDA(cudaMalloc(&S.vals, sizeof(double) * cap));
+    k_sub_fill<<<nb, 256, 0, c->stream>>>(n, c->desc.dof, c->d_row_ptr, c->d_col, prow, rowmask, colmask, S.row_ptr, S.col, S.src);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(counts);
+    S.version = ~0ull;
+    S.owner = nullptr;
+    return 0;
+}
+static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
+    tfb_solver_state* s = c->solver;
+    const int dof = c->desc.dof, dim = c->desc.dim;
+    const unsigned velmask = (1u << dim) - 1u, pmask = 1u << dim, smask = ((1u << dof) - 1u) & ~(velmask | pmask);
+    if (s->sub_prow != prow || !s->subG.row_ptr) {
+        if (sub_build(c, s->subG, prow, velmask, pmask)) return -1;
+        if (sub_build(c, s->subD, prow, pmask, velmask)) return -1;
+        if (smask && sub_build(c, s->subB, prow, velmask, smask)) return -1;
+        s->sub_prow = prow;
+    }
+    for (SubCsr* q : {&s->subG, &s->subD, &s->subB}) {
+        if (!q->row_ptr || q->nnz == 0) continue;
+        if (q->owner == m && q->version == m->version) continue;
+        k_sub_gather<<<vec_blocks(q->nnz), 256, 0, c->stream>>>(q->nnz, q->src, m->d_vals, q->vals);
+        TFB_LAUNCHED();
+        q->owner = m; q->version = m->version;
+    }
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+static int sub_spmv(tfb_ctx* c, const SubCsr& S, const double* x, double* y, const double* rowscale = nullptr) {
+    k_sub_spmv<<<(unsigned)((c->n_local + 255) / 256), 256, 0, c->stream>>>(c->n_local, S.row_ptr, S.col, S.vals, x, y, rowscale);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 static inline unsigned vec_blocks(long long n) { return (unsigned)std::min<long long>((n + 255) / 256, 148 * 16); }
@@ -294,8 +413,58 @@ __global__ void k_pin_shift(long long n, double* q, long long pc, const double* 
 }
 __global__ void k_copy1(const double* src, double* dst) { *dst = *src; }
 
+// ---- optional cuBLAS path for the FDM transforms (they are plain dense GEMMs) ----
+// libcublas is dlopen'ed; when it is absent the hand-written k_axis_gemm above is used.
+#include <dlfcn.h>
+typedef void* cublasHandle_t_;
+static struct {
+    int state;   // 0 untried, 1 ok, -1 unavailable
+    void* lib;
+    cublasHandle_t_ h;
+    int (*Create)(cublasHandle_t_*);
+    int (*SetStream)(cublasHandle_t_, cudaStream_t);
+    int (*DgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const double*, const double*, int, long long,
+                               const double*, int, long long, const double*, double*, int, long long, int);
+} g_blas;
+
+static bool blas_ready(tfb_ctx* c) {
+    if (g_blas.state == 0) {
+        g_blas.state = -1;
+        const char* off = getenv("TFB_NO_CUBLAS");
+        if (!(off && off[0] == '1')) {
+            const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
+            for (const char* nme : names) {
+                g_blas.lib = dlopen(nme, RTLD_NOW | RTLD_LOCAL);
+                if (g_blas.lib) break;
+            }
+            if (g_blas.lib) {
+                *(void**)(&g_blas.Create) = dlsym(g_blas.lib, "cublasCreate_v2");
+                *(void**)(&g_blas.SetStream) = dlsym(g_blas.lib, "cublasSetStream_v2");
+                *(void**)(&g_blas.DgemmStridedBatched) = dlsym(g_blas.lib, "cublasDgemmStridedBatched");
+                if (g_blas.Create && g_blas.SetStream && g_blas.DgemmStridedBatched && g_blas.Create(&g_blas.h) == 0) g_blas.state = 1;
+            }
+        }
+    }
+    if (g_blas.state == 1) g_blas.SetStream(g_blas.h, c->stream);
+    return g_blas.state == 1;
+}
+
 static int axis_gemm(tfb_ctx* c, bool trans, const double* A, double* C, const double* Q, int ldq, int M, int K, int N,
                      long long sm, long long sk, long long sb, int batches) {
+    if (blas_ready(c)) {
+        const double one = 1.0, zero = 0.0;
+        int rc;
+        enum { OP_N = 0, OP_T = 1 };
+        if (sk == 1)   // rows of A are the lines: C_cm(N x M) = op(Q_cm) * A_cm(K x M)
+            rc = g_blas.DgemmStridedBatched(g_blas.h, trans ? OP_T : OP_N, OP_N, N, M, K, &one, Q, ldq, 0, A, (int)sm, sb,
+                                            &zero, C, (int)sm, sb, batches);
+        else           // columns of A_cm are the lines' entries: C_cm(M x N) = A_cm(M x K) * op(Q_cm)
+            rc = g_blas.DgemmStridedBatched(g_blas.h, OP_N, trans ? OP_N : OP_T, M, N, K, &one, A, (int)sk, sb, Q, ldq, 0,
+                                            &zero, C, (int)sk, sb, batches);
+        TFB_LAUNCHED();
+        TFB_CHECK(rc == 0, "cublasDgemmStridedBatched failed");
+        return 0;
+    }
     dim3 grid((M + 63) / 64, (N + 63) / 64, batches);
     if (trans) k_axis_gemm<true><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
     else k_axis_gemm<false><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
@@ -387,7 +556,7 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
             k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
             TFB_LAUNCHED(); TFB_LAUNCHED();
         }
-        if (spmv(c, m, z, ta, prow, velmask, smask)) return -1;          // B s
+        if (sub_spmv(c, s->subB, z, ta)) return -1;                      // B s
         k_axpy<<<vec_blocks(n), 256, 0, c->stream>>>(n, -1.0, ta, ru);
         TFB_LAUNCHED();
     }
@@ -397,9 +566,9 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
     TFB_CUDA(cudaMemsetAsync(ta, 0, sizeof(double) * n, c->stream));
     k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, 1.0);
     TFB_LAUNCHED(); TFB_LAUNCHED();
-    if (spmv(c, m, ta, tb, prow, velmask, pmask, s->d_mass)) return -1;   // M^-1 G t
+    if (sub_spmv(c, s->subG, ta, tb, s->d_mass)) return -1;              // M^-1 G t
     if (spmv(c, m, tb, tc, prow, velmask, velmask, s->d_mass)) return -1; // M^-1 A (.)
-    if (spmv(c, m, tc, ta, prow, pmask, velmask)) return -1;             // D (.)
+    if (sub_spmv(c, s->subD, tc, ta)) return -1;                         // D (.)
     k_deinterleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, ta, c0);
     if (poisson_solve(c, pv, pin_cell, c0, c1, c2)) return -1;
     k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, z, -1.0);  // dp into z
@@ -408,7 +577,7 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
     TFB_CUDA(cudaMemsetAsync(ta, 0, sizeof(double) * n, c->stream));
     k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, -1.0);
     TFB_LAUNCHED();
-    if (spmv(c, m, ta, tb, prow, velmask, pmask)) return -1;             // G dp
+    if (sub_spmv(c, s->subG, ta, tb)) return -1;                         // G dp
     k_axpy<<<vec_blocks(n), 256, 0, c->stream>>>(n, -1.0, tb, ru);
     TFB_LAUNCHED();
     for (int v = 0; v < dim; v++) {
@@ -524,6 +693,7 @@ extern "C" int tfb_precond_apply(tfb_mat* m, const double* r, double* z, int pre
     if (ensure_buffers(c, 0)) return -1;
     tfb_solver_state* s = c->solver;
     TFB_CUDA(cudaMemcpyAsync(s->vec[4], r, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    if (sub_refresh(c, m, pressure_row)) return -1;
     if (apply_precond(c, m, pressure_row, s->vec[4], s->vec[5])) return -1;
     TFB_CUDA(cudaMemcpyAsync(z, s->vec[5], sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(cudaStreamSynchronize(c->stream));
@@ -544,6 +714,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
     TFB_CUDA(cudaEventRecord(e0, c->stream));
 
+    if (sub_refresh(c, m, prow)) return -1;
     double* d_b = s->vec[4];
     double* d_x = s->vec[5];
     TFB_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
@@ -554,7 +725,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     std::vector<double> H((size_t)(mk + 1) * mk, 0.0), g(mk + 1), cs(mk), sn(mk), hcol(mk + 2), y(mk);
     auto Hx = [&](int i, int j) -> double& { return H[(size_t)j * (mk + 1) + i]; };
 
-    int total_its = 0, converged = 0;
+    int total_its = 0, converged = 0, reorth = 0;
     double bnorm = 0.0, relres = 1.0;
     {
         if (multi_dot(c, d_b, 1, d_b, d_h)) return -1;
@@ -598,19 +769,27 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             double* w = V + (size_t)(j + 1) * n;
             if (apply_precond(c, m, prow, vj, zj)) return -1;
             if (spmv(c, m, zj, w, prow)) return -1;
-            // classical Gram-Schmidt, twice (fused multi-dots; one pass over the basis each)
+            // classical Gram-Schmidt with fused multi-dots (one pass over the basis per sweep); the
+            // second sweep only runs when the first one cancelled most of w (DGKS criterion)
+            if (multi_dot(c, w, 1, w, d_h + mk + 2)) return -1;            // |w|^2 before
             if (multi_dot(c, V, j + 1, w, d_h)) return -1;
             if (multi_axpy(c, V, j + 1, d_h, -1.0, w)) return -1;
+            if (multi_dot(c, w, 1, w, d_h + mk + 1)) return -1;            // |w|^2 after
+            double nrm[2];
             TFB_CUDA(cudaMemcpyAsync(hcol.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
+            TFB_CUDA(cudaMemcpyAsync(nrm, d_h + mk + 1, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
             TFB_CUDA(cudaStreamSynchronize(c->stream));
-            if (multi_dot(c, V, j + 1, w, d_h)) return -1;
-            if (multi_axpy(c, V, j + 1, d_h, -1.0, w)) return -1;
-            std::vector<double> h2(j + 1);
-            TFB_CUDA(cudaMemcpyAsync(h2.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
-            if (multi_dot(c, w, 1, w, d_h + mk + 1)) return -1;
-            double hn2 = 0.0;
-            TFB_CUDA(cudaMemcpyAsync(&hn2, d_h + mk + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            TFB_CUDA(cudaStreamSynchronize(c->stream));
+            std::vector<double> h2(j + 1, 0.0);
+            double hn2 = nrm[0];
+            if (nrm[0] < 0.25 * nrm[1]) {
+                if (multi_dot(c, V, j + 1, w, d_h)) return -1;
+                if (multi_axpy(c, V, j + 1, d_h, -1.0, w)) return -1;
+                TFB_CUDA(cudaMemcpyAsync(h2.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
+                if (multi_dot(c, w, 1, w, d_h + mk + 1)) return -1;
+                TFB_CUDA(cudaMemcpyAsync(&hn2, d_h + mk + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                TFB_CUDA(cudaStreamSynchronize(c->stream));
+                reorth++;
+            }
             const double hn = sqrt(hn2);
             for (int i = 0; i <= j; i++) Hx(i, j) = hcol[i] + h2[i];
             Hx(j + 1, j) = hn;
@@ -663,7 +842,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
         info->iters = total_its;
         info->converged = relres <= o->tol * 10.0;
         info->relres = relres;
-        info->setup_ms = 0.f;
+        info->setup_ms = (float)reorth;   // number of second Gram-Schmidt sweeps (diagnostic)
         info->solve_ms = ms;
     }
     return relres <= o->tol * 10.0 ? 0 : 1;
