@@ -152,15 +152,8 @@ def main():
     it = Interface(dict(PARAMS), grid, grid, nz, device=local_rank, slab=(rank * grid, (rank + 1) * grid)) \
         if world > 1 else Interface(dict(PARAMS), grid, grid, grid, device=local_rank)
     if world > 1:
-        import torch
-        idbuf = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            raw = (ctypes.c_uint8 * 128)()
-            check(L.tfb_nccl_unique_id(raw))
-            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
-        dist.broadcast(idbuf, 0)
-        raw = (ctypes.c_uint8 * 128)(*idbuf.tolist())
-        check(L.tfb_comm_init(it._ctx, world, rank, raw))
+        from transiflow_b200 import parallel
+        parallel.init_comm(it, dist, rank, world)
 
     n_local = it.n_local
     cells_local = n_local // it.dof
