@@ -40,8 +40,11 @@ def main():
         gv, gc, gp = compress(jac.values(), col, row_ptr)
         coA, jcoA, begA = orc.jacobian(state)
         e0, e1 = begA[r0], begA[r1]
-        good = (numpy.array_equal(gp, begA[r0:r1 + 1] - e0) and numpy.array_equal(gc, jcoA[e0:e1])
-                and numpy.array_equal(gv, coA[e0:e1]) and numpy.array_equal(f, orc.rhs(state)[r0:r1]))
+        parts = {'row_ptr': numpy.array_equal(gp, begA[r0:r1 + 1] - e0), 'cols': numpy.array_equal(gc, jcoA[e0:e1]),
+                 'values': numpy.array_equal(gv, coA[e0:e1]), 'rhs': numpy.array_equal(f, orc.rhs(state)[r0:r1])}
+        good = all(parts.values())
+        if not good:
+            print('rank', rank, parts, flush=True)
         print('rank %d/%d %s slab [%d,%d): %s' % (rank, world, params.get('Problem Type', 'LDC'), k0, k1,
                                                  'bit-identical to the oracle' if good else 'MISMATCH'), flush=True)
         ok = ok and good

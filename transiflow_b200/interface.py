@@ -221,7 +221,7 @@ class Interface:
 
     # ---- vectors (SciPy.py:37-38; BaseInterface.py:84-92) ----
     def vector(self):
-        return numpy.zeros(self.n)
+        return numpy.zeros(self.n_local)
 
     def vector_from_array(self, array):
         return array
@@ -243,7 +243,7 @@ class Interface:
         '''F(x); replaces Discretization.rhs (Discretization.py:367-390).'''
         self._sync_params()
         state = as_f64(state)
-        out = numpy.empty(self.n)
+        out = numpy.empty(self.n_local)
         check(_lib.lib().tfb_rhs(self._ctx, ptr(state), ptr(out)))
         return out
 
@@ -260,7 +260,7 @@ class Interface:
         self._sync_params()
         state = as_f64(state)
         mat = DeviceMatrix(self)
-        out = numpy.empty(self.n)
+        out = numpy.empty(self.n_local)
         check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
         return mat, out
 
