@@ -100,6 +100,10 @@ int64_t tfb_launch_count(void);
 /* y = A x with host vectors (CrsMatrix.matvec / `jac @ x` of the SciPy backend) */
 int tfb_spmv(tfb_mat* mat, const double* x, double* y);
 
+/* average device time (ms) of `reps` launches of y = J x (masked != 0: the velocity-velocity block
+ * used by the preconditioner) with resident operands; measurement helper for bench.py */
+int tfb_spmv_bench(tfb_mat* mat, int reps, int masked, float* ms_out);
+
 /* Interface.solve (interface/SciPy.py:204-315): solve mat * x = b with the pressure pinned at
  * local row `pressure_row` (<0: no pin) by preconditioned FGMRES to ||r||/||b|| <= tol.
  * Returns 0 converged, 1 not converged (x holds the best iterate). */

@@ -48,6 +48,21 @@ def main():
         print('rank %d/%d %s slab [%d,%d): %s' % (rank, world, params.get('Problem Type', 'LDC'), k0, k1,
                                                  'bit-identical to the oracle' if good else 'MISMATCH'), flush=True)
         ok = ok and good
+        if params.get('Problem Type') is None:
+            # distributed Newton update vs the oracle's pinned SuperLU solve of the whole system
+            from oracle.tf_oracle import direct_solve
+            x = numpy.zeros(orc.n)
+            for step in range(2):
+                jac, f = it.jacobian_rhs(x[r0:r1].copy())
+                dx = it.solve(jac, -f)
+                want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
+                err = numpy.abs(dx - want[r0:r1]).max() / numpy.abs(want).max()
+                good = err <= 1e-8 and it.last_solve['converged']
+                print('rank %d/%d distributed solve step %d: %d its, relres %.1e, err vs spsolve %.1e -> %s' % (
+                    rank, world, step, it.last_solve['iterations'], it.last_solve['relres'], err, 'ok' if good else 'MISMATCH'), flush=True)
+                ok = ok and good
+                # all ranks advance the same global state (gather through the oracle's full solution)
+                x = x + want
     dist.barrier()
     sys.exit(0 if ok else 1)
 

@@ -107,3 +107,25 @@ def test_bordered_solve():
     r1 = J @ y1 + V * y2 - b
     r2 = W @ y1 + C * y2 - b2
     assert numpy.linalg.norm(r1) <= 1e-8 * numpy.linalg.norm(b) and abs(r2) < 1e-8
+
+
+def test_time_integration_operators():
+    """TimeIntegration._newton (TimeIntegration.py:40-73) builds `jacobian(x) - mass / (theta*dt)` and
+    `mass @ v` with the backend's matrix types and hands the result to solve()."""
+    it = _iface({'Reynolds Number': 100}, 8, 8, 8)
+    x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
+    jac, mass = it.jacobian(x), it.mass_matrix()
+    theta, dt = 1.0, 0.1
+    A = jac - mass / (theta * dt)
+    v = numpy.random.default_rng(1).uniform(-1, 1, it.n)
+    b = mass @ v + it.rhs(x)
+    b[3] = 0
+    y = it.solve(A, b)
+    assert it.last_solve['converged']
+    from scipy.sparse import csr_matrix
+    Ah = csr_matrix(A).tolil()
+    Ah[3, :] = 0
+    Ah[:, 3] = 0
+    Ah[3, 3] = -1
+    r = Ah.tocsr() @ y - b
+    assert numpy.linalg.norm(r) <= 1e-8 * numpy.linalg.norm(b)

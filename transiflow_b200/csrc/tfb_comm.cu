@@ -2,6 +2,7 @@
 // dlopen so that single-GPU use has no NCCL dependency at all.
 #include <dlfcn.h>
 #include <string.h>
+#include <vector>
 #include "tfb_internal.h"
 
 typedef struct { char internal[128]; } ncclUniqueId_t;
@@ -61,6 +62,39 @@ extern "C" int tfb_comm_init(tfb_ctx* c, int nranks, int rank, const uint8_t id[
     ncclComm_t_ comm;
     TFB_NCCL(nccl.CommInitRank(&comm, nranks, u, rank));
     c->nccl_comm = comm;
+    // every rank learns every slab: k0 of rank r in slab_k0[r], slab_k0[nranks] = nz
+    TFB_CHECK(nranks <= TFB_MAX_RANKS, "too many ranks");
+    double* d = nullptr;
+    TFB_CUDA(cudaMalloc(&d, sizeof(double) * nranks));
+    std::vector<double> h(nranks, 0.0);
+    h[rank] = (double)c->desc.k0;
+    TFB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(double) * nranks, cudaMemcpyHostToDevice, c->stream));
+    TFB_NCCL(nccl.AllReduce(d, d, (size_t)nranks, NCCL_FLOAT64, NCCL_SUM, comm, c->stream));
+    TFB_CUDA(cudaMemcpyAsync(h.data(), d, sizeof(double) * nranks, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    for (int r = 0; r < nranks; r++) c->slab_k0[r] = (int)h[r];
+    c->slab_k0[nranks] = c->desc.nz;
+    for (int r = 0; r < nranks; r++)
+        TFB_CHECK(c->slab_k0[r] < c->slab_k0[r + 1], "z-slabs must be ordered by rank and non-empty");
+    return 0;
+}
+
+// personalised all-to-all of doubles (counts / displacements in elements), own block by memcpy
+int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
+                  double* recv, const long long* rcount, const long long* rdispl) {
+    TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    TFB_NCCL(nccl.GroupStart());
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) continue;
+        if (scount[r] > 0) TFB_NCCL(nccl.Send(send + sdispl[r], (size_t)scount[r], NCCL_FLOAT64, r, comm, c->stream));
+        if (rcount[r] > 0) TFB_NCCL(nccl.Recv(recv + rdispl[r], (size_t)rcount[r], NCCL_FLOAT64, r, comm, c->stream));
+    }
+    TFB_NCCL(nccl.GroupEnd());
+    TFB_CUDA(cudaMemcpyAsync(recv + rdispl[c->rank], send + sdispl[c->rank], sizeof(double) * scount[c->rank],
+                             cudaMemcpyDeviceToDevice, c->stream));
+    TFB_LAUNCHED();
     return 0;
 }
 

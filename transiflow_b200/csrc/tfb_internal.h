@@ -24,6 +24,7 @@ int tfb_fail(const char* file, int line, const char* what, const char* detail);
     } while (0)
 #define TFB_LAUNCHED() (g_tfb_launches++)
 
+#define TFB_MAX_RANKS 16
 struct tfb_solver_state;  // tfb_solver.cu
 
 struct tfb_ctx {
@@ -56,6 +57,7 @@ struct tfb_ctx {
     tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
     // multi-GPU
     int nranks = 1, rank = 0;
+    int slab_k0[TFB_MAX_RANKS + 1] = {};   // first plane of every rank's slab (after tfb_comm_init)
     void* nccl_comm = nullptr;
     TfbGrid grid() const;
 };
@@ -68,4 +70,7 @@ struct tfb_mat {
 
 int tfb_build_pattern(tfb_ctx* ctx);
 int tfb_halo_exchange(tfb_ctx* ctx, double* d_vec_with_ghosts);
+int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
+int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
+                  double* recv, const long long* rcount, const long long* rdispl);
 void tfb_solver_free(tfb_solver_state* s);

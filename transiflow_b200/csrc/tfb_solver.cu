@@ -61,6 +61,15 @@ struct tfb_solver_state {
     double* comp[3] = {};         // SoA work arrays, ncell each
     double* vec[6] = {};          // interleaved work vectors, n_local each
     double* d_scal = nullptr;     // small device scalars
+    // z-slab runs: ghosted copy of a vector, pencil-layout work arrays, all-to-all staging
+    double* xg = nullptr;
+    double* pen[2] = {nullptr, nullptr};
+    double* sbuf = nullptr;
+    double* rbuf = nullptr;
+    int j0s[TFB_MAX_RANKS + 1] = {};   // y-chunk of every rank in the pencil layout
+    long long a2a_cnt_slab[TFB_MAX_RANKS] = {}, a2a_dsp_slab[TFB_MAX_RANKS] = {};   // slab side (packed by y-chunk)
+    long long a2a_cnt_pen[TFB_MAX_RANKS] = {}, a2a_dsp_pen[TFB_MAX_RANKS] = {};     // pencil side (planes of each rank)
+    bool dist_ready = false;
     double* d_V = nullptr;        // Krylov basis  (m+1) x n
     double* d_Z = nullptr;        // preconditioned basis  m x n
     double* d_h = nullptr;        // dot products
@@ -75,6 +84,7 @@ void tfb_solver_free(tfb_solver_state* s) {
     cudaFree(s->d_mass);
     for (auto p : s->comp) cudaFree(p);
     for (auto p : s->vec) cudaFree(p);
+    cudaFree(s->xg); cudaFree(s->pen[0]); cudaFree(s->pen[1]); cudaFree(s->sbuf); cudaFree(s->rbuf);
     cudaFree(s->d_scal); cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h);
     delete s;
 }
@@ -93,7 +103,7 @@ template <bool MASKED>
 __global__ void __launch_bounds__(256)
 tfb_spmv_kernel(long long nrows, int dof, const int* __restrict__ row_ptr, const int* __restrict__ col,
                 const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                int prow, unsigned rowmask, unsigned colmask, const double* __restrict__ rowscale) {
+                int prow_local, int prow, unsigned rowmask, unsigned colmask, const double* __restrict__ rowscale) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long row = gt >> 3;
     const int lane = threadIdx.x & 7;
@@ -101,7 +111,7 @@ tfb_spmv_kernel(long long nrows, int dof, const int* __restrict__ row_ptr, const
     double s = 0.0;
     const int rv = (int)(row % dof);
     const bool active = !MASKED || ((rowmask >> rv) & 1u);
-    if (active && row != prow) {
+    if (active && row != prow_local) {
         const int e0 = row_ptr[row], e1 = row_ptr[row + 1];
         for (int e = e0 + lane; e < e1; e += 8) {
             const int cidx = col[e];
@@ -114,23 +124,44 @@ tfb_spmv_kernel(long long nrows, int dof, const int* __restrict__ row_ptr, const
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     if (lane == 0) {
-        if (!MASKED && row == prow) s = -x[prow];
+        if (!MASKED && row == prow_local) s = -x[prow];
         if (MASKED && rowscale) s = active ? s / rowscale[row] : 0.0;
         y[row] = s;
     }
+}
+
+// local row index of the (global) pinned row, -1 if another rank owns it
+static inline int local_prow(const tfb_ctx* c, int prow) {
+    if (prow < 0) return -1;
+    const long long l = (long long)prow - c->row0;
+    return (l >= 0 && l < c->n_local) ? (int)l : -1;
+}
+
+// Column indices are GLOBAL.  Single GPU: x itself.  z-slabs: x is copied between two ghost
+// planes, the halos are exchanged (NCCL) and the kernels index a pointer shifted by the first
+// owned row, so that global columns address the ghosted copy.
+static int ghosted(tfb_ctx* c, const double* x, const double** xs) {
+    if (c->nranks == 1) { *xs = x; return 0; }
+    tfb_solver_state* s = c->solver;
+    TFB_CUDA(cudaMemcpyAsync(s->xg + c->plane_rows, x, sizeof(double) * c->n_local, cudaMemcpyDeviceToDevice, c->stream));
+    if (tfb_halo_exchange(c, s->xg)) return -1;
+    *xs = s->xg + c->plane_rows - c->row0;
+    return 0;
 }
 
 static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, unsigned rowmask = 0, unsigned colmask = 0,
                 const double* rowscale = nullptr) {
     const long long threads = c->n_local * 8;
     const unsigned nb = (unsigned)((threads + 255) / 256);
-    // x is indexed by GLOBAL column; single-GPU: global == local
+    const double* xs = nullptr;
+    if (ghosted(c, x, &xs)) return -1;
+    const int pl = local_prow(c, prow);
     if (rowmask)
-        tfb_spmv_kernel<true><<<nb, 256, 0, c->stream>>>(c->n_local, c->desc.dof, c->d_row_ptr, c->d_col, m->d_vals, x, y,
-                                                        prow, rowmask, colmask, rowscale);
+        tfb_spmv_kernel<true><<<nb, 256, 0, c->stream>>>(c->n_local, c->desc.dof, c->d_row_ptr, c->d_col, m->d_vals, xs, y,
+                                                        pl, prow, rowmask, colmask, rowscale);
     else
-        tfb_spmv_kernel<false><<<nb, 256, 0, c->stream>>>(c->n_local, c->desc.dof, c->d_row_ptr, c->d_col, m->d_vals, x, y,
-                                                         prow, 0u, 0u, nullptr);
+        tfb_spmv_kernel<false><<<nb, 256, 0, c->stream>>>(c->n_local, c->desc.dof, c->d_row_ptr, c->d_col, m->d_vals, xs, y,
+                                                         pl, prow, 0u, 0u, nullptr);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -139,11 +170,11 @@ static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, un
 static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned colmask);
 // ---- sub-matrix extraction (structure once per pattern and pin; values once per Jacobian) ----
 __global__ void k_sub_count(long long nrows, int dof, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                            int prow, unsigned rowmask, unsigned colmask, int* __restrict__ counts) {
+                            int prow_local, int prow, unsigned rowmask, unsigned colmask, int* __restrict__ counts) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     int cnt = 0;
-    if (((rowmask >> (row % dof)) & 1u) && row != prow)
+    if (((rowmask >> (row % dof)) & 1u) && row != prow_local)
         for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++) {
             const int cidx = col[e];
             if (cidx != prow && ((colmask >> (cidx % dof)) & 1u)) cnt++;
@@ -151,11 +182,11 @@ __global__ void k_sub_count(long long nrows, int dof, const int* __restrict__ ro
     counts[row] = cnt;
 }
 __global__ void k_sub_fill(long long nrows, int dof, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                           int prow, unsigned rowmask, unsigned colmask, const int* __restrict__ sub_ptr,
+                           int prow_local, int prow, unsigned rowmask, unsigned colmask, const int* __restrict__ sub_ptr,
                            int* __restrict__ sub_col, int* __restrict__ sub_src) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
-    if (!(((rowmask >> (row % dof)) & 1u) && row != prow)) return;
+    if (!(((rowmask >> (row % dof)) & 1u) && row != prow_local)) return;
     int pos = sub_ptr[row];
     for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++) {
         const int cidx = col[e];
@@ -246,7 +277,7 @@ static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned
     TFB_CUDA(cudaMalloc(&counts, sizeof(int) * (n + 1)));
     TFB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (n + 1), c->stream));
     const unsigned nb = (unsigned)((n + 255) / 256);
-    k_sub_count<<<nb, 256, 0, c->stream>>>(n, c->desc.dof, c->d_row_ptr, c->d_col, prow, rowmask, colmask, counts);
+    k_sub_count<<<nb, 256, 0, c->stream>>>(n, c->desc.dof, c->d_row_ptr, c->d_col, local_prow(c, prow), prow, rowmask, colmask, counts);
     TFB_LAUNCHED();
     // exclusive scan on the host side of a small int array is avoided: reuse CUB through a tiny kernel-free path
     std::vector<int> h(n + 1);
@@ -261,7 +292,7 @@ static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned
     TFB_CUDA(cudaMalloc(&S.col, sizeof(int) * cap));
     TFB_CUDA(cudaMalloc(&S.src, sizeof(int) * cap));
     TFB_CUDA(cudaMalloc(&S.vals, sizeof(double) * cap));
-    k_sub_fill<<<nb, 256, 0, c->stream>>>(n, c->desc.dof, c->d_row_ptr, c->d_col, prow, rowmask, colmask, S.row_ptr, S.col, S.src);
+    k_sub_fill<<<nb, 256, 0, c->stream>>>(n, c->desc.dof, c->d_row_ptr, c->d_col, local_prow(c, prow), prow, rowmask, colmask, S.row_ptr, S.col, S.src);
     TFB_LAUNCHED();
     TFB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(counts);
@@ -290,7 +321,9 @@ static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
     return 0;
 }
 static int sub_spmv(tfb_ctx* c, const SubCsr& S, const double* x, double* y, const double* rowscale = nullptr) {
-    k_sub_spmv<<<(unsigned)((c->n_local + 255) / 256), 256, 0, c->stream>>>(c->n_local, S.row_ptr, S.col, S.vals, x, y, rowscale);
+    const double* xs = nullptr;
+    if (ghosted(c, x, &xs)) return -1;
+    k_sub_spmv<<<(unsigned)((c->n_local + 255) / 256), 256, 0, c->stream>>>(c->n_local, S.row_ptr, S.col, S.vals, xs, y, rowscale);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -365,12 +398,14 @@ k_axis_gemm(const double* __restrict__ A, double* __restrict__ C, const double* 
         }
 }
 
-__global__ void k_fdm_scale(int nx, int ny, int nz, int mx, int my, int mz, const double* __restrict__ lx,
+// t /= coef*(lx[i]+ly[j]+lz[k]) on an array of extents (ex, ey, ez) that is a window of the grid
+// starting at global (0, jofs, kofs); m* = active global extents
+__global__ void k_fdm_scale(int ex, int ey, int ez, int jofs, int kofs, int mx, int my, int mz, const double* __restrict__ lx,
                             const double* __restrict__ ly, const double* __restrict__ lz, double coef, double thresh,
                             double* __restrict__ t) {
-    const long long ncell = (long long)nx * ny * nz;
+    const long long ncell = (long long)ex * ey * ez;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(c % nx), j = (int)((c / nx) % ny), k = (int)(c / ((long long)nx * ny));
+        const int i = (int)(c % ex), j = jofs + (int)((c / ex) % ey), k = kofs + (int)(c / ((long long)ex * ey));
         if (i < mx && j < my && k < mz) {
             const double den = coef * (lx[i] + ly[j] + (lz ? lz[k] : 0.0));
             t[c] = fabs(den) > thresh ? t[c] / den : 0.0;
@@ -379,11 +414,26 @@ __global__ void k_fdm_scale(int nx, int ny, int nz, int mx, int my, int mz, cons
 }
 
 // wall-normal boundary unknowns (index >= m along the own axis) have the row -1 * u
-__global__ void k_fdm_walls(int nx, int ny, int nz, int mx, int my, int mz, const double* __restrict__ in, double* __restrict__ out) {
-    const long long ncell = (long long)nx * ny * nz;
+__global__ void k_fdm_walls(int nx, int ny, int nzl, int kofs, int mx, int my, int mz, const double* __restrict__ in, double* __restrict__ out) {
+    const long long ncell = (long long)nx * ny * nzl;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(c % nx), j = (int)((c / nx) % ny), k = (int)(c / ((long long)nx * ny));
+        const int i = (int)(c % nx), j = (int)((c / nx) % ny), k = kofs + (int)(c / ((long long)nx * ny));
         if (i >= mx || j >= my || k >= mz) out[c] = -in[c];
+    }
+}
+
+// slab layout [kl][j][i]  <->  all-to-all buffer packed by destination y-chunk: [r][kl][jj][i]
+struct TfbChunks { int n; int j0[TFB_MAX_RANKS + 1]; long long dsp[TFB_MAX_RANKS]; };
+template <bool PACK>
+__global__ void k_a2a_pack(int nx, int ny, int nzl, TfbChunks ch, double* __restrict__ slab, double* __restrict__ buf) {
+    const long long ncell = (long long)nx * ny * nzl;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(c % nx), j = (int)((c / nx) % ny), kl = (int)(c / ((long long)nx * ny));
+        int r = 0;
+        while (r + 1 < ch.n && j >= ch.j0[r + 1]) r++;
+        const int cy = ch.j0[r + 1] - ch.j0[r];
+        const long long b = ch.dsp[r] + ((long long)kl * cy + (j - ch.j0[r])) * nx + i;
+        if (PACK) buf[b] = slab[c]; else slab[c] = buf[b];
     }
 }
 
@@ -473,62 +523,123 @@ static int axis_gemm(tfb_ctx* c, bool trans, const double* A, double* C, const d
     return 0;
 }
 
-// out = Op_v^-1 in  (SoA arrays; `in` is clobbered, tmp is scratch)
+// z-slab runs: sizes of the all-to-all between the slab layout and the pencil layout (all z, a
+// chunk of y), and the work arrays.  Called once after tfb_comm_init.
+static int dist_setup(tfb_ctx* c) {
+    tfb_solver_state* s = c->solver;
+    if (s->dist_ready || c->nranks == 1) return 0;
+    const int G = c->nranks, nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz;
+    TFB_CHECK(ny >= G, "fewer y-lines than ranks");
+    const int base = ny / G, rem = ny % G;
+    for (int r = 0; r <= G; r++) s->j0s[r] = r * base + std::min(r, rem);
+    const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
+    long long ds = 0;
+    for (int r = 0; r < G; r++) {
+        const int cy = s->j0s[r + 1] - s->j0s[r];
+        s->a2a_cnt_slab[r] = (long long)c->nzl * cy * nx;      // my planes, rank r's y-chunk
+        s->a2a_dsp_slab[r] = ds;
+        ds += s->a2a_cnt_slab[r];
+        const int nzr = c->slab_k0[r + 1] - c->slab_k0[r];
+        s->a2a_cnt_pen[r] = (long long)nzr * cyme * nx;        // rank r's planes, my y-chunk
+        s->a2a_dsp_pen[r] = (long long)c->slab_k0[r] * cyme * nx;
+    }
+    const size_t ncell = (size_t)c->n_local / c->desc.dof, npen = (size_t)nz * cyme * nx;
+    TFB_CUDA(cudaMalloc(&s->xg, sizeof(double) * (size_t)c->plane_rows * (c->nzl + 2)));
+    TFB_CUDA(cudaMemset(s->xg, 0, sizeof(double) * (size_t)c->plane_rows * (c->nzl + 2)));
+    TFB_CUDA(cudaMalloc(&s->pen[0], sizeof(double) * npen));
+    TFB_CUDA(cudaMalloc(&s->pen[1], sizeof(double) * npen));
+    TFB_CUDA(cudaMalloc(&s->sbuf, sizeof(double) * ncell));
+    TFB_CUDA(cudaMalloc(&s->rbuf, sizeof(double) * ncell));
+    s->dist_ready = true;
+    return 0;
+}
+
+// out = Op_v^-1 in  (SoA arrays of the local slab; `in` is preserved, tmp is scratch)
 static int fdm_solve(tfb_ctx* c, int v, double* in, double* tmp, double* out, double* keep_in) {
     tfb_solver_state* s = c->solver;
     const FdmVar& f = s->var[v];
     TFB_CHECK(f.present, "FDM operator missing for a variable (tfb_fdm_set)");
-    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz;
-    const long long ncell = (long long)nx * ny * nz;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl, k0 = c->desc.k0;
+    const long long ncell = (long long)nx * ny * nzl;
     const bool three = c->desc.dim == 3 && nz > 1;
     const int mx = f.m[0], my = f.m[1], mz = three ? f.m[2] : nz;
+    const double thresh = 1e-12 * fabs(f.coef) * f.maxden;
     (void)keep_in;
-    // forward: x, y, (z)
-    if (axis_gemm(c, false, in, tmp, f.Q[0], mx, ny * nz, mx, mx, nx, 1, 0, 1)) return -1;
-    if (axis_gemm(c, false, tmp, out, f.Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nz)) return -1;
+    // forward: x, y on the local planes
+    if (axis_gemm(c, false, in, tmp, f.Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
+    if (axis_gemm(c, false, tmp, out, f.Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
     double* cur = out;
     double* oth = tmp;
-    if (three) {
-        if (axis_gemm(c, false, cur, oth, f.Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
-        std::swap(cur, oth);
+    if (c->nranks == 1) {
+        if (three) {
+            if (axis_gemm(c, false, cur, oth, f.Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
+            std::swap(cur, oth);
+        }
+        k_fdm_scale<<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nz, 0, 0, mx, my, mz, f.lam[0], f.lam[1],
+                                                             three ? f.lam[2] : nullptr, f.coef, thresh, cur);
+        TFB_LAUNCHED();
+        if (three) {
+            if (axis_gemm(c, true, cur, oth, f.Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
+            std::swap(cur, oth);
+        }
+    } else {
+        // z couples the slabs: transpose to the pencil layout (all z, my y-chunk), transform, scale,
+        // transform back, transpose back (two NCCL all-to-alls per solve)
+        TFB_CHECK(three, "z-slabs need a 3-D grid");
+        if (dist_setup(c)) return -1;
+        TfbChunks ch;
+        ch.n = c->nranks;
+        for (int r = 0; r <= c->nranks; r++) ch.j0[r] = s->j0s[r];
+        for (int r = 0; r < c->nranks; r++) ch.dsp[r] = s->a2a_dsp_slab[r];
+        const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
+        const long long npen = (long long)nz * cyme * nx, lines = (long long)cyme * nx;
+        k_a2a_pack<true><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, cur, s->sbuf);
+        TFB_LAUNCHED();
+        if (tfb_alltoallv(c, s->sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, s->pen[0], s->a2a_cnt_pen, s->a2a_dsp_pen)) return -1;
+        if (axis_gemm(c, false, s->pen[0], s->pen[1], f.Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
+        k_fdm_scale<<<vec_blocks(npen), 256, 0, c->stream>>>(nx, cyme, nz, s->j0s[c->rank], 0, mx, my, mz, f.lam[0], f.lam[1],
+                                                            f.lam[2], f.coef, thresh, s->pen[1]);
+        TFB_LAUNCHED();
+        if (axis_gemm(c, true, s->pen[1], s->pen[0], f.Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
+        if (tfb_alltoallv(c, s->pen[0], s->a2a_cnt_pen, s->a2a_dsp_pen, s->rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab)) return -1;
+        k_a2a_pack<false><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, cur, s->rbuf);
+        TFB_LAUNCHED();
     }
-    k_fdm_scale<<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nz, mx, my, mz, f.lam[0], f.lam[1], three ? f.lam[2] : nullptr,
-                                                         f.coef, 1e-12 * fabs(f.coef) * f.maxden, cur);
-    TFB_LAUNCHED();
-    if (three) {
-        if (axis_gemm(c, true, cur, oth, f.Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
-        std::swap(cur, oth);
-    }
-    if (axis_gemm(c, true, cur, oth, f.Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nz)) return -1;
+    if (axis_gemm(c, true, cur, oth, f.Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
     std::swap(cur, oth);
     // last transform must land in `out`
     double* dst = (cur == out) ? tmp : out;
-    if (axis_gemm(c, true, cur, dst, f.Q[0], mx, ny * nz, mx, mx, nx, 1, 0, 1)) return -1;
+    if (axis_gemm(c, true, cur, dst, f.Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
     if (dst != out) TFB_CUDA(cudaMemcpyAsync(out, dst, sizeof(double) * ncell, cudaMemcpyDeviceToDevice, c->stream));
     if (mx < nx || my < ny || mz < nz) {
-        k_fdm_walls<<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nz, mx, my, mz, in, out);
+        k_fdm_walls<<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, k0, mx, my, mz, in, out);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
     return 0;
 }
 
-// pinned Poisson solve on SoA arrays: q = Lp_pinned^-1 rp ; rp is clobbered
+// pinned Poisson solve on SoA arrays: q = Lp_pinned^-1 rp ; rp is modified at the pin.
+// pin_cell is a GLOBAL cell index; with z-slabs the sum and the pinned value are all-reduced.
 static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, double* rp, double* tmp, double* q, double pin_sign = 1.0) {
     tfb_solver_state* s = c->solver;
     const long long ncell = c->n_local / c->desc.dof;
+    const long long cell0 = c->row0 / c->desc.dof;
+    const bool owner = pin_cell >= cell0 && pin_cell < cell0 + ncell;
+    const long long pl = pin_cell - cell0;
     if (pin_cell >= 0) {
-        TFB_CUDA(cudaMemsetAsync(s->d_scal, 0, sizeof(double), c->stream));
+        TFB_CUDA(cudaMemsetAsync(s->d_scal, 0, sizeof(double) * 3, c->stream));
         k_sum<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, rp, s->d_scal);
-        k_pin_rhs<<<1, 1, 0, c->stream>>>(rp, pin_cell, s->d_scal);
-        TFB_LAUNCHED(); TFB_LAUNCHED();
+        TFB_LAUNCHED();
+        if (tfb_allreduce_sum(c, s->d_scal, 1)) return -1;
+        if (owner) { k_pin_rhs<<<1, 1, 0, c->stream>>>(rp, pl, s->d_scal); TFB_LAUNCHED(); }
     }
-    // fdm_solve reads `rp` for the wall fix-up only for velocities; the pressure has no wall dofs
     if (fdm_solve(c, pvar, rp, tmp, q, nullptr)) return -1;
     if (pin_cell >= 0) {
-        k_copy1<<<1, 1, 0, c->stream>>>(q + pin_cell, s->d_scal + 2);
-        k_pin_shift<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, q, pin_cell, s->d_scal, s->d_scal + 2, pin_sign);
-        TFB_LAUNCHED(); TFB_LAUNCHED();
+        if (owner) { k_copy1<<<1, 1, 0, c->stream>>>(q + pl, s->d_scal + 2); TFB_LAUNCHED(); }
+        if (tfb_allreduce_sum(c, s->d_scal + 2, 1)) return -1;   // non-owners contribute 0
+        k_pin_shift<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, q, owner ? pl : -1, s->d_scal, s->d_scal + 2, pin_sign);
+        TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -540,7 +651,7 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
     const int dof = c->desc.dof, dim = c->desc.dim, pv = dim;
     const long long n = c->n_local, ncell = n / dof;
     const unsigned velmask = (1u << dim) - 1u, pmask = 1u << pv, smask = ((1u << dof) - 1u) & ~(velmask | pmask);
-    const long long pin_cell = prow >= 0 ? prow / dof : -1;
+    const long long pin_cell = prow >= 0 ? prow / dof : -1;   // global cell of the pinned pressure
     double *c0 = s->comp[0], *c1 = s->comp[1], *c2 = s->comp[2];
     double *ta = s->vec[0], *tb = s->vec[1], *tc = s->vec[2], *ru = s->vec[3];
     const unsigned vb = vec_blocks(ncell);
@@ -691,6 +802,7 @@ extern "C" int tfb_precond_apply(tfb_mat* m, const double* r, double* z, int pre
     tfb_ctx* c = m->ctx;
     TFB_CUDA(cudaSetDevice(c->desc.device));
     if (ensure_buffers(c, 0)) return -1;
+    if (dist_setup(c)) return -1;
     tfb_solver_state* s = c->solver;
     TFB_CUDA(cudaMemcpyAsync(s->vec[4], r, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
     if (sub_refresh(c, m, pressure_row)) return -1;
@@ -703,8 +815,9 @@ extern "C" int tfb_precond_apply(tfb_mat* m, const double* r, double* z, int pre
 extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
     TFB_CHECK(m && b && x && o, "null argument");
     tfb_ctx* c = m->ctx;
-    TFB_CHECK(c->nranks == 1, "distributed solve not implemented yet");
     TFB_CUDA(cudaSetDevice(c->desc.device));
+    solver_of(c);
+    if (dist_setup(c)) return -1;
     const long long n = c->n_local;
     const int mk = std::max(1, std::min(o->restart, o->maxit));
     if (ensure_buffers(c, mk)) return -1;
@@ -726,6 +839,10 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     auto Hx = [&](int i, int j) -> double& { return H[(size_t)j * (mk + 1) + i]; };
 
     int total_its = 0, converged = 0, reorth = 0;
+    // optional per-phase device timers (verbose >= 1): precondition, operator, orthogonalise
+    const bool prof = o->verbose >= 1;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
     double bnorm = 0.0, relres = 1.0;
     {
         if (multi_dot(c, d_b, 1, d_b, d_h)) return -1;
@@ -767,8 +884,11 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             double* vj = V + (size_t)j * n;
             double* zj = Z + (size_t)j * n;
             double* w = V + (size_t)(j + 1) * n;
+            mark();
             if (apply_precond(c, m, prow, vj, zj)) return -1;
+            mark();
             if (spmv(c, m, zj, w, prow)) return -1;
+            mark();
             // classical Gram-Schmidt with fused multi-dots (one pass over the basis per sweep); the
             // second sweep only runs when the first one cancelled most of w (DGKS criterion)
             if (multi_dot(c, w, 1, w, d_h + mk + 2)) return -1;            // |w|^2 before
@@ -791,6 +911,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
                 reorth++;
             }
             const double hn = sqrt(hn2);
+            mark();
             for (int i = 0; i <= j; i++) Hx(i, j) = hcol[i] + h2[i];
             Hx(j + 1, j) = hn;
             if (hn > 0.0) {
@@ -838,6 +959,14 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     relres = sqrt(rr) / bnorm;
+    if (prof && evs.size() >= 4) {
+        double t[3] = {0, 0, 0};
+        for (size_t e = 0; e + 3 < evs.size(); e += 4)
+            for (int ph = 0; ph < 3; ph++) { float x_ms = 0; cudaEventElapsedTime(&x_ms, evs[e + ph], evs[e + ph + 1]); t[ph] += x_ms; }
+        fprintf(stderr, "tfb_solve: %d its, %.1f ms total: precond %.1f ms, operator %.1f ms, orthogonalisation %.1f ms, %d re-orth sweeps\n",
+                total_its, ms, t[0], t[1], t[2], reorth);
+    }
+    for (auto e : evs) cudaEventDestroy(e);
     if (info) {
         info->iters = total_its;
         info->converged = relres <= o->tol * 10.0;
@@ -846,4 +975,31 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
         info->solve_ms = ms;
     }
     return relres <= o->tol * 10.0 ? 0 : 1;
+}
+
+// average device time of y = J x over `reps` launches (vectors and matrix resident; the operands
+// of a 3-D grid exceed the L2, small grids are measured warm)
+extern "C" int tfb_spmv_bench(tfb_mat* m, int reps, int masked, float* ms_out) {
+    TFB_CHECK(m && reps > 0 && ms_out, "bad arguments");
+    tfb_ctx* c = m->ctx;
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    if (ensure_buffers(c, 0)) return -1;
+    tfb_solver_state* s = c->solver;
+    const int dim = c->desc.dim;
+    const unsigned velmask = (1u << dim) - 1u;
+    TFB_CUDA(cudaMemsetAsync(s->vec[0], 0, sizeof(double) * c->n_local, c->stream));
+    cudaEvent_t e0, e1;
+    TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; w++)
+        if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, velmask, nullptr)) return -1;
+    TFB_CUDA(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < reps; r++)
+        if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, velmask, nullptr)) return -1;
+    TFB_CUDA(cudaEventRecord(e1, c->stream));
+    TFB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out = ms / reps;
+    return 0;
 }

@@ -43,6 +43,33 @@ class DeviceMatrix:
         if h and _lib._LIB is not None:
             _lib._LIB.tfb_mat_destroy(h)
 
+    @classmethod
+    def from_scipy(cls, interface, A):
+        '''Upload a host matrix whose entries lie inside the structural pattern (e.g. the
+        ``J - M / (theta * dt)`` of TimeIntegration.py:58 or a real shifted matrix
+        ``beta * J - alpha * M`` of the eigen-solver glue) so that ``solve`` can run on the device.'''
+        from scipy import sparse
+        A = sparse.csr_matrix(A)
+        if A.shape != (interface.n, interface.n) or numpy.iscomplexobj(A.data):
+            raise NotImplementedError('only real matrices of the Interface size can be uploaded')
+        A.sum_duplicates()
+        A.sort_indices()
+        row_ptr, col = interface.pattern()
+        n = interface.n
+        rows_s = numpy.repeat(numpy.arange(n, dtype=numpy.int64), numpy.diff(row_ptr))
+        rows_a = numpy.repeat(numpy.arange(n, dtype=numpy.int64), numpy.diff(A.indptr))
+        key_s = rows_s * n + col                       # sorted: rows ascending, columns ascending within a row
+        key_a = rows_a * n + A.indices
+        pos = numpy.searchsorted(key_s, key_a)
+        ok = (pos < len(key_s)) & (key_s[numpy.minimum(pos, len(key_s) - 1)] == key_a)
+        if not numpy.all(ok | (A.data == 0)):
+            raise NotImplementedError('matrix has entries outside the structural pattern of this discretization')
+        vals = numpy.zeros(interface.nnz)
+        vals[pos[ok]] = A.data[ok]
+        mat = cls(interface)
+        check(_lib.lib().tfb_mat_set_values(mat._h, ptr(vals)))
+        return mat
+
     def values(self):
         '''CSR values of the full structural pattern (explicit zeros included), D2H copy.'''
         out = numpy.empty(self.interface.nnz)
@@ -289,7 +316,16 @@ class Interface:
         with the preconditioned FGMRES on the device.  With a border (``rhs2, V, W, C``) the
         bordered system is reduced to two solves with J and a 1x1 Schur complement.'''
         if not isinstance(jac, DeviceMatrix):
-            raise NotImplementedError('solve() needs a matrix produced by this backend')
+            # host matrices built from ours (TimeIntegration's J - M/(theta dt), real shifts):
+            # re-upload onto the structural pattern, cached on the matrix object like `jac.lu`
+            dev = getattr(jac, '_tfb_device', None)
+            if dev is None:
+                dev = DeviceMatrix.from_scipy(self, jac)
+                try:
+                    jac._tfb_device = dev
+                except AttributeError:
+                    pass
+            jac = dev
         if V is not None:
             return self._bordered_solve(jac, rhs, rhs2, V, W, C)
         return self._solve1(jac, rhs)
@@ -299,21 +335,22 @@ class Interface:
         b = as_f64(rhs).copy()
         prow = -1
         if self.dof > self.dim:
-            prow = self.pressure_row
-            b[prow] = 0
+            prow = self.pressure_row            # global row; lives on the slab that owns cell 0
+            if self.row0 <= prow < self.row0 + self.n_local:
+                b[prow - self.row0] = 0
         its = self.parameters.get('Iterative Solver', {})
         o = _lib.TfbSolveOpts()
         o.tol = its.get('Convergence Tolerance', 1e-10)
         o.maxit = its.get('Maximum Iterations', 1000)
         # 180 GB of HBM: keep the whole Krylov space whenever it fits (no restart), the basis
         # needs 16 bytes per unknown and iteration
-        fit = max(20, int(100e9 // (16 * self.n)))
+        fit = max(20, int(100e9 // (16 * self.n_local)))
         o.restart = min(its.get('Restart', 500), fit)
         o.pressure_row = prow
         o.precond = its.get('Preconditioner Id', 0)
         o.verbose = int(bool(self.parameters.get('Verbose', False)))
         info = _lib.TfbSolveInfo()
-        y = numpy.zeros(self.n)
+        y = numpy.zeros(self.n_local)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
         self.last_solve = {'iterations': info.iters, 'relres': info.relres, 'converged': rc == 0,
                            'setup_ms': info.setup_ms, 'solve_ms': info.solve_ms}
