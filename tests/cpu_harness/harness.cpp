@@ -24,10 +24,13 @@ static int run(const TfbGrid& g, const TfbParams& prm, const double* state, cons
             double J[32]; double f = 0.0;
             for (int s = 0; s < 32; s++) J[s] = 0.0;
             TfbArraySink sink{J};
-            const bool interior = !(c.near[0] || c.far[0] || c.far2[0] || c.near[1] || c.far[1] || c.far2[1] ||
-                                    (!Cfg::FLAT && (c.near[2] || c.far[2] || c.far2[2])) || (Cfg::ID == 7 && i <= 1 && j <= 1));
-            if (interior) Cfg::template row<true, true, false>(d1, prm, c, P, sink, f);   // BC-free fast path
-            else Cfg::template row<true, true, true>(d1, prm, c, P, sink, f);
+            const bool yz_interior = !(c.near[1] || c.far[1] || c.far2[1] ||
+                                       (!Cfg::FLAT && (c.near[2] || c.far[2] || c.far2[2])) || (Cfg::ID == 7 && i <= 1 && j <= 1));
+            const bool x_interior = !(c.near[0] || c.far[0] || c.far2[0]);
+            // the same three instantiations the CUDA kernels use
+            if (yz_interior && x_interior) Cfg::template row<true, true, 0>(d1, prm, c, P, sink, f);   // BC-free
+            else if (yz_interior) Cfg::template row<true, true, 1>(d1, prm, c, P, sink, f);             // x-face ops only
+            else Cfg::template row<true, true, 2>(d1, prm, c, P, sink, f);                               // full recipe
             unsigned m = Cfg::mask(d1, c);
             int ns = Cfg::nslot(d1);
             for (int s = 0; s < ns; s++) if (m >> s & 1u) {

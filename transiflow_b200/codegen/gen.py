@@ -412,16 +412,27 @@ class RowEmitter:
             lines.append('}')
 
     def bc_lines(self, pre, keys, with_frc):
+        '''BCM template parameter: 0 = no boundary code (interior cells), 1 = only the x-face ops
+        (cells that are interior in y and z: the warp-uniform fast path keeps x-edge lanes without
+        a second pass), 2 = the full recipe.'''
         lines = []
         fidx = 0
         for op in self.cfg.recipe:
+            sub = []
             if op[0] == 'wall':
-                self._wall(pre, keys, op, lines, with_frc)
+                self._wall(pre, keys, op, sub, with_frc)
+                level = 1 if op[1] == 0 else 2
             elif op[0] == 'force':
-                self._force(pre, keys, op, fidx, lines, with_frc)
+                self._force(pre, keys, op, fidx, sub, with_frc)
                 fidx += 1
+                level = 1 if op[1] == 0 else 2
             else:
-                self._pin(pre, keys, lines, with_frc)
+                self._pin(pre, keys, sub, with_frc)
+                level = 2
+            if sub:
+                lines.append('if (BCM >= %d) {' % level)
+                lines += ['    ' + ln for ln in sub]
+                lines.append('}')
         return lines
 
     # ---- structural mask (which slots exist at this cell) ----
@@ -498,7 +509,7 @@ class RowEmitter:
         out = []
         w = out.append
         name = '%s_row%d' % (cfg.name, d1)
-        w('template <bool DO_J, bool DO_F, bool BC, class Cell, class State, class Sink>')
+        w('template <bool DO_J, bool DO_F, int BCM, class Cell, class State, class Sink>')
         w('TFB_HD void %s(const TfbParams& prm, const Cell& c, const State& P, Sink& Jout, double& rhs_out) {' % name)
         # make sure every state value the RHS product needs is loaded
         for k in self.fkeys:
@@ -544,10 +555,8 @@ class RowEmitter:
             else:
                 e = cname('l', k)
             w('        double %s = %s;' % (cname('F', k), e))
-        w('        if (BC) {')
         for ln in self.bc_lines('F', self.fkeys, True):
-            w('            ' + ln)
-        w('        }')
+            w('        ' + ln)
         terms = ['(%s * %s)' % (cname('F', k), row.P(k[0], (k[1] - 1, k[2] - 1, k[3] - 1))) for k in self.fkeys]
         e = terms[0]
         for t in terms[1:]:
@@ -565,10 +574,8 @@ class RowEmitter:
             if k in L:
                 parts = cname('l', k) if parts is None else '%s + %s' % (parts, cname('l', k))
             w('        double %s = %s;' % (cname('J', k), parts))
-        w('        if (BC) {')
         for ln in self.bc_lines('J', self.jkeys, False):
-            w('            ' + ln)
-        w('        }')
+            w('        ' + ln)
         for ci, (col, ckeys) in enumerate(self.cols):
             if len(ckeys) == 1:
                 w('        Jout.put(%d, %s);' % (ci, cname('J', ckeys[0])))
@@ -628,11 +635,11 @@ def emit_config(cfg):
     w('        }')
     w('        d2 = code & 15; dx = ((code >> 4) & 3) - 1; dy = ((code >> 6) & 3) - 1; dz = ((code >> 8) & 3) - 1;')
     w('    }')
-    w('    template <bool DO_J, bool DO_F, bool BC, class Cell, class State, class Sink>')
+    w('    template <bool DO_J, bool DO_F, int BCM, class Cell, class State, class Sink>')
     w('    TFB_HD static void row(int d1, const TfbParams& prm, const Cell& c, const State& P, Sink& Jout, double& rhs_out) {')
     w('        switch (d1) {')
     for d in range(cfg.dof):
-        w('        case %d: %s_row%d<DO_J, DO_F, BC>(prm, c, P, Jout, rhs_out); break;' % (d, cfg.name, d))
+        w('        case %d: %s_row%d<DO_J, DO_F, BCM>(prm, c, P, Jout, rhs_out); break;' % (d, cfg.name, d))
     w('        }')
     w('    }')
     w('    template <class Cell>')

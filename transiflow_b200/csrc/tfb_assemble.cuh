@@ -163,11 +163,11 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
         const int rp = DO_J ? a.row_ptr[row] : 0;
         if (tfb_is_interior<Cfg>(c)) {
             TfbSmemSink sink{out + (rp - galign)};
-            Cfg::template row<DO_J, DO_F, false>(d1, a.prm, c, P, sink, f);
+            Cfg::template row<DO_J, DO_F, 0>(d1, a.prm, c, P, sink, f);
         } else {
             double J[Cfg::MAXSLOT];
             TfbArraySink sink{J};
-            Cfg::template row<DO_J, DO_F, true>(d1, a.prm, c, P, sink, f);
+            Cfg::template row<DO_J, DO_F, 2>(d1, a.prm, c, P, sink, f);
             if (DO_J) {
                 const unsigned m = Cfg::mask(d1, c);
                 int pos = rp - galign;
@@ -370,11 +370,11 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
             double f = 0.0;
             if (xy_interior && !(c.near[2] | c.far[2] | c.far2[2])) {
                 TfbSmemSink sink{out + (rp - galign)};
-                Cfg::template row<DO_J, DO_F, false>(d1, a.prm, c, P, sink, f);
+                Cfg::template row<DO_J, DO_F, 0>(d1, a.prm, c, P, sink, f);
             } else {
                 double J[Cfg::MAXSLOT];
                 TfbArraySink sink{J};
-                Cfg::template row<DO_J, DO_F, true>(d1, a.prm, c, P, sink, f);
+                Cfg::template row<DO_J, DO_F, 2>(d1, a.prm, c, P, sink, f);
                 if (DO_J) {
                     const unsigned m = Cfg::mask(d1, c);
                     int pos = rp - galign;

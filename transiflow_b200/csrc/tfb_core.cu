@@ -300,19 +300,14 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
     }
     if constexpr (Cfg::ID == 1 && DO_J && DO_F) {   // Cfg_ldc3d
         switch (variant) {
-        case 1: return launch_assemble_v<Cfg, DO_J, DO_F, 4, 1>(c, m);
-        case 2: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 2>(c, m);
-        case 3: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 3>(c, m);
-        case 4: return launch_assemble_v<Cfg, DO_J, DO_F, 2, 4>(c, m);
-        case 7: return launch_assemble_v<Cfg, DO_J, DO_F, 4, 2>(c, m);
-        case 10: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 4>(c, m);
-        case 11: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 3>(c, m);
-        case 12: return launch_march_v<Cfg, DO_J, DO_F, 2, 8, 4>(c, m);
-        case 13: return launch_march_v<Cfg, DO_J, DO_F, 4, 16, 2>(c, m);
-        case 14: return launch_march_v<Cfg, DO_J, DO_F, 2, 32, 4>(c, m);
-        case 15: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 6>(c, m);
         case 16: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);
         case 17: return launch_march_v<Cfg, DO_J, DO_F, 4, 16, 1>(c, m);
+        case 18: return launch_march_v<Cfg, DO_J, DO_F, 2, 32, 2>(c, m);
+        case 19: return launch_march_v<Cfg, DO_J, DO_F, 2, 8, 2>(c, m);
+        case 20: return launch_march_v<Cfg, DO_J, DO_F, 3, 16, 1>(c, m);
+        case 21: return launch_march_v<Cfg, DO_J, DO_F, 4, 32, 1>(c, m);
+        case 22: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 4>(c, m);
+        case 23: return launch_march_v<Cfg, DO_J, DO_F, 1, 32, 4>(c, m);
         default: break;
         }
     }
