@@ -258,6 +258,9 @@ def main():
     alg_bytes = 8 * nnz + 16 * n_local       # CSR values written + state read + RHS written
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    # capture of this kernel on this workload (profiles/r1_ncu_assemble_march_128.csv)
+    ncu_traffic = {(128, 1): 105.420288e6 + 970.983680e6}.get((grid, world))
     line = {
         'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
@@ -266,7 +269,8 @@ def main():
                    'grid': [grid, grid, nz], 'unknowns': n_local * world, 'nnz_per_gpu': nnz,
                    'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': None, 'peak_source': peak_src, 'kernel': 'tfb_assemble_kernel<Cfg_ldc3d,J,F>',
+                     'traffic': ncu_traffic, 'peak_source': peak_src,
+                     'kernel': 'tfb_assemble_march_kernel<Cfg_ldc3d,J=1,F=1,TJ=2,KCH=16>',
                      'algorithmic_bytes_per_launch': alg_bytes},
         'e2e': {'value': total_cells / (e2e_ms * 1e-3), 'unit': 'cells/s', 'ms_per_step': e2e_ms,
                 'h2d_bytes_per_step': 8 * n_local, 'd2h_bytes_per_step': 8 * n_local},
