@@ -23,6 +23,7 @@ struct TfbAsmArgs {
     double* vals;
     double* rhs;
     int k0, nzl;
+    int kc0;                  // first z-chunk handled by this launch (pipelined host path)
 };
 
 template <class Cfg>
@@ -249,7 +250,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
     const int tid = (jl * DOF + d1) * 32 + il;
     const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
-    const int kbeg = blockIdx.z * KCH, kend = min(kbeg + KCH, a.nzl);   // local planes
+    const int kbeg = (blockIdx.z + a.kc0) * KCH, kend = min(kbeg + KCH, a.nzl);   // local planes
     const int kofs = 1 - a.k0;
     const long long plane = (long long)g.nx * g.ny * DOF;
 

@@ -2,6 +2,7 @@
 #include <cub/device/device_scan.cuh>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include "tfb_assemble.cuh"
 
 thread_local std::string g_tfb_err;
@@ -246,6 +247,7 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     a.rhs = c->d_rhs;
     a.k0 = c->desc.k0;
     a.nzl = c->nzl;
+    a.kc0 = 0;
     constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
     size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
     auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ, MINB>;
@@ -262,6 +264,8 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     return 0;
 }
 
+#define TFB_KCH 16   // planes per z-chunk of the marching kernel (also the host pipeline granularity)
+
 template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB>
 static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     TfbAsmArgs a;
@@ -274,6 +278,9 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     a.rhs = c->d_rhs;
     a.k0 = c->desc.k0;
     a.nzl = c->nzl;
+    const int nchunks = (c->nzl + KCH - 1) / KCH;
+    a.kc0 = c->chunk0 >= 0 ? c->chunk0 : 0;
+    const int nlaunch = c->chunk0 >= 0 ? std::min(c->chunkn, nchunks - a.kc0) : nchunks;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
     auto kern = tfb_assemble_march_kernel<Cfg, DO_J, DO_F, TJ, KCH, MINB>;
     static bool configured = false;
@@ -282,7 +289,7 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
         configured = true;
     }
     dim3 block(32, Cfg::DOF, TJ);
-    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (c->nzl + KCH - 1) / KCH);
+    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, nlaunch);
     kern<<<grid, block, smem, c->stream>>>(a);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
@@ -313,8 +320,8 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
     }
     if constexpr (!Cfg::FLAT) {
         // true 3-D grids: z-marching kernel (ring of state planes, software prefetch)
-        if constexpr (Cfg::DOF >= 5) return launch_march_v<Cfg, DO_J, DO_F, 3, 16, 1>(c, m);
-        else return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);
+        if constexpr (Cfg::DOF >= 5) return launch_march_v<Cfg, DO_J, DO_F, 3, TFB_KCH, 1>(c, m);
+        else return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 2>(c, m);
     } else {
         return launch_assemble_v<Cfg, DO_J, DO_F, (Cfg::DOF >= 5 ? 3 : 4), 1>(c, m);
     }
@@ -326,6 +333,8 @@ static int launch_assemble(tfb_ctx* c, tfb_mat* m, bool do_j, bool do_f) {
     if (do_j) return launch_assemble_t<Cfg, true, false>(c, m);
     return launch_assemble_t<Cfg, false, true>(c, m);
 }
+
+static int dispatch_assemble(tfb_ctx* c, tfb_mat* m, int do_j, int do_f);
 
 extern "C" int tfb_state_upload(tfb_ctx* c, const double* state) {
     TFB_CHECK(c && state, "null argument");
@@ -344,10 +353,7 @@ extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f)
         if (rc) return rc;
     }
     if (do_j) m->version++;
-#define X(C) if (c->desc.config == C::ID) return launch_assemble<C>(c, m, do_j != 0, do_f != 0);
-    TFB_FOR_EACH_CONFIG(X)
-#undef X
-    return tfb_fail(__FILE__, __LINE__, "tfb_assemble_resident", "unknown config");
+    return dispatch_assemble(c, m, do_j, do_f);
 }
 
 extern "C" int tfb_rhs_download(tfb_ctx* c, double* out) {
@@ -372,7 +378,64 @@ extern "C" int tfb_rhs(tfb_ctx* c, const double* state, double* out) {
     return tfb_rhs_download(c, out);
 }
 
+static int dispatch_assemble_impl(tfb_ctx* c, tfb_mat* m, int do_j, int do_f) {
+#define X(C) if (c->desc.config == C::ID) return launch_assemble<C>(c, m, do_j != 0, do_f != 0);
+    TFB_FOR_EACH_CONFIG(X)
+#undef X
+    return tfb_fail(__FILE__, __LINE__, "dispatch_assemble", "unknown config");
+}
+static int dispatch_assemble(tfb_ctx* c, tfb_mat* m, int do_j, int do_f) { return dispatch_assemble_impl(c, m, do_j, do_f); }
+
+// Host-buffer path for 3-D grids on one GPU: the upload of the state, the assembly and the download
+// of F(x) are pipelined over z-chunks on three streams (PCIe is full duplex), so the call costs
+// about max(H2D, D2H) instead of H2D + kernel + D2H.
+static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, double* rhs_out) {
+    const int nch = (c->nzl + TFB_KCH - 1) / TFB_KCH;
+    if (!c->s_h2d) {
+        TFB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        TFB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        for (int e = 0; e < TFB_MAX_CHUNKS; e++) {
+            TFB_CUDA(cudaEventCreateWithFlags(&c->ev_up[e], cudaEventDisableTiming));
+            TFB_CUDA(cudaEventCreateWithFlags(&c->ev_k[e], cudaEventDisableTiming));
+        }
+    }
+    // order against earlier work on the compute stream (e.g. a solve still reading the old values)
+    TFB_CUDA(cudaEventRecord(c->ev_k[TFB_MAX_CHUNKS - 1], c->stream));
+    TFB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[TFB_MAX_CHUNKS - 1], 0));
+    const size_t pr = (size_t)c->plane_rows;
+    for (int ch = 0; ch < nch; ch++) {
+        const int p0 = ch * TFB_KCH, p1 = std::min(p0 + TFB_KCH, c->nzl);
+        TFB_CUDA(cudaMemcpyAsync(c->d_state + pr * (p0 + 1), state + pr * p0, sizeof(double) * pr * (p1 - p0),
+                                 cudaMemcpyHostToDevice, c->s_h2d));
+        TFB_CUDA(cudaEventRecord(c->ev_up[ch], c->s_h2d));
+    }
+    m->version++;
+    for (int ch = 0; ch < nch; ch++) {
+        const int p0 = ch * TFB_KCH, p1 = std::min(p0 + TFB_KCH, c->nzl);
+        TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[std::min(ch + 1, nch - 1)], 0));   // needs the first plane of the next chunk
+        c->chunk0 = ch; c->chunkn = 1;
+        int rc = dispatch_assemble(c, m, 1, rhs_out != nullptr);
+        c->chunk0 = -1;
+        if (rc) return rc;
+        if (rhs_out) {
+            TFB_CUDA(cudaEventRecord(c->ev_k[ch], c->stream));
+            TFB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[ch], 0));
+            TFB_CUDA(cudaMemcpyAsync(rhs_out + pr * p0, c->d_rhs + pr * p0, sizeof(double) * pr * (p1 - p0),
+                                     cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+    }
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    if (rhs_out) TFB_CUDA(cudaStreamSynchronize(c->s_d2h));
+    return 0;
+}
+
 extern "C" int tfb_jacobian(tfb_ctx* c, const double* state, tfb_mat* m, double* rhs_out) {
+    TFB_CHECK(c && state && m && m->ctx == c, "bad arguments");
+    TFB_CHECK(c->have_params, "tfb_set_params has not been called");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    const int nch = (c->nzl + TFB_KCH - 1) / TFB_KCH;
+    if (c->nranks == 1 && c->desc.nz > 1 && c->desc.dim == 3 && nch >= 2 && nch < TFB_MAX_CHUNKS && !getenv("TFB_NO_PIPELINE"))
+        return jacobian_pipelined(c, state, m, rhs_out);
     int rc = tfb_state_upload(c, state);
     if (rc) return rc;
     rc = tfb_assemble_resident(c, m, 1, rhs_out != nullptr);

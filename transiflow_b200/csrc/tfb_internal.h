@@ -25,6 +25,7 @@ int tfb_fail(const char* file, int line, const char* what, const char* detail);
 #define TFB_LAUNCHED() (g_tfb_launches++)
 
 #define TFB_MAX_RANKS 16
+#define TFB_MAX_CHUNKS 80
 struct tfb_solver_state;  // tfb_solver.cu
 
 struct tfb_ctx {
@@ -54,6 +55,10 @@ struct tfb_ctx {
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     cudaEvent_t ev[16] = {};
+    // pipelined host path of tfb_jacobian: copy streams, per-chunk events, z-chunk window of a launch
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_up[TFB_MAX_CHUNKS] = {}, ev_k[TFB_MAX_CHUNKS] = {};
+    int chunk0 = -1, chunkn = 0;
     tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
     // multi-GPU
     int nranks = 1, rank = 0;
