@@ -223,6 +223,19 @@ def main():
     e2e_ms = max_over_ranks(ms.value / args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- SpMV y = J x on the assembled matrix (resident operands; 1.6 GB of operands >> L2) ----
+    spmv = None
+    try:
+        ms_sp = ctypes.c_float()
+        check(L.tfb_spmv_bench(mat._h, 50, 0, ctypes.byref(ms_sp)))
+        sp_ms = max_over_ranks(ms_sp.value)
+        sp_bytes = 12 * it.nnz + 4 * (n_local + 1) + 16 * n_local     # CSR algorithmic bytes
+        spmv = {'ms': sp_ms, 'algorithmic_bytes': sp_bytes, 'achieved_gbs': sp_bytes / (sp_ms * 1e-3) / 1e9,
+                'frac_of_hbm_peak': sp_bytes / (sp_ms * 1e-3) / 1e9 / measured_peaks()[0],
+                'kernel': 'tfb_spmv_march_kernel (values-only stream, TMA bulk loads, no column indices)'}
+    except Exception as e:     # noqa: BLE001
+        spmv = {'error': str(e)}
+
     # ---- Newton step: fused assembly + preconditioned FGMRES to 1e-10 (single GPU) ----
     newton = None
     if args.newton_steps > 0:
@@ -277,6 +290,7 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks,
         'newton': newton,
+        'spmv': spmv,
     }
     if not args.no_cpu_baseline and world == 1:
         planes = max(2, min(grid, 32))

@@ -129,3 +129,17 @@ def test_time_integration_operators():
     Ah[3, 3] = -1
     r = Ah.tocsr() @ y - b
     assert numpy.linalg.norm(r) <= 1e-8 * numpy.linalg.norm(b)
+
+
+def test_structured_spmv_matches_csr_kernel_and_scipy():
+    """3-D grids use the column-index-free marching SpMV; it must agree with scipy on ragged grids."""
+    for params, nx, ny, nz in (({'Reynolds Number': 100}, 37, 9, 19),
+                               ({'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 800.0, 'Prandtl Number': 10.0,
+                                 'Biot Number': 1.0, 'X-max': 10, 'Y-max': 10}, 33, 7, 18)):
+        it = _iface(params, nx, ny, nz)
+        x = numpy.random.default_rng(0).uniform(-0.5, 0.5, it.n)
+        jac = it.jacobian(x)
+        v = numpy.random.default_rng(1).uniform(-1, 1, it.n)
+        want = jac.tocsr() @ v
+        got = jac @ v
+        assert numpy.abs(got - want).max() <= 1e-13 * numpy.abs(want).max()

@@ -4,6 +4,7 @@
 #include <string.h>
 #include <algorithm>
 #include "tfb_assemble.cuh"
+#include "tfb_spmv_march.cuh"
 
 thread_local std::string g_tfb_err;
 int64_t g_tfb_launches = 0;
@@ -204,8 +205,9 @@ extern "C" int tfb_mat_create(tfb_ctx* c, tfb_mat** out) {
     TFB_CUDA(cudaSetDevice(c->desc.device));
     tfb_mat* m = new tfb_mat();
     m->ctx = c;
-    TFB_CUDA(cudaMalloc(&m->d_vals, sizeof(double) * (size_t)c->nnz));
-    TFB_CUDA(cudaMemset(m->d_vals, 0, sizeof(double) * (size_t)c->nnz));
+    // +2: the structured SpMV fetches whole 16-byte pairs and may read one element past the last span
+    TFB_CUDA(cudaMalloc(&m->d_vals, sizeof(double) * ((size_t)c->nnz + 2)));
+    TFB_CUDA(cudaMemset(m->d_vals, 0, sizeof(double) * ((size_t)c->nnz + 2)));
     *out = m;
     return 0;
 }
@@ -501,4 +503,51 @@ extern "C" int tfb_pinned_alloc(size_t bytes, void** out) {
 extern "C" int tfb_pinned_free(void* p) {
     if (p) TFB_CUDA(cudaFreeHost(p));
     return 0;
+}
+
+// ------------------------------- structured SpMV (tfb_spmv_march.cuh) -------------------------------
+template <class Cfg>
+static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
+                             int prow, unsigned rowmask, unsigned colmask, const double* rowscale) {
+    constexpr int TJ = Cfg::DOF >= 5 ? 3 : 2;
+    TfbSpmvArgs a;
+    a.g = c->grid();
+    a.x = x_global_base;
+    a.kvalid0 = kvalid0; a.kvalid1 = kvalid1;
+    a.row_ptr = c->d_row_ptr;
+    a.vals = m->d_vals;
+    a.y = y;
+    a.rowscale = rowscale;
+    a.k0 = c->desc.k0; a.nzl = c->nzl;
+    a.pvar = -1; a.prow_cell_i = a.prow_cell_j = a.prow_cell_k = -1;
+    if (prow >= 0) {
+        const long long cell = prow / c->desc.dof;
+        a.pvar = prow % c->desc.dof;
+        a.prow_cell_i = (int)(cell % c->desc.nx);
+        a.prow_cell_j = (int)((cell / c->desc.nx) % c->desc.ny);
+        a.prow_cell_k = (int)(cell / ((long long)c->desc.nx * c->desc.ny));
+    }
+    a.rowmask = rowmask; a.colmask = colmask;
+    size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(true);
+    auto kern = tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH>;
+    static bool configured = false;
+    if (!configured) {
+        TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 block(32, Cfg::DOF, TJ);
+    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (c->nzl + TFB_KCH - 1) / TFB_KCH);
+    kern<<<grid, block, smem, c->stream>>>(a);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// returns 1 when the configuration has no structured kernel (2-D / folded grids): caller uses the CSR kernel
+int tfb_spmv_structured(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
+                        int prow, unsigned rowmask, unsigned colmask, const double* rowscale) {
+#define X(C) if (c->desc.config == C::ID) { if constexpr (C::FLAT) return 1; else return launch_spmv_march<C>(c, m, x_global_base, kvalid0, kvalid1, y, prow, rowmask, colmask, rowscale); }
+    TFB_FOR_EACH_CONFIG(X)
+#undef X
+    return 1;
 }

@@ -74,6 +74,8 @@ struct tfb_mat {
 };
 
 int tfb_build_pattern(tfb_ctx* ctx);
+int tfb_spmv_structured(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
+                        int prow, unsigned rowmask, unsigned colmask, const double* rowscale);
 int tfb_halo_exchange(tfb_ctx* ctx, double* d_vec_with_ghosts);
 int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
 int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,

@@ -155,6 +155,15 @@ static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, un
     const unsigned nb = (unsigned)((threads + 255) / 256);
     const double* xs = nullptr;
     if (ghosted(c, x, &xs)) return -1;
+    {   // true 3-D grids: structured kernel that never reads the column indices
+        static int use_structured = -1;
+        if (use_structured < 0) { const char* e = getenv("TFB_SPMV_CSR"); use_structured = !(e && e[0] == '1'); }
+        if (use_structured) {
+            const int kv0 = c->nranks == 1 ? 0 : c->desc.k0 - 1, kv1 = c->nranks == 1 ? c->desc.nz : c->desc.k1 + 1;
+            const int rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
+            if (rc <= 0) return rc;
+        }
+    }
     const int pl = local_prow(c, prow);
     if (rowmask)
         tfb_spmv_kernel<true><<<nb, 256, 0, c->stream>>>(c->n_local, c->desc.dof, c->d_row_ptr, c->d_col, m->d_vals, xs, y,
