@@ -276,6 +276,71 @@ __global__ void __launch_bounds__(256) k_multi_axpy(long long n, const double* _
     }
 }
 
+// ---- single-pass orthogonalisation kernels: every basis vector and w are read exactly once ----
+// h[v] += sum_i V[v][i] * w[i] for all v < nv.  A CTA owns a tile of rows, keeps its w values in
+// registers and walks over the basis vectors; per-warp partial sums are parked in shared memory.
+#define TFB_ORTH_ROWS 4
+__global__ void __launch_bounds__(256) k_all_dots(long long n, const double* __restrict__ V, long long ld, int nv,
+                                                  const double* __restrict__ w, double* __restrict__ out) {
+    extern __shared__ double part[];   // [8 warps][nv]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int v = threadIdx.x; v < 8 * nv; v += 256) part[v] = 0.0;
+    __syncthreads();
+    const long long tile = (long long)256 * TFB_ORTH_ROWS;
+    for (long long base = (long long)blockIdx.x * tile; base < n; base += (long long)gridDim.x * tile) {
+        double wr[TFB_ORTH_ROWS];
+#pragma unroll
+        for (int r = 0; r < TFB_ORTH_ROWS; r++) {
+            const long long i = base + r * 256 + threadIdx.x;
+            wr[r] = i < n ? w[i] : 0.0;
+        }
+        for (int v = 0; v < nv; v++) {
+            const double* vp = V + (long long)v * ld;
+            double a = 0.0;
+#pragma unroll
+            for (int r = 0; r < TFB_ORTH_ROWS; r++) {
+                const long long i = base + r * 256 + threadIdx.x;
+                if (i < n) a += vp[i] * wr[r];
+            }
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) part[warp * nv + v] += a;
+        }
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += 256) {
+        double a = 0.0;
+        for (int wv = 0; wv < 8; wv++) a += part[wv * nv + v];
+        atomicAdd(&out[v], a);
+    }
+}
+// w += sign * sum_v h[v] V[v]; optionally accumulates |w_new|^2 into *nrm2
+__global__ void __launch_bounds__(256) k_all_axpy(long long n, const double* __restrict__ V, long long ld, int nv,
+                                                  const double* __restrict__ h, double sign, double* __restrict__ w,
+                                                  double* __restrict__ nrm2) {
+    extern __shared__ double hs[];
+    for (int v = threadIdx.x; v < nv; v += 256) hs[v] = h[v];
+    __syncthreads();
+    double loc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double a = 0.0;
+        for (int v = 0; v < nv; v++) a += hs[v] * V[(long long)v * ld + i];
+        const double wn = w[i] + sign * a;
+        w[i] = wn;
+        loc += wn * wn;
+    }
+    if (nrm2) {
+        for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+        __shared__ double red[8];
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int wv = 0; wv < 8; wv++) t += red[wv];
+            atomicAdd(nrm2, t);
+        }
+    }
+}
+
 static inline unsigned vec_blocks(long long n);
 static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned colmask) {
     const long long n = c->n_local;
@@ -771,24 +836,32 @@ static int ensure_buffers(tfb_ctx* c, int krylov) {
     return 0;
 }
 
-// h[0..nv) = V^T w ; chunked in groups of 8 vectors
+// h[0..nv) = V^T w   (one pass over the basis)
 static int multi_dot(tfb_ctx* c, const double* V, int nv, const double* w, double* d_out) {
     const long long n = c->n_local;
     TFB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * nv, c->stream));
-    for (int v0 = 0; v0 < nv; v0 += 8) {
-        k_multi_dot<8><<<vec_blocks(n), 256, 0, c->stream>>>(n, V + (size_t)v0 * n, n, std::min(8, nv - v0), w, d_out + v0);
+    const unsigned nb = (unsigned)std::min<long long>((n + 1023) / 1024, 148 * 8);
+    for (int v0 = 0; v0 < nv; v0 += 512) {     // 8 warps x 512 partial sums = 32 KB of shared memory
+        const int cnt = std::min(512, nv - v0);
+        k_all_dots<<<nb, 256, sizeof(double) * 8 * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, w, d_out + v0);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
     return tfb_allreduce_sum(c, d_out, nv);
 }
-static int multi_axpy(tfb_ctx* c, const double* V, int nv, const double* d_h, double sign, double* w) {
+// w += sign * V h   (one pass over the basis); d_nrm2 (optional, zeroed here) receives the LOCAL |w|^2
+static int multi_axpy(tfb_ctx* c, const double* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2 = nullptr) {
     const long long n = c->n_local;
-    for (int v0 = 0; v0 < nv; v0 += 8) {
-        k_multi_axpy<8><<<vec_blocks(n), 256, 0, c->stream>>>(n, V + (size_t)v0 * n, n, std::min(8, nv - v0), d_h + v0, sign, w);
+    if (d_nrm2) TFB_CUDA(cudaMemsetAsync(d_nrm2, 0, sizeof(double), c->stream));
+    for (int v0 = 0; v0 < nv; v0 += 2048) {
+        const int cnt = std::min(2048, nv - v0);
+        const bool last = v0 + cnt >= nv;
+        k_all_axpy<<<vec_blocks(n), 256, sizeof(double) * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, d_h + v0, sign, w,
+                                                                          last ? d_nrm2 : nullptr);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
+    if (d_nrm2) return tfb_allreduce_sum(c, d_nrm2, 1);
     return 0;
 }
 
@@ -902,8 +975,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             // second sweep only runs when the first one cancelled most of w (DGKS criterion)
             if (multi_dot(c, w, 1, w, d_h + mk + 2)) return -1;            // |w|^2 before
             if (multi_dot(c, V, j + 1, w, d_h)) return -1;
-            if (multi_axpy(c, V, j + 1, d_h, -1.0, w)) return -1;
-            if (multi_dot(c, w, 1, w, d_h + mk + 1)) return -1;            // |w|^2 after
+            if (multi_axpy(c, V, j + 1, d_h, -1.0, w, d_h + mk + 1)) return -1;   // fused |w|^2 after
             double nrm[2];
             TFB_CUDA(cudaMemcpyAsync(hcol.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
             TFB_CUDA(cudaMemcpyAsync(nrm, d_h + mk + 1, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
@@ -912,9 +984,8 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             double hn2 = nrm[0];
             if (nrm[0] < 0.25 * nrm[1]) {
                 if (multi_dot(c, V, j + 1, w, d_h)) return -1;
-                if (multi_axpy(c, V, j + 1, d_h, -1.0, w)) return -1;
+                if (multi_axpy(c, V, j + 1, d_h, -1.0, w, d_h + mk + 1)) return -1;
                 TFB_CUDA(cudaMemcpyAsync(h2.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
-                if (multi_dot(c, w, 1, w, d_h + mk + 1)) return -1;
                 TFB_CUDA(cudaMemcpyAsync(&hn2, d_h + mk + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
                 TFB_CUDA(cudaStreamSynchronize(c->stream));
                 reorth++;
