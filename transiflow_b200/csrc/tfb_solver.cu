@@ -231,50 +231,6 @@ __global__ void k_sub(long long n, const double* __restrict__ a, const double* _
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = a[i] - b[i];
 }
 
-// out[v] (+)= sum_i V[v*ld + i] * w[i] for v < nv <= 8 : one pass over w, fused dots
-template <int NV>
-__global__ void __launch_bounds__(256) k_multi_dot(long long n, const double* __restrict__ V, long long ld, int nv,
-                                                   const double* __restrict__ w, double* __restrict__ out) {
-    double acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) acc[v] = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double wi = w[i];
-#pragma unroll
-        for (int v = 0; v < NV; v++)
-            if (v < nv) acc[v] += V[v * ld + i] * wi;
-    }
-    __shared__ double red[NV][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int v = 0; v < NV; v++) {
-        double a = acc[v];
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) red[v][warp] = a;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV && threadIdx.x < nv) {
-        double a = 0.0;
-        for (int wv = 0; wv < 8; wv++) a += red[threadIdx.x][wv];
-        atomicAdd(&out[threadIdx.x], a);
-    }
-}
-
-// w -= sum_v h[v] * V[v*ld + i]   (or w += with sign)
-template <int NV>
-__global__ void __launch_bounds__(256) k_multi_axpy(long long n, const double* __restrict__ V, long long ld, int nv,
-                                                    const double* __restrict__ h, double sign, double* __restrict__ w) {
-    double hv[NV];
-#pragma unroll
-    for (int v = 0; v < NV; v++) hv[v] = v < nv ? h[v] : 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        double a = 0.0;
-#pragma unroll
-        for (int v = 0; v < NV; v++)
-            if (v < nv) a += hv[v] * V[v * ld + i];
-        w[i] += sign * a;
-    }
-}
 
 // ---- single-pass orthogonalisation kernels: every basis vector and w are read exactly once ----
 // h[v] += sum_i V[v][i] * w[i] for all v < nv.  A CTA owns a tile of rows, keeps its w values in
