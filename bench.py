@@ -28,6 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PARAMS = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1}
+# secondary workload (--problem rb): BASELINE config 4, 3-D Rayleigh-Benard (dof 5), assembly only
+RB_PARAMS = {'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 1000.0, 'Prandtl Number': 10.0, 'Biot Number': 1.0,
+             'X-max': 10, 'Y-max': 10}
 
 
 def measured_peaks():
@@ -126,7 +129,12 @@ def main():
     ap.add_argument('--grid', type=int, default=128)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--problem', default='ldc', choices=['ldc', 'rb'])
     args = ap.parse_args()
+    if args.problem == 'rb':
+        PARAMS.clear()
+        PARAMS.update(RB_PARAMS)
+        args.newton_steps = 0
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -278,7 +286,8 @@ def main():
         'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': '3D lid-driven cavity %d^3 per GPU, Re=100, fused Jacobian+RHS assembly' % grid,
+        'config': {'workload': ('3D lid-driven cavity %d^3 per GPU, Re=100, fused Jacobian+RHS assembly' if args.problem == 'ldc'
+                                else '3D Rayleigh-Benard %d^3 per GPU (dof 5), Ra=1000, fused Jacobian+RHS assembly') % grid,
                    'grid': [grid, grid, nz], 'unknowns': n_local * world, 'nnz_per_gpu': nnz,
                    'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

@@ -322,7 +322,15 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
     }
     if constexpr (!Cfg::FLAT) {
         // true 3-D grids: z-marching kernel (ring of state planes, software prefetch)
-        if constexpr (Cfg::DOF >= 5) return launch_march_v<Cfg, DO_J, DO_F, 3, TFB_KCH, 1>(c, m);
+        if constexpr (Cfg::DOF >= 5) {
+            if constexpr (DO_J && DO_F) {
+                if (variant == 31) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 2>(c, m);
+                if (variant == 32) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);
+                if (variant == 33) return launch_march_v<Cfg, DO_J, DO_F, 4, TFB_KCH, 1>(c, m);
+                if (variant == 34) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3>(c, m);
+            }
+            return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);   // dof 5: 160 registers, no spills
+        }
         else return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 2>(c, m);
     } else {
         return launch_assemble_v<Cfg, DO_J, DO_F, (Cfg::DOF >= 5 ? 3 : 4), 1>(c, m);
