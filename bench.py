@@ -8,8 +8,11 @@ grid^3 cells (default 128^3, n = 8.4 M unknowns, nnz = 118 M), synthetic state
 uniform(-0.5, 0.5) seed 0.  One "step" = one fused Jacobian+RHS assembly on the fixed
 sparsity pattern.  `value` = cells/s with the state resident in HBM; `e2e` = the same through
 Interface.jacobian_rhs() with host buffers (H2D state + D2H F(x) inside the timed region).
-With N > 1 (torchrun, one process per GPU) the grid is split into z-slabs, weak scaling:
-every rank owns grid/1 planes of a (grid x grid x N*grid) domain... see --scaling.
+Further keys: `spmv` (y = J x on the assembled matrix), `newton` (fused assembly + FGMRES solve to
+1e-10 per step), `roofline`, `cpu_baseline`, `clocks`.
+With N > 1 (torchrun, one process per GPU) the grid is split into z-slabs, weak scaling: every
+rank owns `grid` planes of a (grid x grid x N*grid) cavity with Z-max = N (cubic cells); halos
+are exchanged with NCCL inside the library.
 
 `--impl reference` times the CPU implementation of the same path (the C port of the
 reference in oracle/, all host threads) on a bounded sample of the workload.

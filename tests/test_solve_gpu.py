@@ -143,3 +143,21 @@ def test_structured_spmv_matches_csr_kernel_and_scipy():
         want = jac.tocsr() @ v
         got = jac @ v
         assert numpy.abs(got - want).max() <= 1e-13 * numpy.abs(want).max()
+
+
+def test_parameter_continuation_reaches_the_reference_branch_point():
+    """The reference's pseudo-arclength continuation (Continuation.continuation, SciPy backend) ends at the
+    steady state for Re = 400; stepping the shared parameter dict through set_parameter and converging
+    Newton with the device solver must land on the same state (tests/golden/make_golden_continuation.py)."""
+    g = numpy.load(os.path.join(GEN, 'continuation_ldc2d.npz'))
+    params = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 0, 'Lid Velocity': 1, 'Grid Stretching Factor': 1.5}
+    from transiflow_b200 import Interface
+    it = Interface(params, int(g['nx']), int(g['ny']))
+    x = it.vector()
+    for Re in (0, 100, 200, 300, float(g['mu'])):
+        it.set_parameter('Reynolds Number', Re)
+        x, k = newton(it, x, tol=1e-11, maxit=12)
+    assert numpy.linalg.norm(it.rhs(x)) < 1e-10
+    assert numpy.abs(x - g['x']).max() <= 1e-8 * numpy.abs(g['x']).max()
+    # the reference's un-polished continuation end point lies within its own corrector tolerance of that state
+    assert numpy.abs(g['x_continuation'] - x).max() <= 1e-2 * numpy.abs(x).max()
