@@ -537,15 +537,16 @@ static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_globa
     }
     a.rowmask = rowmask; a.colmask = colmask;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(true);
-    auto kern = tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH>;
     static bool configured = false;
     if (!configured) {
-        TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFB_CUDA(cudaFuncSetAttribute(tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TFB_CUDA(cudaFuncSetAttribute(tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 block(32, Cfg::DOF, TJ);
     dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (c->nzl + TFB_KCH - 1) / TFB_KCH);
-    kern<<<grid, block, smem, c->stream>>>(a);
+    if (rowmask || colmask) tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, true><<<grid, block, smem, c->stream>>>(a);
+    else tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, false><<<grid, block, smem, c->stream>>>(a);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;

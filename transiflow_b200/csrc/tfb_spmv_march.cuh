@@ -45,29 +45,51 @@ __device__ __forceinline__ void tfb_bulk_load(double* smem_dst, const double* gs
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-template <class Cfg, int D1, int TJ>
-__device__ __forceinline__ double tfb_row_dot(const double* __restrict__ v, unsigned m, bool full, const RingState<Cfg, TJ>& P,
-                                              const TfbSpmvArgs& a, int i, int j, int k) {
-    double acc = 0.0;
-    int pos = 0;
+// One row: sum over the structural slots.  Four independent accumulators break the fp64
+// dependency chain; the pin / mask tests are compiled out (MASKED) or hoisted (pin_near).
+template <class Cfg, int D1, int TJ, bool MASKED>
+__device__ __forceinline__ double tfb_row_dot(const double* __restrict__ v, unsigned m, bool full, bool pin_near,
+                                              const RingState<Cfg, TJ>& P, const TfbSpmvArgs& a, int i, int j, int k) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (full && !pin_near) {
 #pragma unroll
-    for (int s = 0; s < Cfg::nslot(D1); s++) {
-        int d2, dx, dy, dz;
-        Cfg::slot(D1, s, d2, dx, dy, dz);
-        const bool present = full || ((m >> s) & 1u);
-        if (present) {
-            bool take = a.colmask == 0u || ((a.colmask >> d2) & 1u);
-            if (d2 == a.pvar && i + dx == a.prow_cell_i && j + dy == a.prow_cell_j && k + dz == a.prow_cell_k) take = false;
-            const double val = v[full ? s : pos];
-            if (take) acc += val * P(d2, dx, dy, dz);
-            pos++;
+        for (int s = 0; s < Cfg::nslot(D1); s++) {
+            int d2, dx, dy, dz;
+            Cfg::slot(D1, s, d2, dx, dy, dz);
+            if (!MASKED || ((a.colmask >> d2) & 1u)) acc[s & 3] += v[s] * P(d2, dx, dy, dz);
+        }
+    } else {
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < Cfg::nslot(D1); s++) {
+            int d2, dx, dy, dz;
+            Cfg::slot(D1, s, d2, dx, dy, dz);
+            if (full || ((m >> s) & 1u)) {
+                bool take = !MASKED || ((a.colmask >> d2) & 1u);
+                if (pin_near && d2 == a.pvar && i + dx == a.prow_cell_i && j + dy == a.prow_cell_j && k + dz == a.prow_cell_k) take = false;
+                if (take) acc[s & 3] += v[pos] * P(d2, dx, dy, dz);
+                pos++;
+            }
         }
     }
-    return acc;
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
-template <class Cfg, int TJ, int KCH>
-__global__ void __launch_bounds__(32 * Cfg::DOF * TJ, 2)
+template <class Cfg, int TJ, bool MASKED>
+__device__ __forceinline__ double tfb_row_dot_any(int d1, const double* __restrict__ v, unsigned m, bool full, bool pin_near,
+                                                  const RingState<Cfg, TJ>& P, const TfbSpmvArgs& a, int i, int j, int k) {
+    switch (d1) {
+    case 0: return tfb_row_dot<Cfg, 0, TJ, MASKED>(v, m, full, pin_near, P, a, i, j, k);
+    case 1: return tfb_row_dot<Cfg, 1, TJ, MASKED>(v, m, full, pin_near, P, a, i, j, k);
+    case 2: return tfb_row_dot<Cfg, 2, TJ, MASKED>(v, m, full, pin_near, P, a, i, j, k);
+    case 3: return tfb_row_dot<Cfg, (Cfg::DOF > 3 ? 3 : 0), TJ, MASKED>(v, m, full, pin_near, P, a, i, j, k);
+    case 4: return tfb_row_dot<Cfg, (Cfg::DOF > 4 ? 4 : 0), TJ, MASKED>(v, m, full, pin_near, P, a, i, j, k);
+    default: return tfb_row_dot<Cfg, (Cfg::DOF > 5 ? 5 : 0), TJ, MASKED>(v, m, full, pin_near, P, a, i, j, k);
+    }
+}
+
+template <class Cfg, int TJ, int KCH, bool MASKED>
+__global__ void __launch_bounds__(32 * Cfg::DOF * TJ, (Cfg::DOF <= 4 ? 3 : 2))
 tfb_spmv_march_kernel(const TfbSpmvArgs a) {
     using M = TfbMarch<Cfg, TJ>;
     constexpr int DOF = Cfg::DOF, W = M::W, H = M::H, DSTR = M::DSTR, SLOT = M::SLOT, LINE_CAP = M::LINE_CAP;
@@ -152,7 +174,7 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
                              !(Cfg::ID == 7 && i <= 1 && j <= 1);
     const int kfar2 = tfb_far2_index(g.nz);
     const int cell_off = (jl + 1) * W + (il + 1);
-    const bool row_on = a.rowmask == 0u || ((a.rowmask >> d1) & 1u);
+    const bool row_on = !MASKED || ((a.rowmask >> d1) & 1u);
     int s0 = 0;
     __syncthreads();
 
@@ -183,16 +205,11 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
             const unsigned m = full ? 0u : Cfg::mask(d1, c);
             double acc = 0.0;
             if (row_on) {
-                switch (d1) {
-                case 0: acc = tfb_row_dot<Cfg, 0, TJ>(vrow, m, full, P, a, i, j, k); break;
-                case 1: acc = tfb_row_dot<Cfg, 1, TJ>(vrow, m, full, P, a, i, j, k); break;
-                case 2: acc = tfb_row_dot<Cfg, 2, TJ>(vrow, m, full, P, a, i, j, k); break;
-                case 3: acc = tfb_row_dot<Cfg, (Cfg::DOF > 3 ? 3 : 0), TJ>(vrow, m, full, P, a, i, j, k); break;
-                case 4: acc = tfb_row_dot<Cfg, (Cfg::DOF > 4 ? 4 : 0), TJ>(vrow, m, full, P, a, i, j, k); break;
-                default: acc = tfb_row_dot<Cfg, (Cfg::DOF > 5 ? 5 : 0), TJ>(vrow, m, full, P, a, i, j, k); break;
-                }
+                const bool pin_near = a.pvar >= 0 && abs(i - a.prow_cell_i) <= 1 && abs(j - a.prow_cell_j) <= 1 &&
+                                      abs(k - a.prow_cell_k) <= 1;
+                acc = tfb_row_dot_any<Cfg, TJ, MASKED>(d1, vrow, m, full, pin_near, P, a, i, j, k);
                 if (d1 == a.pvar && i == a.prow_cell_i && j == a.prow_cell_j && k == a.prow_cell_k)
-                    acc = a.rowmask == 0u ? -P(d1, 0, 0, 0) : 0.0;     // pinned row: -1 on the diagonal (full operator only)
+                    acc = MASKED ? 0.0 : -P(d1, 0, 0, 0);     // pinned row: -1 on the diagonal (full operator only)
                 if (a.rowscale) acc /= a.rowscale[row];
             }
             a.y[row] = acc;
