@@ -133,6 +133,8 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--problem', default='ldc', choices=['ldc', 'rb'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak (default): grid^3 cells per GPU; strong: one grid^3 problem split over the GPUs')
     args = ap.parse_args()
     if args.problem == 'rb':
         PARAMS.clear()
@@ -159,12 +161,15 @@ def main():
 
     grid = args.grid
     # weak scaling: every rank owns `grid` planes of a (grid x grid x world*grid) domain
-    nz = grid * world
+    nz = grid * world if args.scaling == 'weak' else grid
     params = dict(PARAMS)
-    if world > 1:
+    if world > 1 and args.scaling == 'weak':
         params['Z-max'] = float(world)      # the cavity grows with the GPU count: cells stay cubic
-    it = Interface(params, grid, grid, nz, device=local_rank, slab=(rank * grid, (rank + 1) * grid)) \
-        if world > 1 else Interface(params, grid, grid, grid, device=local_rank)
+    if world > 1:
+        from transiflow_b200 import parallel
+        it = Interface(params, grid, grid, nz, device=local_rank, slab=parallel.slab_range(nz, world, rank))
+    else:
+        it = Interface(params, grid, grid, grid, device=local_rank)
     if world > 1:
         from transiflow_b200 import parallel
         parallel.init_comm(it, dist, rank, world)
@@ -272,13 +277,13 @@ def main():
         newton = {'steps_per_s': 1e3 / nms, 'ms_per_step': nms, 'timed_steps': len(timed),
                   'krylov_iterations': [h['iterations'] for h in timed], 'relres': [h['relres'] for h in timed],
                   'fnorm_before': [h['fnorm'] for h in timed], 'all_converged': all(h['converged'] for h in hist),
-                  'tolerance': 1e-10, 'unknowns': n_local * world,
+                  'tolerance': 1e-10, 'unknowns': it.n,
                   'solver': 'FGMRES + LSC block preconditioner (FDM sub-solves), host vectors in/out'
                             + ('; z-slabs: NCCL halo exchange, all-reduce, all-to-all transposes' if world > 1 else '')}
 
     if rank != 0:
         return
-    total_cells = cells_local * world
+    total_cells = (cells_local * world) if args.scaling == 'weak' else grid ** 3
     value = total_cells / (step_ms * 1e-3)
     nnz = it.nnz
     alg_bytes = 8 * nnz + 16 * n_local       # CSR values written + state read + RHS written
@@ -290,10 +295,10 @@ def main():
     line = {
         'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': ('3D lid-driven cavity %d^3 per GPU, Re=100, fused Jacobian+RHS assembly' if args.problem == 'ldc'
                                 else '3D Rayleigh-Benard %d^3 per GPU (dof 5), Ra=1000, fused Jacobian+RHS assembly') % grid,
-                   'grid': [grid, grid, nz], 'unknowns': n_local * world, 'nnz_per_gpu': nnz,
+                   'grid': [grid, grid, nz], 'unknowns': it.n, 'nnz_per_gpu': nnz,
                    'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': ncu_traffic, 'peak_source': peak_src,

@@ -13,6 +13,7 @@ int tfb_fail(const char* file, int line, const char* what, const char* detail) {
     char buf[1024];
     snprintf(buf, sizeof buf, "%s:%d: %s: %s", file, line, what, detail ? detail : "");
     g_tfb_err = buf;
+    cudaGetLastError();   // do not let this failure resurface at the next launch check
     return -1;
 }
 

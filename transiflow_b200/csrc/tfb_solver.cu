@@ -140,8 +140,10 @@ static inline int local_prow(const tfb_ctx* c, int prow) {
 // Column indices are GLOBAL.  Single GPU: x itself.  z-slabs: x is copied between two ghost
 // planes, the halos are exchanged (NCCL) and the kernels index a pointer shifted by the first
 // owned row, so that global columns address the ghosted copy.
+static int dist_setup(tfb_ctx* c);
 static int ghosted(tfb_ctx* c, const double* x, const double** xs) {
     if (c->nranks == 1) { *xs = x; return 0; }
+    if (dist_setup(c)) return -1;
     tfb_solver_state* s = c->solver;
     TFB_CUDA(cudaMemcpyAsync(s->xg + c->plane_rows, x, sizeof(double) * c->n_local, cudaMemcpyDeviceToDevice, c->stream));
     if (tfb_halo_exchange(c, s->xg)) return -1;
