@@ -325,8 +325,12 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     // x/y part of the cell context is plane-invariant
     TfbCell c;
     tfb_cell_flags<Cfg::NFORCE>(g, i, j, a.k0 + kbeg, c);
-    const bool xy_interior = !(c.near[0] | c.far[0] | c.far2[0] | c.near[1] | c.far[1] | c.far2[1]) &&
-                             !(Cfg::ID == 7 && i <= 1 && j <= 1);
+    const bool xy_interior_lane = !(c.near[0] | c.far[0] | c.far2[0] | c.near[1] | c.far[1] | c.far2[1]) &&
+                                  !(Cfg::ID == 7 && i <= 1 && j <= 1);
+    // The choice between the BC-free and the boundary instantiation is made per WARP: a warp that
+    // holds even one wall cell (lanes 0 / 30 / 31 of the x-edge warps) runs the boundary code for all
+    // its lanes instead of running both instantiations under divergence.
+    const bool xy_interior = __all_sync(0xffffffffu, xy_interior_lane || !valid);
     const int kfar2 = tfb_far2_index(g.nz);
     const int cell_off = (jl + 1) * W + (il + 1);
     int s0 = 0;   // ring slot of plane k-1

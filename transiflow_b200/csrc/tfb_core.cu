@@ -312,6 +312,7 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
         switch (variant) {
         case 16: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);
         case 17: return launch_march_v<Cfg, DO_J, DO_F, 4, 16, 1>(c, m);
+        case 24: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 3>(c, m);
         case 18: return launch_march_v<Cfg, DO_J, DO_F, 2, 32, 2>(c, m);
         case 19: return launch_march_v<Cfg, DO_J, DO_F, 2, 8, 2>(c, m);
         case 20: return launch_march_v<Cfg, DO_J, DO_F, 3, 16, 1>(c, m);

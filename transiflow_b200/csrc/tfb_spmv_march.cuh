@@ -170,8 +170,10 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
 
     TfbCell c;
     tfb_cell_flags<0>(g, i, j, a.k0 + kbeg, c);
-    const bool xy_interior = !(c.near[0] | c.far[0] | c.far2[0] | c.near[1] | c.far[1] | c.far2[1]) &&
-                             !(Cfg::ID == 7 && i <= 1 && j <= 1);
+    const bool xy_interior_lane = !(c.near[0] | c.far[0] | c.far2[0] | c.near[1] | c.far[1] | c.far2[1]) &&
+                                  !(Cfg::ID == 7 && i <= 1 && j <= 1);
+    // static-slot fast path only for warps without any wall cell (warp-uniform choice, no double pass)
+    const bool xy_interior_warp = __all_sync(0xffffffffu, xy_interior_lane || !valid);
     const int kfar2 = tfb_far2_index(g.nz);
     const int cell_off = (jl + 1) * W + (il + 1);
     const bool row_on = !MASKED || ((a.rowmask >> d1) & 1u);
@@ -201,8 +203,9 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
             P.pl[0] = ring + s0 * SLOT + cell_off;
             P.pl[1] = ring + s1 * SLOT + cell_off;
             P.pl[2] = ring + s2 * SLOT + cell_off;
-            const bool full = xy_interior && !(c.near[2] | c.far[2] | c.far2[2]);
-            const unsigned m = full ? 0u : Cfg::mask(d1, c);
+            const bool z_interior = !(c.near[2] | c.far[2] | c.far2[2]);
+            const bool full = xy_interior_warp && z_interior;
+            const unsigned m = full ? 0u : ((xy_interior_lane && z_interior) ? ((1u << Cfg::nslot(d1)) - 1u) : Cfg::mask(d1, c));
             double acc = 0.0;
             if (row_on) {
                 const bool pin_near = a.pvar >= 0 && abs(i - a.prow_cell_i) <= 1 && abs(j - a.prow_cell_j) <= 1 &&
