@@ -31,9 +31,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PARAMS = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1}
-# secondary workload (--problem rb): BASELINE config 4, 3-D Rayleigh-Benard (dof 5), assembly only
+# secondary workloads (--problem ...): the other BASELINE configurations
 RB_PARAMS = {'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 1000.0, 'Prandtl Number': 10.0, 'Biot Number': 1.0,
              'X-max': 10, 'Y-max': 10}
+# name: (parameters, nx, ny, description)  -- 2-D configurations run on one GPU at their BASELINE size
+PROBLEMS_2D = {
+    'ldc2d': ({'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1, 'Grid Stretching Factor': 1.5},
+              32, 32, '2D lid-driven cavity 32x32 (stretched), Re=100'),
+    'dhc2d': ({'Problem Type': 'Differentially Heated Cavity', 'Rayleigh Number': 1e6, 'Prandtl Number': 1000,
+               'Reynolds Number': 1, 'X-max': 4.08 / 80, 'Y-max': 1}, 64, 64, '2D differentially heated cavity 64x64, Ra=1e6'),
+    'qg': ({'Problem Type': 'Double Gyre', 'Reynolds Number': 16, 'Rossby Parameter': 1000, 'Wind Stress Parameter': 100},
+           256, 128, '2D quasi-geostrophic double gyre 256x128'),
+    'amoc': ({'Problem Type': 'AMOC', 'Rayleigh Number': 4e4, 'Prandtl Number': 2.25, 'Lewis Number': 1, 'Freshwater Flux': 0,
+              'Temperature Forcing': 0.1, 'X-max': 5}, 256, 128, '2D AMOC 256x128'),
+}
 
 
 def measured_peaks():
@@ -132,7 +143,7 @@ def main():
     ap.add_argument('--grid', type=int, default=128)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--problem', default='ldc', choices=['ldc', 'rb'])
+    ap.add_argument('--problem', default='ldc', choices=['ldc', 'rb'] + sorted(PROBLEMS_2D))
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak (default): grid^3 cells per GPU; strong: one grid^3 problem split over the GPUs')
     args = ap.parse_args()
@@ -140,6 +151,11 @@ def main():
         PARAMS.clear()
         PARAMS.update(RB_PARAMS)
         args.newton_steps = 0
+    two_d = PROBLEMS_2D.get(args.problem)
+    if two_d:
+        PARAMS.clear()
+        PARAMS.update(two_d[0])
+        PARAMS['Iterative Solver'] = {'Maximum Iterations': 4000, 'Restart': 4000}
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -165,7 +181,11 @@ def main():
     params = dict(PARAMS)
     if world > 1 and args.scaling == 'weak':
         params['Z-max'] = float(world)      # the cavity grows with the GPU count: cells stay cubic
-    if world > 1:
+    if two_d:
+        if world > 1:
+            raise SystemExit('2-D configurations are single-GPU ("replicas only", DESIGN.md section 5)')
+        it = Interface(params, two_d[1], two_d[2], 1, device=local_rank)
+    elif world > 1:
         from transiflow_b200 import parallel
         it = Interface(params, grid, grid, nz, device=local_rank, slab=parallel.slab_range(nz, world, rank))
     else:
@@ -283,7 +303,7 @@ def main():
 
     if rank != 0:
         return
-    total_cells = (cells_local * world) if args.scaling == 'weak' else grid ** 3
+    total_cells = (cells_local * world) if (args.scaling == 'weak' or two_d) else grid ** 3
     value = total_cells / (step_ms * 1e-3)
     nnz = it.nnz
     alg_bytes = 8 * nnz + 16 * n_local       # CSR values written + state read + RHS written
@@ -296,9 +316,10 @@ def main():
         'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
         'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': ('3D lid-driven cavity %d^3 per GPU, Re=100, fused Jacobian+RHS assembly' if args.problem == 'ldc'
+        'config': {'workload': (two_d[3] + ', fused Jacobian+RHS assembly (launch-latency bound: absolute numbers only)') if two_d else
+                               ('3D lid-driven cavity %d^3 per GPU, Re=100, fused Jacobian+RHS assembly' if args.problem == 'ldc'
                                 else '3D Rayleigh-Benard %d^3 per GPU (dof 5), Ra=1000, fused Jacobian+RHS assembly') % grid,
-                   'grid': [grid, grid, nz], 'unknowns': it.n, 'nnz_per_gpu': nnz,
+                   'grid': [it.nx, it.ny, it.nz], 'unknowns': it.n, 'nnz_per_gpu': nnz,
                    'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': ncu_traffic, 'peak_source': peak_src,
@@ -311,7 +332,7 @@ def main():
         'newton': newton,
         'spmv': spmv,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not two_d:
         planes = max(2, min(grid, 32))
         v, cores, dt = cpu_port_cells_per_s(grid, planes, repeats=2)
         line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
