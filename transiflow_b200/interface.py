@@ -87,9 +87,9 @@ class DeviceMatrix:
             row_ptr, col = self.interface.pattern()
             vals = self.values()
             keep = numpy.abs(vals) > 1e-14
-            counts = numpy.zeros(self.shape[0] + 1, dtype=numpy.int64)
-            numpy.add.at(counts, numpy.repeat(numpy.arange(self.shape[0]), numpy.diff(row_ptr))[keep] + 1, 1)
-            self._host = sparse.csr_matrix((vals[keep], col[keep], numpy.cumsum(counts)), self.shape)
+            # kept entries per row through one cumulative sum (every structural row is non-empty)
+            csum = numpy.concatenate(([0], numpy.cumsum(keep, dtype=numpy.int64)))
+            self._host = sparse.csr_matrix((vals[keep], col[keep], csum[row_ptr]), self.shape)
         return self._host
 
     def tocsc(self):
