@@ -71,6 +71,11 @@ void tfb_mat_destroy(tfb_mat* mat);
 int tfb_mat_get_values(tfb_mat* mat, double* vals_out);        /* D2H, nnz_local doubles */
 int tfb_mat_set_values(tfb_mat* mat, const double* vals_in);   /* H2D */
 
+/* dst = src + alpha * diag(d): the matrix arithmetic TimeIntegration needs on the backend's matrix type
+ * (`jacobian(x) - mass / (theta * dt)`, TimeIntegration.py:58); d has one entry per local row.  Every row
+ * with d != 0 must have a structural diagonal (all rows with mass do). dst may equal src. */
+int tfb_mat_add_diag(tfb_mat* dst, const tfb_mat* src, double alpha, const double* d);
+
 /* Interface.rhs -> Discretization.rhs (Discretization.py:367-390); host in, host out. */
 int tfb_rhs(tfb_ctx* ctx, const double* state, double* out);
 /* Interface.jacobian -> Discretization.jacobian (:392-415) into `mat`; if rhs_out != NULL the

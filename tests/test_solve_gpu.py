@@ -117,13 +117,17 @@ def test_time_integration_operators():
     jac, mass = it.jacobian(x), it.mass_matrix()
     theta, dt = 1.0, 0.1
     A = jac - mass / (theta * dt)
+    from transiflow_b200 import DeviceMatrix
+    assert isinstance(A, DeviceMatrix)          # diagonal update happens on the device, no host round trip
+    want = (jac.tocsc() - mass / (theta * dt)).tocsr()
+    got = A.tocsr()
+    assert abs(got - want).max() <= 1e-15 * abs(want).max()
     v = numpy.random.default_rng(1).uniform(-1, 1, it.n)
     b = mass @ v + it.rhs(x)
     b[3] = 0
     y = it.solve(A, b)
     assert it.last_solve['converged']
-    from scipy.sparse import csr_matrix
-    Ah = csr_matrix(A).tolil()
+    Ah = A.tocsr().tolil()
     Ah[3, :] = 0
     Ah[:, 3] = 0
     Ah[3, 3] = -1

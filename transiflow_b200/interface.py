@@ -114,14 +114,30 @@ class DeviceMatrix:
     def __neg__(self):
         return -self.tocsc()
 
+    def _plus_diagonal(self, other, sign):
+        '''J +/- D for a diagonal host matrix D (e.g. ``mass / (theta * dt)``): stays on the device.'''
+        from scipy import sparse
+        if not sparse.issparse(other) or other.shape != self.shape or numpy.iscomplexobj(other):
+            return None
+        coo = sparse.coo_matrix(other)
+        if coo.nnz and numpy.any(coo.row != coo.col):
+            return None
+        d = numpy.zeros(self.shape[0])
+        numpy.add.at(d, coo.row, coo.data)
+        out = DeviceMatrix(self.interface)
+        check(_lib.lib().tfb_mat_add_diag(out._h, self._h, ctypes.c_double(sign), ptr(d)))
+        return out
+
     def __add__(self, other):
-        return self.tocsc() + _host_matrix(other)
+        dev = self._plus_diagonal(other, 1.0)
+        return dev if dev is not None else self.tocsc() + _host_matrix(other)
 
     def __radd__(self, other):
         return _host_matrix(other) + self.tocsc()
 
     def __sub__(self, other):
-        return self.tocsc() - _host_matrix(other)
+        dev = self._plus_diagonal(other, -1.0)
+        return dev if dev is not None else self.tocsc() - _host_matrix(other)
 
     def __rsub__(self, other):
         return _host_matrix(other) - self.tocsc()
