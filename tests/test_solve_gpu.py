@@ -165,3 +165,27 @@ def test_parameter_continuation_reaches_the_reference_branch_point():
     assert numpy.abs(x - g['x']).max() <= 1e-8 * numpy.abs(g['x']).max()
     # the reference's un-polished continuation end point lies within its own corrector tolerance of that state
     assert numpy.abs(g['x_continuation'] - x).max() <= 1e-2 * numpy.abs(x).max()
+
+
+def test_implicit_euler_matches_reference_time_integration():
+    """TimeIntegration.integration with theta = 1 (TimeIntegration.py:40-115) restated on the backend's matrix
+    types: mass @ v, jacobian(x) - mass / (theta * dt) (device-side), solve.  Golden: the reference's own run
+    (tests/golden/make_golden_time.py)."""
+    g = numpy.load(os.path.join(GEN, 'time_ldc2d.npz'))
+    params = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1}
+    from transiflow_b200 import Interface
+    it = Interface(params, int(g['nx']), int(g['ny']))
+    theta, dt = 1.0, float(g['dt'])
+    x = it.vector()
+    for _ in range(int(g['steps'])):
+        x0 = x
+        b0 = it.rhs(x0)
+        mass = it.mass_matrix()
+        for k in range(10):
+            fval = mass @ (x0 - x) + dt * theta * it.rhs(x) + dt * (1 - theta) * b0
+            fval /= theta * dt
+            if numpy.linalg.norm(fval) < 1e-10:
+                break
+            jac = it.jacobian(x) - mass / (theta * dt)
+            x = x + it.solve(jac, -fval)
+    assert numpy.abs(x - g['x']).max() <= 1e-8 * numpy.abs(g['x']).max()
