@@ -107,6 +107,33 @@ def cpu_port_cells_per_s(grid, planes, repeats=1):
     return grid * grid * planes / best, lib().tfo_num_threads(), best
 
 
+def parity_gate(device, flat):
+    '''Correctness gate reported with every perf number: a small instance of the same
+    problem against the CPU oracle -- pattern after compress, CSR values, RHS, Newton update.'''
+    from oracle.tf_oracle import Oracle, direct_solve
+    from transiflow_b200 import Interface
+    n = 12
+    params = {k: v for k, v in PARAMS.items() if k != 'Iterative Solver'}
+    it = Interface(dict(params), n, n, 1 if flat else n, device=device)
+    orc = Oracle(dict(params), it.nx, it.ny, it.nz)
+    x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
+    jac, f = it.jacobian_rhs(x)
+    csr = jac.tocsr()
+    coA, jcoA, begA = orc.jacobian(x)
+    fo = orc.rhs(x)
+    out = {'checked_on': '%dx%dx%d instance vs CPU oracle' % (it.nx, it.ny, it.nz),
+           'pattern_exact': bool(numpy.array_equal(csr.indptr, begA) and numpy.array_equal(csr.indices, jcoA)),
+           'values_max_rel_err': float(numpy.max(numpy.abs(csr.data - coA) / numpy.abs(coA))) if len(coA) == csr.nnz else None,
+           'rhs_max_abs_err': float(numpy.abs(f - fo).max())}
+    try:
+        dx = it.solve(jac, -f)
+        want = direct_solve(orc.jacobian_csr(x), -fo, orc.dim, orc.dof)
+        out['newton_update_max_rel_err_vs_spsolve'] = float(numpy.abs(dx - want).max() / numpy.abs(want).max())
+    except Exception as e:     # noqa: BLE001
+        out['newton_update_error'] = str(e)
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -331,6 +358,7 @@ def main():
         'clocks': clocks,
         'newton': newton,
         'spmv': spmv,
+        'parity': parity_gate(local_rank, bool(two_d)),
     }
     if not args.no_cpu_baseline and world == 1 and not two_d:
         planes = max(2, min(grid, 32))
