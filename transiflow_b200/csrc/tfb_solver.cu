@@ -59,7 +59,7 @@ struct tfb_solver_state {
     int sub_prow = -2;
     double* d_mass = nullptr;     // velocity mass diagonal (LSC scaling), n_local
     double* comp[3] = {};         // SoA work arrays, ncell each
-    double* vec[6] = {};          // interleaved work vectors, n_local each
+    double* vec[8] = {};          // interleaved work vectors, n_local each
     double* d_scal = nullptr;     // small device scalars
     // z-slab runs: ghosted copy of a vector, pencil-layout work arrays, all-to-all staging
     double* xg = nullptr;
@@ -70,7 +70,8 @@ struct tfb_solver_state {
     long long a2a_cnt_slab[TFB_MAX_RANKS] = {}, a2a_dsp_slab[TFB_MAX_RANKS] = {};   // slab side (packed by y-chunk)
     long long a2a_cnt_pen[TFB_MAX_RANKS] = {}, a2a_dsp_pen[TFB_MAX_RANKS] = {};     // pencil side (planes of each rank)
     bool dist_ready = false;
-    double* d_V = nullptr;        // Krylov basis  (m+1) x n
+    double* d_V = nullptr;        // Krylov basis  (m+1) x n  (fp64, or fp32 when basis_single)
+    bool basis_single = false;
     double* d_Z = nullptr;        // preconditioned basis  m x n
     double* d_h = nullptr;        // dot products
     int cap = 0;                  // allocated Krylov dimension
@@ -238,7 +239,8 @@ __global__ void k_sub(long long n, const double* __restrict__ a, const double* _
 // h[v] += sum_i V[v][i] * w[i] for all v < nv.  A CTA owns a tile of rows, keeps its w values in
 // registers and walks over the basis vectors; per-warp partial sums are parked in shared memory.
 #define TFB_ORTH_ROWS 4
-__global__ void __launch_bounds__(256) k_all_dots(long long n, const double* __restrict__ V, long long ld, int nv,
+template <class BT>
+__global__ void __launch_bounds__(256) k_all_dots(long long n, const BT* __restrict__ V, long long ld, int nv,
                                                   const double* __restrict__ w, double* __restrict__ out) {
     extern __shared__ double part[];   // [8 warps][nv]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,12 +255,12 @@ __global__ void __launch_bounds__(256) k_all_dots(long long n, const double* __r
             wr[r] = i < n ? w[i] : 0.0;
         }
         for (int v = 0; v < nv; v++) {
-            const double* vp = V + (long long)v * ld;
+            const BT* vp = V + (long long)v * ld;
             double a = 0.0;
 #pragma unroll
             for (int r = 0; r < TFB_ORTH_ROWS; r++) {
                 const long long i = base + r * 256 + threadIdx.x;
-                if (i < n) a += vp[i] * wr[r];
+                if (i < n) a += (double)vp[i] * wr[r];
             }
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
             if (lane == 0) part[warp * nv + v] += a;
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(256) k_all_dots(long long n, const double* __r
     }
 }
 // w += sign * sum_v h[v] V[v]; optionally accumulates |w_new|^2 into *nrm2
-__global__ void __launch_bounds__(256) k_all_axpy(long long n, const double* __restrict__ V, long long ld, int nv,
+template <class BT>
+__global__ void __launch_bounds__(256) k_all_axpy(long long n, const BT* __restrict__ V, long long ld, int nv,
                                                   const double* __restrict__ h, double sign, double* __restrict__ w,
                                                   double* __restrict__ nrm2) {
     extern __shared__ double hs[];
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(256) k_all_axpy(long long n, const double* __r
     double loc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double a = 0.0;
-        for (int v = 0; v < nv; v++) a += hs[v] * V[(long long)v * ld + i];
+        for (int v = 0; v < nv; v++) a += hs[v] * (double)V[(long long)v * ld + i];
         const double wn = w[i] + sign * a;
         w[i] = wn;
         loc += wn * wn;
@@ -297,6 +300,16 @@ __global__ void __launch_bounds__(256) k_all_axpy(long long n, const double* __r
             atomicAdd(nrm2, t);
         }
     }
+}
+
+// y (basis type) = x / scal[idx];  x64 = (double) basis vector
+template <class BT>
+__global__ void k_store_scaled(long long n, const double* __restrict__ scal, int idx, const double* __restrict__ x, BT* __restrict__ y) {
+    const double a = 1.0 / scal[idx];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = (BT)(a * x[i]);
+}
+__global__ void k_widen(long long n, const float* __restrict__ x, double* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = (double)x[i];
 }
 
 static inline unsigned vec_blocks(long long n);
@@ -765,7 +778,7 @@ extern "C" int tfb_fdm_pin(tfb_ctx* c, int var, int64_t cell, double sign) {
     return 0;
 }
 
-static int ensure_buffers(tfb_ctx* c, int krylov) {
+static int ensure_buffers(tfb_ctx* c, int krylov, bool single = false) {
     tfb_solver_state* s = solver_of(c);
     const long long n = c->n_local, ncell = n / c->desc.dof;
     if (!s->d_mass) {
@@ -778,15 +791,17 @@ static int ensure_buffers(tfb_ctx* c, int krylov) {
         for (auto& p : s->vec) TFB_CUDA(cudaMalloc(&p, sizeof(double) * n));
         TFB_CUDA(cudaMalloc(&s->d_scal, sizeof(double) * 16));
     }
-    if (krylov > s->cap) {
+    if (krylov > s->cap || (krylov > 0 && single != s->basis_single)) {
         cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h);
         s->d_V = s->d_Z = s->d_h = nullptr;
         s->cap = 0;
         size_t freeb = 0, total = 0;
         TFB_CUDA(cudaMemGetInfo(&freeb, &total));
-        const size_t need = sizeof(double) * (size_t)n * (2 * (size_t)krylov + 1);
+        const size_t vbytes = single ? sizeof(float) : sizeof(double);
+        const size_t need = (size_t)n * ((size_t)krylov + 1) * vbytes + sizeof(double) * (size_t)n * krylov;
         TFB_CHECK(need < freeb * 0.9, "Krylov basis does not fit in device memory; lower 'Restart'");
-        TFB_CUDA(cudaMalloc(&s->d_V, sizeof(double) * (size_t)n * (krylov + 1)));
+        TFB_CUDA(cudaMalloc(&s->d_V, vbytes * (size_t)n * (krylov + 1)));
+        s->basis_single = single;
         TFB_CUDA(cudaMalloc(&s->d_Z, sizeof(double) * (size_t)n * krylov));
         TFB_CUDA(cudaMalloc(&s->d_h, sizeof(double) * (krylov + 8)));
         s->cap = krylov;
@@ -795,26 +810,28 @@ static int ensure_buffers(tfb_ctx* c, int krylov) {
 }
 
 // h[0..nv) = V^T w   (one pass over the basis)
-static int multi_dot(tfb_ctx* c, const double* V, int nv, const double* w, double* d_out) {
+template <class BT>
+static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d_out) {
     const long long n = c->n_local;
     TFB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * nv, c->stream));
     const unsigned nb = (unsigned)std::min<long long>((n + 1023) / 1024, 148 * 8);
     for (int v0 = 0; v0 < nv; v0 += 512) {     // 8 warps x 512 partial sums = 32 KB of shared memory
         const int cnt = std::min(512, nv - v0);
-        k_all_dots<<<nb, 256, sizeof(double) * 8 * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, w, d_out + v0);
+        k_all_dots<BT><<<nb, 256, sizeof(double) * 8 * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, w, d_out + v0);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
     return tfb_allreduce_sum(c, d_out, nv);
 }
 // w += sign * V h   (one pass over the basis); d_nrm2 (optional, zeroed here) receives the LOCAL |w|^2
-static int multi_axpy(tfb_ctx* c, const double* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2 = nullptr) {
+template <class BT>
+static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2 = nullptr) {
     const long long n = c->n_local;
     if (d_nrm2) TFB_CUDA(cudaMemsetAsync(d_nrm2, 0, sizeof(double), c->stream));
     for (int v0 = 0; v0 < nv; v0 += 2048) {
         const int cnt = std::min(2048, nv - v0);
         const bool last = v0 + cnt >= nv;
-        k_all_axpy<<<vec_blocks(n), 256, sizeof(double) * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, d_h + v0, sign, w,
+        k_all_axpy<BT><<<vec_blocks(n), 256, sizeof(double) * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, d_h + v0, sign, w,
                                                                           last ? d_nrm2 : nullptr);
         TFB_LAUNCHED();
     }
@@ -852,15 +869,17 @@ extern "C" int tfb_precond_apply(tfb_mat* m, const double* r, double* z, int pre
     return 0;
 }
 
-extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
-    TFB_CHECK(m && b && x && o, "null argument");
+// FGMRES driver.  BT = storage type of the Krylov basis V: double, or float ("compressed basis":
+// all arithmetic stays fp64, the basis is only STORED in fp32, which halves the traffic of the
+// orthogonalisation; the residual estimate is then only trusted up to ~1e-6 per cycle and every
+// cycle restarts from the true fp64 residual).  Z (preconditioned directions) is always fp64.
+template <class BT>
+static int fgmres_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
     tfb_ctx* c = m->ctx;
-    TFB_CUDA(cudaSetDevice(c->desc.device));
-    solver_of(c);
-    if (dist_setup(c)) return -1;
     const long long n = c->n_local;
     const int mk = std::max(1, std::min(o->restart, o->maxit));
-    if (ensure_buffers(c, mk)) return -1;
+    constexpr bool SINGLE = sizeof(BT) == 4;
+    if (ensure_buffers(c, mk, SINGLE)) return -1;
     tfb_solver_state* s = c->solver;
     const int prow = o->pressure_row;
     cudaEvent_t e0, e1;
@@ -870,22 +889,23 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     if (sub_refresh(c, m, prow)) return -1;
     double* d_b = s->vec[4];
     double* d_x = s->vec[5];
+    double* w = s->vec[6];        // vector being orthogonalised (fp64)
+    double* v64 = s->vec[7];      // fp64 copy of the current basis vector when the basis is fp32
     TFB_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     TFB_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * n, c->stream));
-    double* V = s->d_V;
+    BT* V = reinterpret_cast<BT*>(s->d_V);
     double* Z = s->d_Z;
     double* d_h = s->d_h;
     std::vector<double> H((size_t)(mk + 1) * mk, 0.0), g(mk + 1), cs(mk), sn(mk), hcol(mk + 2), y(mk);
     auto Hx = [&](int i, int j) -> double& { return H[(size_t)j * (mk + 1) + i]; };
 
-    int total_its = 0, converged = 0, reorth = 0;
-    // optional per-phase device timers (verbose >= 1): precondition, operator, orthogonalise
+    int total_its = 0, converged = 0, reorth = 0, cycles = 0;
     const bool prof = o->verbose >= 1;
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
-    double bnorm = 0.0, relres = 1.0;
+    double bnorm = 0.0, relres = 1.0, prev_true = 1e300;
     {
-        if (multi_dot(c, d_b, 1, d_b, d_h)) return -1;
+        if (multi_dot<double>(c, d_b, 1, d_b, d_h)) return -1;
         TFB_CUDA(cudaMemcpyAsync(&bnorm, d_h, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         TFB_CUDA(cudaStreamSynchronize(c->stream));
         bnorm = sqrt(bnorm);
@@ -895,45 +915,55 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
         if (info) { info->iters = 0; info->converged = 1; info->relres = 0.0; info->setup_ms = info->solve_ms = 0; }
         return 0;
     }
+    // with an fp32 basis the estimate of a cycle is good for ~6 digits: end the cycle there
+    const double cycle_gain = SINGLE ? 1e-6 : 0.0;
     while (total_its < o->maxit && !converged) {
-        // r = b - J x  -> V0
+        // true residual r = b - J x  -> w
         if (total_its == 0) {
-            TFB_CUDA(cudaMemcpyAsync(V, d_b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+            TFB_CUDA(cudaMemcpyAsync(w, d_b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
         } else {
             if (spmv(c, m, d_x, s->vec[0], prow)) return -1;
-            k_sub<<<vec_blocks(n), 256, 0, c->stream>>>(n, d_b, s->vec[0], V);
+            k_sub<<<vec_blocks(n), 256, 0, c->stream>>>(n, d_b, s->vec[0], w);
             TFB_LAUNCHED();
         }
-        if (multi_dot(c, V, 1, V, d_h)) return -1;
+        if (multi_dot<double>(c, w, 1, w, d_h)) return -1;
         double beta = 0.0;
         TFB_CUDA(cudaMemcpyAsync(&beta, d_h, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         TFB_CUDA(cudaStreamSynchronize(c->stream));
         beta = sqrt(beta);
         relres = beta / bnorm;
         if (relres <= o->tol) { converged = 1; break; }
-        {
-            double inv = beta;
-            TFB_CUDA(cudaMemcpyAsync(s->d_scal + 4, &inv, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            k_scale_to<<<vec_blocks(n), 256, 0, c->stream>>>(n, s->d_scal, 4, V, V);
-            TFB_LAUNCHED();
-        }
+        if (cycles > 0 && relres > 0.5 * prev_true) break;     // a whole cycle did not help: stagnation
+        prev_true = relres;
+        cycles++;
+        TFB_CUDA(cudaMemcpyAsync(s->d_scal + 4, &beta, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        k_store_scaled<BT><<<vec_blocks(n), 256, 0, c->stream>>>(n, s->d_scal, 4, w, V);
+        TFB_LAUNCHED();
         std::fill(g.begin(), g.end(), 0.0);
         g[0] = beta;
+        const double cycle_target = std::max(o->tol * bnorm, cycle_gain * beta);
         int j = 0;
         for (; j < mk && total_its < o->maxit; j++, total_its++) {
-            double* vj = V + (size_t)j * n;
+            const BT* vjb = V + (size_t)j * n;
+            const double* vj;
+            if (SINGLE) {
+                k_widen<<<vec_blocks(n), 256, 0, c->stream>>>(n, reinterpret_cast<const float*>(vjb), v64);
+                TFB_LAUNCHED();
+                vj = v64;
+            } else {
+                vj = reinterpret_cast<const double*>(vjb);
+            }
             double* zj = Z + (size_t)j * n;
-            double* w = V + (size_t)(j + 1) * n;
             mark();
             if (apply_precond(c, m, prow, vj, zj)) return -1;
             mark();
             if (spmv(c, m, zj, w, prow)) return -1;
             mark();
-            // classical Gram-Schmidt with fused multi-dots (one pass over the basis per sweep); the
-            // second sweep only runs when the first one cancelled most of w (DGKS criterion)
-            if (multi_dot(c, w, 1, w, d_h + mk + 2)) return -1;            // |w|^2 before
-            if (multi_dot(c, V, j + 1, w, d_h)) return -1;
-            if (multi_axpy(c, V, j + 1, d_h, -1.0, w, d_h + mk + 1)) return -1;   // fused |w|^2 after
+            // classical Gram-Schmidt with single-pass fused kernels; the second sweep only runs when
+            // the first one cancelled most of w (DGKS criterion)
+            if (multi_dot<double>(c, w, 1, w, d_h + mk + 2)) return -1;            // |w|^2 before
+            if (multi_dot<BT>(c, V, j + 1, w, d_h)) return -1;
+            if (multi_axpy<BT>(c, V, j + 1, d_h, -1.0, w, d_h + mk + 1)) return -1;   // fused |w|^2 after
             double nrm[2];
             TFB_CUDA(cudaMemcpyAsync(hcol.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
             TFB_CUDA(cudaMemcpyAsync(nrm, d_h + mk + 1, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
@@ -941,8 +971,8 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             std::vector<double> h2(j + 1, 0.0);
             double hn2 = nrm[0];
             if (nrm[0] < 0.25 * nrm[1]) {
-                if (multi_dot(c, V, j + 1, w, d_h)) return -1;
-                if (multi_axpy(c, V, j + 1, d_h, -1.0, w, d_h + mk + 1)) return -1;
+                if (multi_dot<BT>(c, V, j + 1, w, d_h)) return -1;
+                if (multi_axpy<BT>(c, V, j + 1, d_h, -1.0, w, d_h + mk + 1)) return -1;
                 TFB_CUDA(cudaMemcpyAsync(h2.data(), d_h, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
                 TFB_CUDA(cudaMemcpyAsync(&hn2, d_h + mk + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
                 TFB_CUDA(cudaStreamSynchronize(c->stream));
@@ -954,7 +984,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             Hx(j + 1, j) = hn;
             if (hn > 0.0) {
                 TFB_CUDA(cudaMemcpyAsync(s->d_scal + 4, &hn, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-                k_scale_to<<<vec_blocks(n), 256, 0, c->stream>>>(n, s->d_scal, 4, w, w);
+                k_store_scaled<BT><<<vec_blocks(n), 256, 0, c->stream>>>(n, s->d_scal, 4, w, V + (size_t)(j + 1) * n);
                 TFB_LAUNCHED();
             }
             // Givens rotations
@@ -970,9 +1000,9 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             g[j] = cs[j] * g[j];
             relres = fabs(g[j + 1]) / bnorm;
             if (o->verbose > 1) fprintf(stderr, "  fgmres %4d  relres %.3e\n", total_its + 1, relres);
-            if (relres <= o->tol || hn == 0.0) { j++; total_its++; converged = relres <= o->tol; break; }
+            if (fabs(g[j + 1]) <= cycle_target || hn == 0.0) { j++; total_its++; break; }
         }
-        // x += Z y with H y = g
+        // x += Z y with H y = g; convergence is decided on the TRUE residual at the top of the loop
         const int k = j;
         for (int i = k - 1; i >= 0; i--) {
             double acc = g[i];
@@ -980,14 +1010,14 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
             y[i] = acc / Hx(i, i);
         }
         TFB_CUDA(cudaMemcpyAsync(d_h, y.data(), sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
-        if (multi_axpy(c, Z, k, d_h, 1.0, d_x)) return -1;
+        if (multi_axpy<double>(c, Z, k, d_h, 1.0, d_x)) return -1;
         TFB_CUDA(cudaStreamSynchronize(c->stream));
     }
-    // true residual
+    // true residual of the returned iterate
     if (spmv(c, m, d_x, s->vec[0], prow)) return -1;
     k_sub<<<vec_blocks(n), 256, 0, c->stream>>>(n, d_b, s->vec[0], s->vec[1]);
     TFB_LAUNCHED();
-    if (multi_dot(c, s->vec[1], 1, s->vec[1], d_h)) return -1;
+    if (multi_dot<double>(c, s->vec[1], 1, s->vec[1], d_h)) return -1;
     double rr = 0.0;
     TFB_CUDA(cudaMemcpyAsync(&rr, d_h, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(cudaMemcpyAsync(x, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1001,18 +1031,28 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
         double t[3] = {0, 0, 0};
         for (size_t e = 0; e + 3 < evs.size(); e += 4)
             for (int ph = 0; ph < 3; ph++) { float x_ms = 0; cudaEventElapsedTime(&x_ms, evs[e + ph], evs[e + ph + 1]); t[ph] += x_ms; }
-        fprintf(stderr, "tfb_solve: %d its, %.1f ms total: precond %.1f ms, operator %.1f ms, orthogonalisation %.1f ms, %d re-orth sweeps\n",
-                total_its, ms, t[0], t[1], t[2], reorth);
+        fprintf(stderr, "tfb_solve: %d its in %d cycle(s), %.1f ms total: precond %.1f ms, operator %.1f ms, orthogonalisation %.1f ms, %d re-orth sweeps, %s basis\n",
+                total_its, cycles, ms, t[0], t[1], t[2], reorth, SINGLE ? "fp32" : "fp64");
     }
     for (auto e : evs) cudaEventDestroy(e);
     if (info) {
         info->iters = total_its;
-        info->converged = relres <= o->tol * 10.0;
+        info->converged = relres <= o->tol * 1.0001;
         info->relres = relres;
         info->setup_ms = (float)reorth;   // number of second Gram-Schmidt sweeps (diagnostic)
         info->solve_ms = ms;
     }
-    return relres <= o->tol * 10.0 ? 0 : 1;
+    return relres <= o->tol * 1.0001 ? 0 : 1;
+}
+
+extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
+    TFB_CHECK(m && b && x && o, "null argument");
+    tfb_ctx* c = m->ctx;
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    solver_of(c);
+    if (dist_setup(c)) return -1;
+    if (o->reserved[0] == 1) return fgmres_run<float>(m, b, x, o, info);
+    return fgmres_run<double>(m, b, x, o, info);
 }
 
 // average device time of y = J x over `reps` launches (vectors and matrix resident; the operands

@@ -365,6 +365,9 @@ class Interface:
         o.pressure_row = prow
         o.precond = its.get('Preconditioner Id', 0)
         o.verbose = int(bool(self.parameters.get('Verbose', False)))
+        # 'Basis Precision': 'single' stores the Krylov basis in fp32 (compressed-basis GMRES, all
+        # arithmetic fp64, cycles restart from the true residual); default fp64
+        o.reserved[0] = int(its.get('Basis Precision', 'double') == 'single')
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
