@@ -189,3 +189,19 @@ def test_implicit_euler_matches_reference_time_integration():
             jac = it.jacobian(x) - mass / (theta * dt)
             x = x + it.solve(jac, -fval)
     assert numpy.abs(x - g['x']).max() <= 1e-8 * numpy.abs(g['x']).max()
+
+
+@pytest.mark.parametrize('options', [{'Method': 'BiCGStab'}, {'Basis Precision': 'single', 'Restart': 40}])
+def test_alternative_krylov_options_reach_the_same_solution(options):
+    """BiCGStab and the fp32-stored GMRES basis must deliver the same 1e-10 true residual / SuperLU parity."""
+    name = 'ldc3d_12_str'
+    params, nx, ny, nz = NEWTON_CASES[name]
+    g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
+    params = dict(params)
+    params['Iterative Solver'] = dict(options)
+    from transiflow_b200 import Interface
+    it = Interface(params, nx, ny, nz)
+    jac = it.jacobian(g['x'])
+    y = it.solve(jac, g['b'])
+    assert it.last_solve['converged'], it.last_solve
+    assert numpy.abs(y - g['y']).max() <= 1e-8 * numpy.abs(g['y']).max()

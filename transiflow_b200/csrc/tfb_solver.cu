@@ -1045,12 +1045,142 @@ static int fgmres_run(tfb_mat* m, const double* b, double* x, const tfb_solve_op
     return relres <= o->tol * 1.0001 ? 0 : 1;
 }
 
+// out = a*x + b*y + c*z (null pointers are skipped)
+__global__ void k_lincomb(long long n, double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                          double cc, const double* __restrict__ z, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = a * x[i];
+        if (y) v += b * y[i];
+        if (z) v += cc * z[i];
+        out[i] = v;
+    }
+}
+
+// Right-preconditioned BiCGStab (the preconditioner is a fixed linear operator): 7 work vectors instead
+// of a Krylov basis -- the memory-light alternative when even 180 GB cannot hold an un-restarted GMRES
+// basis.  Two preconditioner applications and two operator products per iteration; convergence is
+// confirmed on the true residual, from which the recurrence is restarted if necessary.
+static int bicgstab_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
+    tfb_ctx* c = m->ctx;
+    const long long n = c->n_local;
+    if (ensure_buffers(c, 5, false)) return -1;
+    tfb_solver_state* s = c->solver;
+    const int prow = o->pressure_row;
+    cudaEvent_t e0, e1;
+    TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
+    TFB_CUDA(cudaEventRecord(e0, c->stream));
+    if (sub_refresh(c, m, prow)) return -1;
+    double* d_b = s->vec[4];
+    double* d_x = s->vec[5];
+    double* W = s->d_V;   // 6 vectors
+    double *r = W, *rh = W + n, *p = W + 2 * n, *v = W + 3 * n, *sv = W + 4 * n, *t = W + 5 * n;
+    double *y = s->d_Z, *z = s->d_Z + n;
+    double* d_h = s->d_h;
+    const unsigned nb = vec_blocks(n);
+    TFB_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    TFB_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * n, c->stream));
+    auto dot = [&](const double* a, const double* bb, double& out) -> int {
+        if (multi_dot<double>(c, a, 1, bb, d_h)) return -1;
+        TFB_CUDA(cudaMemcpyAsync(&out, d_h, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    double bn2 = 0.0;
+    if (dot(d_b, d_b, bn2)) return -1;
+    const double bnorm = sqrt(bn2);
+    int its = 0, converged = 0;
+    double relres = 1.0;
+    if (bnorm == 0.0) {
+        memset(x, 0, sizeof(double) * n);
+        if (info) { info->iters = 0; info->converged = 1; info->relres = 0.0; info->setup_ms = info->solve_ms = 0; }
+        return 0;
+    }
+    double prev_true = 1e300;
+    while (its < o->maxit && !converged) {
+        // (re)start from the true residual
+        if (its == 0) TFB_CUDA(cudaMemcpyAsync(r, d_b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+        else {
+            if (spmv(c, m, d_x, s->vec[0], prow)) return -1;
+            k_sub<<<nb, 256, 0, c->stream>>>(n, d_b, s->vec[0], r);
+            TFB_LAUNCHED();
+        }
+        double rr = 0.0;
+        if (dot(r, r, rr)) return -1;
+        relres = sqrt(rr) / bnorm;
+        if (relres <= o->tol) { converged = 1; break; }
+        if (relres > 0.5 * prev_true && its > 0) break;
+        prev_true = relres;
+        TFB_CUDA(cudaMemcpyAsync(rh, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+        TFB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * n, c->stream));
+        TFB_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * n, c->stream));
+        double rho = 1.0, alpha = 1.0, omega = 1.0;
+        for (; its < o->maxit; its++) {
+            double rho_new = 0.0;
+            if (dot(rh, r, rho_new)) return -1;
+            if (rho_new == 0.0 || omega == 0.0) break;                      // breakdown: restart
+            const double beta = (rho_new / rho) * (alpha / omega);
+            k_lincomb<<<nb, 256, 0, c->stream>>>(n, 1.0, r, beta, p, -beta * omega, v, p);   // p = r + beta (p - omega v)
+            TFB_LAUNCHED();
+            if (apply_precond(c, m, prow, p, y)) return -1;
+            if (spmv(c, m, y, v, prow)) return -1;
+            double rhv = 0.0;
+            if (dot(rh, v, rhv)) return -1;
+            if (rhv == 0.0) break;
+            alpha = rho_new / rhv;
+            k_lincomb<<<nb, 256, 0, c->stream>>>(n, 1.0, r, -alpha, v, 0.0, nullptr, sv);          // s = r - alpha v
+            TFB_LAUNCHED();
+            double ss = 0.0;
+            if (dot(sv, sv, ss)) return -1;
+            if (sqrt(ss) / bnorm <= o->tol) {
+                k_axpy<<<nb, 256, 0, c->stream>>>(n, alpha, y, d_x);
+                TFB_LAUNCHED();
+                its++;
+                break;
+            }
+            if (apply_precond(c, m, prow, sv, z)) return -1;
+            if (spmv(c, m, z, t, prow)) return -1;
+            double ts = 0.0, tt = 0.0;
+            if (dot(t, sv, ts) || dot(t, t, tt)) return -1;
+            if (tt == 0.0) break;
+            omega = ts / tt;
+            k_lincomb<<<nb, 256, 0, c->stream>>>(n, 1.0, d_x, alpha, y, omega, z, d_x);            // x += alpha y + omega z
+            k_lincomb<<<nb, 256, 0, c->stream>>>(n, 1.0, sv, -omega, t, 0.0, nullptr, r);          // r = s - omega t
+            TFB_LAUNCHED(); TFB_LAUNCHED();
+            rho = rho_new;
+            double rn = 0.0;
+            if (dot(r, r, rn)) return -1;
+            relres = sqrt(rn) / bnorm;
+            if (o->verbose > 1) fprintf(stderr, "  bicgstab %4d  relres %.3e\n", its + 1, relres);
+            if (relres <= o->tol) { its++; break; }
+        }
+    }
+    if (spmv(c, m, d_x, s->vec[0], prow)) return -1;
+    k_sub<<<nb, 256, 0, c->stream>>>(n, d_b, s->vec[0], s->vec[1]);
+    TFB_LAUNCHED();
+    double rr = 0.0;
+    if (dot(s->vec[1], s->vec[1], rr)) return -1;
+    TFB_CUDA(cudaMemcpyAsync(x, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaEventRecord(e1, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    relres = sqrt(rr) / bnorm;
+    if (o->verbose >= 1) fprintf(stderr, "tfb_solve: BiCGStab %d its, %.1f ms, true relres %.2e\n", its, ms, relres);
+    if (info) {
+        info->iters = its; info->converged = relres <= o->tol * 1.0001; info->relres = relres;
+        info->setup_ms = 0.f; info->solve_ms = ms;
+    }
+    return relres <= o->tol * 1.0001 ? 0 : 1;
+}
+
 extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
     TFB_CHECK(m && b && x && o, "null argument");
     tfb_ctx* c = m->ctx;
     TFB_CUDA(cudaSetDevice(c->desc.device));
     solver_of(c);
     if (dist_setup(c)) return -1;
+    if (o->reserved[1] == 1) return bicgstab_run(m, b, x, o, info);
     if (o->reserved[0] == 1) return fgmres_run<float>(m, b, x, o, info);
     return fgmres_run<double>(m, b, x, o, info);
 }

@@ -368,6 +368,7 @@ class Interface:
         # 'Basis Precision': 'single' stores the Krylov basis in fp32 (compressed-basis GMRES, all
         # arithmetic fp64, cycles restart from the true residual); default fp64
         o.reserved[0] = int(its.get('Basis Precision', 'double') == 'single')
+        o.reserved[1] = int(str(its.get('Method', 'FGMRES')).lower() == 'bicgstab')
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
