@@ -118,7 +118,8 @@ typedef struct {
     int32_t pressure_row;
     int32_t precond;        /* TFB_PREC_* */
     int32_t verbose;
-    int32_t reserved[3];    /* reserved[0] = 1: fp32 storage of the GMRES basis (arithmetic fp64); reserved[1] = 1: BiCGStab */
+    int32_t reserved[3];    /* reserved[0] = 1: fp32 storage of the GMRES basis (arithmetic fp64); reserved[1] = 1: BiCGStab;
+                       reserved[2] = 1: FDM sub-solves of the preconditioner in fp32 */
 } tfb_solve_opts;
 typedef struct {
     int32_t iters, converged;

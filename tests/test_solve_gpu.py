@@ -191,7 +191,10 @@ def test_implicit_euler_matches_reference_time_integration():
     assert numpy.abs(x - g['x']).max() <= 1e-8 * numpy.abs(g['x']).max()
 
 
-@pytest.mark.parametrize('options', [{'Method': 'BiCGStab'}, {'Basis Precision': 'single', 'Restart': 40}])
+@pytest.mark.parametrize('options', [{'Method': 'BiCGStab'}, {'Basis Precision': 'single', 'Restart': 40},
+                                     {'Preconditioner Precision': 'single'},
+                                     {'Preconditioner Precision': 'single', 'Basis Precision': 'single'},
+                                     {'Velocity Iterations': 3}])
 def test_alternative_krylov_options_reach_the_same_solution(options):
     """BiCGStab and the fp32-stored GMRES basis must deliver the same 1e-10 true residual / SuperLU parity."""
     name = 'ldc3d_12_str'

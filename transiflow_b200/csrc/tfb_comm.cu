@@ -7,7 +7,7 @@
 
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef void* ncclComm_t_;
-enum { NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
 static struct {
     void* handle;
@@ -81,21 +81,30 @@ extern "C" int tfb_comm_init(tfb_ctx* c, int nranks, int rank, const uint8_t id[
 }
 
 // personalised all-to-all of doubles (counts / displacements in elements), own block by memcpy
-int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
-                  double* recv, const long long* rcount, const long long* rdispl) {
+int tfb_alltoallv_bytes(tfb_ctx* c, const void* send, const long long* scount, const long long* sdispl, void* recv,
+                        const long long* rcount, const long long* rdispl, int elem_bytes) {
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    TFB_CHECK(elem_bytes == 8 || elem_bytes == 4, "element size");
     ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    const int dt = elem_bytes == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32;
+    const char* sp = (const char*)send;
+    char* rp = (char*)recv;
     TFB_NCCL(nccl.GroupStart());
     for (int r = 0; r < c->nranks; r++) {
         if (r == c->rank) continue;
-        if (scount[r] > 0) TFB_NCCL(nccl.Send(send + sdispl[r], (size_t)scount[r], NCCL_FLOAT64, r, comm, c->stream));
-        if (rcount[r] > 0) TFB_NCCL(nccl.Recv(recv + rdispl[r], (size_t)rcount[r], NCCL_FLOAT64, r, comm, c->stream));
+        if (scount[r] > 0) TFB_NCCL(nccl.Send(sp + sdispl[r] * elem_bytes, (size_t)scount[r], dt, r, comm, c->stream));
+        if (rcount[r] > 0) TFB_NCCL(nccl.Recv(rp + rdispl[r] * elem_bytes, (size_t)rcount[r], dt, r, comm, c->stream));
     }
     TFB_NCCL(nccl.GroupEnd());
-    TFB_CUDA(cudaMemcpyAsync(recv + rdispl[c->rank], send + sdispl[c->rank], sizeof(double) * scount[c->rank],
-                             cudaMemcpyDeviceToDevice, c->stream));
+    TFB_CUDA(cudaMemcpyAsync(rp + rdispl[c->rank] * elem_bytes, sp + sdispl[c->rank] * elem_bytes,
+                             (size_t)elem_bytes * scount[c->rank], cudaMemcpyDeviceToDevice, c->stream));
     TFB_LAUNCHED();
     return 0;
+}
+
+int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
+                  double* recv, const long long* rcount, const long long* rdispl) {
+    return tfb_alltoallv_bytes(c, send, scount, sdispl, recv, rcount, rdispl, 8);
 }
 
 // One-layer halo exchange of a slab vector stored with ghost planes:

@@ -25,6 +25,8 @@
 #include "tfb_internal.h"
 
 int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
+int tfb_alltoallv_bytes(tfb_ctx* c, const void* send, const long long* scount, const long long* sdispl, void* recv,
+                        const long long* rcount, const long long* rdispl, int elem_bytes);
 
 #define TFB_MAXVAR 6
 
@@ -33,6 +35,8 @@ struct FdmVar {
     int m[3] = {0, 0, 0};         // active extent per axis (n-1 along the velocity's own axis)
     double* Q[3] = {nullptr, nullptr, nullptr};   // m x m, row-major, M-orthonormal eigenvectors
     double* lam[3] = {nullptr, nullptr, nullptr}; // m generalized eigenvalues
+    float* Qf[3] = {nullptr, nullptr, nullptr};   // fp32 copies for the single-precision preconditioner
+    float* lamf[3] = {nullptr, nullptr, nullptr};
     double coef = 1.0;
     double maxden = 0.0;
     long long pin_cell = -1;      // singular (all-Neumann) scalar operators are pinned at one cell
@@ -70,6 +74,14 @@ struct tfb_solver_state {
     long long a2a_cnt_slab[TFB_MAX_RANKS] = {}, a2a_dsp_slab[TFB_MAX_RANKS] = {};   // slab side (packed by y-chunk)
     long long a2a_cnt_pen[TFB_MAX_RANKS] = {}, a2a_dsp_pen[TFB_MAX_RANKS] = {};     // pencil side (planes of each rank)
     bool dist_ready = false;
+    bool precond_single = false;  // apply the FDM sub-solves in fp32 (FGMRES keeps the outer iteration exact)
+    // velocity sub-solve: inner GMRES on the convection-diffusion block, preconditioned by the FDM solve
+    int inner_its = 0;            // 0: one FDM (diffusion-only) solve
+    double inner_tol = 1e-2;
+    double* d_Vi = nullptr;       // (inner_cap + 1) x n
+    double* d_Zi = nullptr;       // inner_cap x n
+    int inner_cap = 0;
+    long long inner_total = 0;    // inner iterations of the current solve (diagnostic)
     double* d_V = nullptr;        // Krylov basis  (m+1) x n  (fp64, or fp32 when basis_single)
     bool basis_single = false;
     double* d_Z = nullptr;        // preconditioned basis  m x n
@@ -80,13 +92,13 @@ struct tfb_solver_state {
 void tfb_solver_free(tfb_solver_state* s) {
     if (!s) return;
     for (auto& v : s->var)
-        for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); }
+        for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); cudaFree(v.Qf[a]); cudaFree(v.lamf[a]); }
     for (SubCsr* q : {&s->subG, &s->subD, &s->subB}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
     cudaFree(s->d_mass);
     for (auto p : s->comp) cudaFree(p);
     for (auto p : s->vec) cudaFree(p);
     cudaFree(s->xg); cudaFree(s->pen[0]); cudaFree(s->pen[1]); cudaFree(s->sbuf); cudaFree(s->rbuf);
-    cudaFree(s->d_scal); cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h);
+    cudaFree(s->d_scal); cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h); cudaFree(s->d_Vi); cudaFree(s->d_Zi);
     delete s;
 }
 
@@ -379,50 +391,52 @@ static inline unsigned vec_blocks(long long n) { return (unsigned)std::min<long 
 // ------------------------------------------------------------------------------------
 // FDM building blocks (SoA arrays of one variable, dims (nz, ny, nx), x fastest)
 // ------------------------------------------------------------------------------------
-__global__ void k_deinterleave(long long ncell, int dof, int v, const double* __restrict__ x, double* __restrict__ c) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) c[i] = x[i * dof + v];
+template <class FT>
+__global__ void k_deinterleave(long long ncell, int dof, int v, const double* __restrict__ x, FT* __restrict__ c) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) c[i] = (FT)x[i * dof + v];
 }
-__global__ void k_interleave(long long ncell, int dof, int v, const double* __restrict__ c, double* __restrict__ x, double sign) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) x[i * dof + v] = sign * c[i];
+template <class FT>
+__global__ void k_interleave(long long ncell, int dof, int v, const FT* __restrict__ c, double* __restrict__ x, double sign) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) x[i * dof + v] = sign * (double)c[i];
 }
 
 // C(b, m, n) = sum_k A(b, m, k) * Q(k, n)   [TRANS: Q(n, k)],   A/C element (b,m,k) at b*sb + m*sm + k*sk.
 // 64 x 64 output tile per CTA, 16-deep k-slabs in shared memory, 4 x 4 outputs per thread, fp64 FMA.
-template <bool TRANS>
+template <bool TRANS, class FT>
 __global__ void __launch_bounds__(256)
-k_axis_gemm(const double* __restrict__ A, double* __restrict__ C, const double* __restrict__ Q, int ldq,
+k_axis_gemm(const FT* __restrict__ A, FT* __restrict__ C, const FT* __restrict__ Q, int ldq,
             int M, int K, int N, long long sm, long long sk, long long sb) {
-    __shared__ double As[16][64 + 1];
-    __shared__ double Qs[16][64 + 1];
+    __shared__ FT As[16][64 + 1];
+    __shared__ FT Qs[16][64 + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-    const double* Ab = A + (long long)blockIdx.z * sb;
-    double* Cb = C + (long long)blockIdx.z * sb;
-    double acc[4][4];
+    const FT* Ab = A + (long long)blockIdx.z * sb;
+    FT* Cb = C + (long long)blockIdx.z * sb;
+    FT acc[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+        for (int b = 0; b < 4; b++) acc[a][b] = (FT)0;
     for (int k0 = 0; k0 < K; k0 += 16) {
         // A tile: 64 (m) x 16 (k); pick the thread->element map that follows the unit stride
         for (int e = threadIdx.x; e < 64 * 16; e += 256) {
             int mm, kk;
             if (sk == 1) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
             const int gm = m0 + mm, gk = k0 + kk;
-            As[kk][mm] = (gm < M && gk < K) ? Ab[gm * sm + gk * sk] : 0.0;
+            As[kk][mm] = (gm < M && gk < K) ? Ab[gm * sm + gk * sk] : (FT)0;
         }
         for (int e = threadIdx.x; e < 16 * 64; e += 256) {
             int kk, nn;
             if (TRANS) { kk = e & 15; nn = e >> 4; } else { nn = e & 63; kk = e >> 6; }
             const int gk = k0 + kk, gn = n0 + nn;
-            double q = 0.0;
+            FT q = (FT)0;
             if (gk < K && gn < N) q = TRANS ? Q[(long long)gn * ldq + gk] : Q[(long long)gk * ldq + gn];
             Qs[kk][nn] = q;
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; kk++) {
-            double a[4], q[4];
+            FT a[4], q[4];
 #pragma unroll
             for (int r = 0; r < 4; r++) a[r] = As[kk][ty * 4 + r];
 #pragma unroll
@@ -445,21 +459,23 @@ k_axis_gemm(const double* __restrict__ A, double* __restrict__ C, const double* 
 
 // t /= coef*(lx[i]+ly[j]+lz[k]) on an array of extents (ex, ey, ez) that is a window of the grid
 // starting at global (0, jofs, kofs); m* = active global extents
+template <class FT>
 __global__ void k_fdm_scale(int ex, int ey, int ez, int jofs, int kofs, int mx, int my, int mz, const double* __restrict__ lx,
                             const double* __restrict__ ly, const double* __restrict__ lz, double coef, double thresh,
-                            double* __restrict__ t) {
+                            FT* __restrict__ t) {
     const long long ncell = (long long)ex * ey * ez;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(c % ex), j = jofs + (int)((c / ex) % ey), k = kofs + (int)(c / ((long long)ex * ey));
         if (i < mx && j < my && k < mz) {
             const double den = coef * (lx[i] + ly[j] + (lz ? lz[k] : 0.0));
-            t[c] = fabs(den) > thresh ? t[c] / den : 0.0;
+            t[c] = fabs(den) > thresh ? (FT)((double)t[c] / den) : (FT)0;
         }
     }
 }
 
 // wall-normal boundary unknowns (index >= m along the own axis) have the row -1 * u
-__global__ void k_fdm_walls(int nx, int ny, int nzl, int kofs, int mx, int my, int mz, const double* __restrict__ in, double* __restrict__ out) {
+template <class FT>
+__global__ void k_fdm_walls(int nx, int ny, int nzl, int kofs, int mx, int my, int mz, const FT* __restrict__ in, FT* __restrict__ out) {
     const long long ncell = (long long)nx * ny * nzl;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(c % nx), j = (int)((c / nx) % ny), k = kofs + (int)(c / ((long long)nx * ny));
@@ -469,8 +485,8 @@ __global__ void k_fdm_walls(int nx, int ny, int nzl, int kofs, int mx, int my, i
 
 // slab layout [kl][j][i]  <->  all-to-all buffer packed by destination y-chunk: [r][kl][jj][i]
 struct TfbChunks { int n; int j0[TFB_MAX_RANKS + 1]; long long dsp[TFB_MAX_RANKS]; };
-template <bool PACK>
-__global__ void k_a2a_pack(int nx, int ny, int nzl, TfbChunks ch, double* __restrict__ slab, double* __restrict__ buf) {
+template <bool PACK, class FT>
+__global__ void k_a2a_pack(int nx, int ny, int nzl, TfbChunks ch, FT* __restrict__ slab, FT* __restrict__ buf) {
     const long long ncell = (long long)nx * ny * nzl;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(c % nx), j = (int)((c / nx) % ny), kl = (int)(c / ((long long)nx * ny));
@@ -483,9 +499,10 @@ __global__ void k_a2a_pack(int nx, int ny, int nzl, TfbChunks ch, double* __rest
 }
 
 // pinned Neumann Poisson: make the rhs compatible / shift the solution so that cell `pc` is the pin
-__global__ void k_sum(long long n, const double* __restrict__ x, double* __restrict__ out) {
+template <class FT>
+__global__ void k_sum(long long n, const FT* __restrict__ x, double* __restrict__ out) {
     double a = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a += x[i];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a += (double)x[i];
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     __shared__ double red[8];
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
@@ -496,17 +513,20 @@ __global__ void k_sum(long long n, const double* __restrict__ x, double* __restr
         atomicAdd(out, s);
     }
 }
-__global__ void k_pin_rhs(double* rp, long long pc, double* scal) {   // scal[0] = sum(rp) on entry
-    const double r0 = rp[pc];
+template <class FT>
+__global__ void k_pin_rhs(FT* rp, long long pc, double* scal) {   // scal[0] = sum(rp) on entry
+    const double r0 = (double)rp[pc];
     scal[1] = r0;
-    rp[pc] = -(scal[0] - r0);
+    rp[pc] = (FT)(-(scal[0] - r0));
 }
-__global__ void k_pin_shift(long long n, double* q, long long pc, const double* __restrict__ scal, double* qpin, double sign) {
+template <class FT>
+__global__ void k_pin_shift(long long n, FT* q, long long pc, const double* __restrict__ scal, double* qpin, double sign) {
     const double q0 = *qpin;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        q[i] = (i == pc) ? sign * scal[1] : q[i] - q0;
+        q[i] = (i == pc) ? (FT)(sign * scal[1]) : (FT)((double)q[i] - q0);
 }
-__global__ void k_copy1(const double* src, double* dst) { *dst = *src; }
+template <class FT>
+__global__ void k_copy1(const FT* src, double* dst) { *dst = (double)*src; }
 
 // ---- optional cuBLAS path for the FDM transforms (they are plain dense GEMMs) ----
 // libcublas is dlopen'ed; when it is absent the hand-written k_axis_gemm above is used.
@@ -520,6 +540,8 @@ static struct {
     int (*SetStream)(cublasHandle_t_, cudaStream_t);
     int (*DgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const double*, const double*, int, long long,
                                const double*, int, long long, const double*, double*, int, long long, int);
+    int (*SgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const float*, const float*, int, long long,
+                               const float*, int, long long, const float*, float*, int, long long, int);
 } g_blas;
 
 static bool blas_ready(tfb_ctx* c) {
@@ -536,7 +558,10 @@ static bool blas_ready(tfb_ctx* c) {
                 *(void**)(&g_blas.Create) = dlsym(g_blas.lib, "cublasCreate_v2");
                 *(void**)(&g_blas.SetStream) = dlsym(g_blas.lib, "cublasSetStream_v2");
                 *(void**)(&g_blas.DgemmStridedBatched) = dlsym(g_blas.lib, "cublasDgemmStridedBatched");
-                if (g_blas.Create && g_blas.SetStream && g_blas.DgemmStridedBatched && g_blas.Create(&g_blas.h) == 0) g_blas.state = 1;
+                *(void**)(&g_blas.SgemmStridedBatched) = dlsym(g_blas.lib, "cublasSgemmStridedBatched");
+                if (g_blas.Create && g_blas.SetStream && g_blas.DgemmStridedBatched && g_blas.SgemmStridedBatched &&
+                    g_blas.Create(&g_blas.h) == 0)
+                    g_blas.state = 1;
             }
         }
     }
@@ -544,25 +569,34 @@ static bool blas_ready(tfb_ctx* c) {
     return g_blas.state == 1;
 }
 
-static int axis_gemm(tfb_ctx* c, bool trans, const double* A, double* C, const double* Q, int ldq, int M, int K, int N,
+static inline int blas_gemm(int ta, int tb, int m, int n, int k, const double* A, int lda, long long sa, const double* B,
+                            int ldb, long long sbb, double* C, int ldc, long long sc, int batches) {
+    const double one = 1.0, zero = 0.0;
+    return g_blas.DgemmStridedBatched(g_blas.h, ta, tb, m, n, k, &one, A, lda, sa, B, ldb, sbb, &zero, C, ldc, sc, batches);
+}
+static inline int blas_gemm(int ta, int tb, int m, int n, int k, const float* A, int lda, long long sa, const float* B,
+                            int ldb, long long sbb, float* C, int ldc, long long sc, int batches) {
+    const float one = 1.f, zero = 0.f;
+    return g_blas.SgemmStridedBatched(g_blas.h, ta, tb, m, n, k, &one, A, lda, sa, B, ldb, sbb, &zero, C, ldc, sc, batches);
+}
+
+template <class FT>
+static int axis_gemm(tfb_ctx* c, bool trans, const FT* A, FT* C, const FT* Q, int ldq, int M, int K, int N,
                      long long sm, long long sk, long long sb, int batches) {
     if (blas_ready(c)) {
-        const double one = 1.0, zero = 0.0;
         int rc;
         enum { OP_N = 0, OP_T = 1 };
         if (sk == 1)   // rows of A are the lines: C_cm(N x M) = op(Q_cm) * A_cm(K x M)
-            rc = g_blas.DgemmStridedBatched(g_blas.h, trans ? OP_T : OP_N, OP_N, N, M, K, &one, Q, ldq, 0, A, (int)sm, sb,
-                                            &zero, C, (int)sm, sb, batches);
+            rc = blas_gemm(trans ? OP_T : OP_N, OP_N, N, M, K, Q, ldq, 0, A, (int)sm, sb, C, (int)sm, sb, batches);
         else           // columns of A_cm are the lines' entries: C_cm(M x N) = A_cm(M x K) * op(Q_cm)
-            rc = g_blas.DgemmStridedBatched(g_blas.h, OP_N, trans ? OP_N : OP_T, M, N, K, &one, A, (int)sk, sb, Q, ldq, 0,
-                                            &zero, C, (int)sk, sb, batches);
+            rc = blas_gemm(OP_N, trans ? OP_N : OP_T, M, N, K, A, (int)sk, sb, Q, ldq, 0, C, (int)sk, sb, batches);
         TFB_LAUNCHED();
-        TFB_CHECK(rc == 0, "cublasDgemmStridedBatched failed");
+        TFB_CHECK(rc == 0, "cublas gemmStridedBatched failed");
         return 0;
     }
     dim3 grid((M + 63) / 64, (N + 63) / 64, batches);
-    if (trans) k_axis_gemm<true><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
-    else k_axis_gemm<false><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
+    if (trans) k_axis_gemm<true, FT><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
+    else k_axis_gemm<false, FT><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -600,31 +634,36 @@ static int dist_setup(tfb_ctx* c) {
 }
 
 // out = Op_v^-1 in  (SoA arrays of the local slab; `in` is preserved, tmp is scratch)
-static int fdm_solve(tfb_ctx* c, int v, double* in, double* tmp, double* out, double* keep_in) {
+template <class FT> static inline FT* const* fdm_q(const FdmVar& f);
+template <> inline double* const* fdm_q<double>(const FdmVar& f) { return f.Q; }
+template <> inline float* const* fdm_q<float>(const FdmVar& f) { return f.Qf; }
+
+template <class FT>
+static int fdm_solve(tfb_ctx* c, int v, FT* in, FT* tmp, FT* out) {
     tfb_solver_state* s = c->solver;
     const FdmVar& f = s->var[v];
+    FT* const* Q = fdm_q<FT>(f);
     TFB_CHECK(f.present, "FDM operator missing for a variable (tfb_fdm_set)");
     const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl, k0 = c->desc.k0;
     const long long ncell = (long long)nx * ny * nzl;
     const bool three = c->desc.dim == 3 && nz > 1;
     const int mx = f.m[0], my = f.m[1], mz = three ? f.m[2] : nz;
     const double thresh = 1e-12 * fabs(f.coef) * f.maxden;
-    (void)keep_in;
     // forward: x, y on the local planes
-    if (axis_gemm(c, false, in, tmp, f.Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
-    if (axis_gemm(c, false, tmp, out, f.Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
-    double* cur = out;
-    double* oth = tmp;
+    if (axis_gemm(c, false, in, tmp, Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
+    if (axis_gemm(c, false, tmp, out, Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
+    FT* cur = out;
+    FT* oth = tmp;
     if (c->nranks == 1) {
         if (three) {
-            if (axis_gemm(c, false, cur, oth, f.Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
+            if (axis_gemm(c, false, cur, oth, Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
             std::swap(cur, oth);
         }
-        k_fdm_scale<<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nz, 0, 0, mx, my, mz, f.lam[0], f.lam[1],
+        k_fdm_scale<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nz, 0, 0, mx, my, mz, f.lam[0], f.lam[1],
                                                              three ? f.lam[2] : nullptr, f.coef, thresh, cur);
         TFB_LAUNCHED();
         if (three) {
-            if (axis_gemm(c, true, cur, oth, f.Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
+            if (axis_gemm(c, true, cur, oth, Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
             std::swap(cur, oth);
         }
     } else {
@@ -638,26 +677,27 @@ static int fdm_solve(tfb_ctx* c, int v, double* in, double* tmp, double* out, do
         for (int r = 0; r < c->nranks; r++) ch.dsp[r] = s->a2a_dsp_slab[r];
         const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
         const long long npen = (long long)nz * cyme * nx, lines = (long long)cyme * nx;
-        k_a2a_pack<true><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, cur, s->sbuf);
+        FT *pen0 = (FT*)s->pen[0], *pen1 = (FT*)s->pen[1], *sbuf = (FT*)s->sbuf, *rbuf = (FT*)s->rbuf;
+        k_a2a_pack<true, FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, cur, sbuf);
         TFB_LAUNCHED();
-        if (tfb_alltoallv(c, s->sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, s->pen[0], s->a2a_cnt_pen, s->a2a_dsp_pen)) return -1;
-        if (axis_gemm(c, false, s->pen[0], s->pen[1], f.Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
-        k_fdm_scale<<<vec_blocks(npen), 256, 0, c->stream>>>(nx, cyme, nz, s->j0s[c->rank], 0, mx, my, mz, f.lam[0], f.lam[1],
-                                                            f.lam[2], f.coef, thresh, s->pen[1]);
+        if (tfb_alltoallv_bytes(c, sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, pen0, s->a2a_cnt_pen, s->a2a_dsp_pen, (int)sizeof(FT))) return -1;
+        if (axis_gemm(c, false, pen0, pen1, Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
+        k_fdm_scale<FT><<<vec_blocks(npen), 256, 0, c->stream>>>(nx, cyme, nz, s->j0s[c->rank], 0, mx, my, mz, f.lam[0], f.lam[1],
+                                                            f.lam[2], f.coef, thresh, pen1);
         TFB_LAUNCHED();
-        if (axis_gemm(c, true, s->pen[1], s->pen[0], f.Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
-        if (tfb_alltoallv(c, s->pen[0], s->a2a_cnt_pen, s->a2a_dsp_pen, s->rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab)) return -1;
-        k_a2a_pack<false><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, cur, s->rbuf);
+        if (axis_gemm(c, true, pen1, pen0, Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
+        if (tfb_alltoallv_bytes(c, pen0, s->a2a_cnt_pen, s->a2a_dsp_pen, rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, (int)sizeof(FT))) return -1;
+        k_a2a_pack<false, FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, cur, rbuf);
         TFB_LAUNCHED();
     }
-    if (axis_gemm(c, true, cur, oth, f.Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
+    if (axis_gemm(c, true, cur, oth, Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
     std::swap(cur, oth);
     // last transform must land in `out`
-    double* dst = (cur == out) ? tmp : out;
-    if (axis_gemm(c, true, cur, dst, f.Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
-    if (dst != out) TFB_CUDA(cudaMemcpyAsync(out, dst, sizeof(double) * ncell, cudaMemcpyDeviceToDevice, c->stream));
+    FT* dst = (cur == out) ? tmp : out;
+    if (axis_gemm(c, true, cur, dst, Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
+    if (dst != out) TFB_CUDA(cudaMemcpyAsync(out, dst, sizeof(FT) * ncell, cudaMemcpyDeviceToDevice, c->stream));
     if (mx < nx || my < ny || mz < nz) {
-        k_fdm_walls<<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, k0, mx, my, mz, in, out);
+        k_fdm_walls<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, k0, mx, my, mz, in, out);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
@@ -666,7 +706,8 @@ static int fdm_solve(tfb_ctx* c, int v, double* in, double* tmp, double* out, do
 
 // pinned Poisson solve on SoA arrays: q = Lp_pinned^-1 rp ; rp is modified at the pin.
 // pin_cell is a GLOBAL cell index; with z-slabs the sum and the pinned value are all-reduced.
-static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, double* rp, double* tmp, double* q, double pin_sign = 1.0) {
+template <class FT>
+static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, FT* rp, FT* tmp, FT* q, double pin_sign = 1.0) {
     tfb_solver_state* s = c->solver;
     const long long ncell = c->n_local / c->desc.dof;
     const long long cell0 = c->row0 / c->desc.dof;
@@ -674,30 +715,139 @@ static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, double* rp, d
     const long long pl = pin_cell - cell0;
     if (pin_cell >= 0) {
         TFB_CUDA(cudaMemsetAsync(s->d_scal, 0, sizeof(double) * 3, c->stream));
-        k_sum<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, rp, s->d_scal);
+        k_sum<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, rp, s->d_scal);
         TFB_LAUNCHED();
         if (tfb_allreduce_sum(c, s->d_scal, 1)) return -1;
-        if (owner) { k_pin_rhs<<<1, 1, 0, c->stream>>>(rp, pl, s->d_scal); TFB_LAUNCHED(); }
+        if (owner) { k_pin_rhs<FT><<<1, 1, 0, c->stream>>>(rp, pl, s->d_scal); TFB_LAUNCHED(); }
     }
-    if (fdm_solve(c, pvar, rp, tmp, q, nullptr)) return -1;
+    if (fdm_solve<FT>(c, pvar, rp, tmp, q)) return -1;
     if (pin_cell >= 0) {
-        if (owner) { k_copy1<<<1, 1, 0, c->stream>>>(q + pl, s->d_scal + 2); TFB_LAUNCHED(); }
+        if (owner) { k_copy1<FT><<<1, 1, 0, c->stream>>>(q + pl, s->d_scal + 2); TFB_LAUNCHED(); }
         if (tfb_allreduce_sum(c, s->d_scal + 2, 1)) return -1;   // non-owners contribute 0
-        k_pin_shift<<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, q, owner ? pl : -1, s->d_scal, s->d_scal + 2, pin_sign);
+        k_pin_shift<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(ncell, q, owner ? pl : -1, s->d_scal, s->d_scal + 2, pin_sign);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
     return 0;
 }
 
+template <class BT> static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d_out);
+template <class BT> static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2 = nullptr);
+template <class BT> __global__ void k_store_scaled(long long n, const double* __restrict__ scal, int idx, const double* __restrict__ x, BT* __restrict__ y);
+
+// y = x on the rows of the selected variables, 0 elsewhere
+__global__ void k_mask_copy(long long n, int dof, unsigned mask, const double* __restrict__ x, double* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = ((mask >> (int)(i % dof)) & 1u) ? x[i] : 0.0;
+}
+
+// z(velocity rows) += FDM_v^-1 r_v for every velocity component (the diffusion part of the block)
+template <class FT>
+static int velocity_fdm(tfb_ctx* c, const double* r, double* z) {
+    tfb_solver_state* s = c->solver;
+    const int dof = c->desc.dof, dim = c->desc.dim;
+    const long long ncell = c->n_local / dof;
+    FT *c0 = (FT*)s->comp[0], *c1 = (FT*)s->comp[1], *c2 = (FT*)s->comp[2];
+    const unsigned vb = vec_blocks(ncell);
+    for (int v = 0; v < dim; v++) {
+        k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, r, c0);
+        if (fdm_solve<FT>(c, v, c0, c1, c2)) return -1;
+        k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
+        TFB_LAUNCHED(); TFB_LAUNCHED();
+    }
+    return 0;
+}
+
+// Velocity sub-solve  z_u = F^-1 r_u  of the block preconditioner.  F = the velocity-velocity block
+// of J (diffusion + linearised convection [+ Coriolis]).  inner_its == 0: one FDM solve (exact for
+// the diffusion part only).  inner_its > 0: that many steps (at most) of right-preconditioned GMRES
+// on F with the FDM solve as its preconditioner -- the outer FGMRES is flexible, so the inner
+// iteration may stop on a loose tolerance.  z's velocity rows must be zero on entry.
+template <class FT>
+static int velocity_solve(tfb_ctx* c, tfb_mat* m, int prow, const double* ru, double* z) {
+    tfb_solver_state* s = c->solver;
+    const int dof = c->desc.dof, dim = c->desc.dim;
+    const long long n = c->n_local;
+    const unsigned velmask = (1u << dim) - 1u;
+    if (s->inner_its <= 0) return velocity_fdm<FT>(c, ru, z);
+    const int k = s->inner_its;
+    if (k > s->inner_cap) {
+        cudaFree(s->d_Vi); cudaFree(s->d_Zi);
+        s->d_Vi = s->d_Zi = nullptr;
+        TFB_CUDA(cudaMalloc(&s->d_Vi, sizeof(double) * (size_t)n * (k + 1)));
+        TFB_CUDA(cudaMalloc(&s->d_Zi, sizeof(double) * (size_t)n * k));
+        s->inner_cap = k;
+    }
+    double* V = s->d_Vi;
+    double* Z = s->d_Zi;
+    double* w = s->vec[0];              // free at this point of apply_precond
+    double* d_hh = s->d_scal + 8;       // needs k + 3 <= 8 doubles beyond: use a dedicated slice of d_scal
+    const unsigned nb = vec_blocks(n);
+    k_mask_copy<<<nb, 256, 0, c->stream>>>(n, dof, velmask, ru, w);
+    TFB_LAUNCHED();
+    double beta = 0.0;
+    if (multi_dot<double>(c, w, 1, w, d_hh)) return -1;
+    TFB_CUDA(cudaMemcpyAsync(&beta, d_hh, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    beta = sqrt(beta);
+    if (beta == 0.0) return 0;
+    TFB_CUDA(cudaMemcpyAsync(s->d_scal + 5, &beta, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_store_scaled<double><<<nb, 256, 0, c->stream>>>(n, s->d_scal, 5, w, V);
+    TFB_LAUNCHED();
+    std::vector<double> H((size_t)(k + 1) * k, 0.0), g(k + 1, 0.0), cs(k), sn(k), hcol(k + 2), y(k);
+    auto Hx = [&](int i, int j) -> double& { return H[(size_t)j * (k + 1) + i]; };
+    g[0] = beta;
+    int j = 0;
+    for (; j < k; j++) {
+        double* zj = Z + (size_t)j * n;
+        TFB_CUDA(cudaMemsetAsync(zj, 0, sizeof(double) * n, c->stream));
+        if (velocity_fdm<FT>(c, V + (size_t)j * n, zj)) return -1;
+        if (spmv(c, m, zj, w, prow, velmask, velmask)) return -1;
+        if (multi_dot<double>(c, V, j + 1, w, d_hh)) return -1;
+        if (multi_axpy<double>(c, V, j + 1, d_hh, -1.0, w, d_hh + k + 1)) return -1;
+        TFB_CUDA(cudaMemcpyAsync(hcol.data(), d_hh, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(cudaMemcpyAsync(hcol.data() + k + 1, d_hh + k + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(cudaStreamSynchronize(c->stream));
+        const double hn = sqrt(hcol[k + 1]);
+        for (int i = 0; i <= j; i++) Hx(i, j) = hcol[i];
+        Hx(j + 1, j) = hn;
+        for (int i = 0; i < j; i++) {
+            const double t = cs[i] * Hx(i, j) + sn[i] * Hx(i + 1, j);
+            Hx(i + 1, j) = -sn[i] * Hx(i, j) + cs[i] * Hx(i + 1, j);
+            Hx(i, j) = t;
+        }
+        const double d = hypot(Hx(j, j), Hx(j + 1, j));
+        cs[j] = Hx(j, j) / d; sn[j] = Hx(j + 1, j) / d;
+        Hx(j, j) = d; Hx(j + 1, j) = 0.0;
+        g[j + 1] = -sn[j] * g[j];
+        g[j] = cs[j] * g[j];
+        s->inner_total++;
+        if (fabs(g[j + 1]) <= s->inner_tol * beta || hn == 0.0 || j + 1 == k) { j++; break; }
+        TFB_CUDA(cudaMemcpyAsync(s->d_scal + 5, &hn, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        k_store_scaled<double><<<nb, 256, 0, c->stream>>>(n, s->d_scal, 5, w, V + (size_t)(j + 1) * n);
+        TFB_LAUNCHED();
+    }
+    const int kk = j;
+    for (int i = kk - 1; i >= 0; i--) {
+        double acc = g[i];
+        for (int l = i + 1; l < kk; l++) acc -= Hx(i, l) * y[l];
+        y[i] = acc / Hx(i, i);
+    }
+    TFB_CUDA(cudaMemcpyAsync(d_hh, y.data(), sizeof(double) * kk, cudaMemcpyHostToDevice, c->stream));
+    if (multi_axpy<double>(c, Z, kk, d_hh, 1.0, z, nullptr)) return -1;
+    TFB_CUDA(cudaStreamSynchronize(c->stream));   // y (host) must outlive the copy
+    return 0;
+}
+
 // z = P^-1 r  (interleaved vectors of length n_local)
-static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, double* z) {
+template <class FT>
+static int apply_precond_t(tfb_ctx* c, tfb_mat* m, int prow, const double* r, double* z) {
     tfb_solver_state* s = c->solver;
     const int dof = c->desc.dof, dim = c->desc.dim, pv = dim;
     const long long n = c->n_local, ncell = n / dof;
     const unsigned velmask = (1u << dim) - 1u, pmask = 1u << pv, smask = ((1u << dof) - 1u) & ~(velmask | pmask);
     const long long pin_cell = prow >= 0 ? prow / dof : -1;   // global cell of the pinned pressure
-    double *c0 = s->comp[0], *c1 = s->comp[1], *c2 = s->comp[2];
+    FT *c0 = (FT*)s->comp[0], *c1 = (FT*)s->comp[1], *c2 = (FT*)s->comp[2];
     double *ta = s->vec[0], *tb = s->vec[1], *tc = s->vec[2], *ru = s->vec[3];
     const unsigned vb = vec_blocks(ncell);
     TFB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * n, c->stream));
@@ -705,11 +855,11 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
     TFB_CUDA(cudaMemcpyAsync(ru, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     if (smask) {
         for (int v = pv + 1; v < dof; v++) {
-            k_deinterleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, r, c0);
+            k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, r, c0);
             if (s->var[v].pin_cell >= 0) {
-                if (poisson_solve(c, v, s->var[v].pin_cell, c0, c1, c2, s->var[v].pin_sign)) return -1;
-            } else if (fdm_solve(c, v, c0, c1, c2, nullptr)) return -1;
-            k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
+                if (poisson_solve<FT>(c, v, s->var[v].pin_cell, c0, c1, c2, s->var[v].pin_sign)) return -1;
+            } else if (fdm_solve<FT>(c, v, c0, c1, c2)) return -1;
+            k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
             TFB_LAUNCHED(); TFB_LAUNCHED();
         }
         if (sub_spmv(c, s->subB, z, ta)) return -1;                      // B s
@@ -717,33 +867,32 @@ static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, doub
         TFB_LAUNCHED();
     }
     // ---- pressure: dp = -Lp^-1 D M^-1 A M^-1 G Lp^-1 r_p ----
-    k_deinterleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, r, c0);
-    if (poisson_solve(c, pv, pin_cell, c0, c1, c2)) return -1;
+    k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, r, c0);
+    if (poisson_solve<FT>(c, pv, pin_cell, c0, c1, c2)) return -1;
     TFB_CUDA(cudaMemsetAsync(ta, 0, sizeof(double) * n, c->stream));
-    k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, 1.0);
+    k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, 1.0);
     TFB_LAUNCHED(); TFB_LAUNCHED();
     if (sub_spmv(c, s->subG, ta, tb, s->d_mass)) return -1;              // M^-1 G t
     if (spmv(c, m, tb, tc, prow, velmask, velmask, s->d_mass)) return -1; // M^-1 A (.)
     if (sub_spmv(c, s->subD, tc, ta)) return -1;                         // D (.)
-    k_deinterleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, ta, c0);
-    if (poisson_solve(c, pv, pin_cell, c0, c1, c2)) return -1;
-    k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, z, -1.0);  // dp into z
+    k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, ta, c0);
+    if (poisson_solve<FT>(c, pv, pin_cell, c0, c1, c2)) return -1;
+    k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, z, -1.0);  // dp into z
     TFB_LAUNCHED(); TFB_LAUNCHED();
     // ---- velocities: u = Ah^-1 (ru - G dp) ----
     TFB_CUDA(cudaMemsetAsync(ta, 0, sizeof(double) * n, c->stream));
-    k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, -1.0);
+    k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, -1.0);
     TFB_LAUNCHED();
     if (sub_spmv(c, s->subG, ta, tb)) return -1;                         // G dp
     k_axpy<<<vec_blocks(n), 256, 0, c->stream>>>(n, -1.0, tb, ru);
     TFB_LAUNCHED();
-    for (int v = 0; v < dim; v++) {
-        k_deinterleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, ru, c0);
-        if (fdm_solve(c, v, c0, c1, c2, nullptr)) return -1;
-        k_interleave<<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
-        TFB_LAUNCHED(); TFB_LAUNCHED();
-    }
+    if (velocity_solve<FT>(c, m, prow, ru, z)) return -1;
     TFB_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int apply_precond(tfb_ctx* c, tfb_mat* m, int prow, const double* r, double* z) {
+    return c->solver->precond_single ? apply_precond_t<float>(c, m, prow, r, z) : apply_precond_t<double>(c, m, prow, r, z);
 }
 
 // ------------------------------------------------------------------------------------
@@ -755,13 +904,19 @@ extern "C" int tfb_fdm_set(tfb_ctx* c, int var, int axis, int m, const double* Q
     tfb_solver_state* s = solver_of(c);
     FdmVar& f = s->var[var];
     if (f.m[axis] != m) {
-        cudaFree(f.Q[axis]); cudaFree(f.lam[axis]);
+        cudaFree(f.Q[axis]); cudaFree(f.lam[axis]); cudaFree(f.Qf[axis]);
         TFB_CUDA(cudaMalloc(&f.Q[axis], sizeof(double) * m * m));
         TFB_CUDA(cudaMalloc(&f.lam[axis], sizeof(double) * m));
+        TFB_CUDA(cudaMalloc(&f.Qf[axis], sizeof(float) * m * m));
         f.m[axis] = m;
     }
     TFB_CUDA(cudaMemcpy(f.Q[axis], Q, sizeof(double) * m * m, cudaMemcpyHostToDevice));
     TFB_CUDA(cudaMemcpy(f.lam[axis], lam, sizeof(double) * m, cudaMemcpyHostToDevice));
+    {
+        std::vector<float> qf((size_t)m * m);
+        for (size_t i = 0; i < qf.size(); i++) qf[i] = (float)Q[i];
+        TFB_CUDA(cudaMemcpy(f.Qf[axis], qf.data(), sizeof(float) * qf.size(), cudaMemcpyHostToDevice));
+    }
     f.coef = coef;
     f.present = true;
     double mx = 0.0;
@@ -789,7 +944,7 @@ static int ensure_buffers(tfb_ctx* c, int krylov, bool single = false) {
         TFB_CUDA(cudaMemcpy(s->d_mass, diag.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
         for (auto& p : s->comp) TFB_CUDA(cudaMalloc(&p, sizeof(double) * ncell));
         for (auto& p : s->vec) TFB_CUDA(cudaMalloc(&p, sizeof(double) * n));
-        TFB_CUDA(cudaMalloc(&s->d_scal, sizeof(double) * 16));
+        TFB_CUDA(cudaMalloc(&s->d_scal, sizeof(double) * 64));
     }
     if (krylov > s->cap || (krylov > 0 && single != s->basis_single)) {
         cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h);
@@ -825,7 +980,7 @@ static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d
 }
 // w += sign * V h   (one pass over the basis); d_nrm2 (optional, zeroed here) receives the LOCAL |w|^2
 template <class BT>
-static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2 = nullptr) {
+static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2) {
     const long long n = c->n_local;
     if (d_nrm2) TFB_CUDA(cudaMemsetAsync(d_nrm2, 0, sizeof(double), c->stream));
     for (int v0 = 0; v0 < nv; v0 += 2048) {
@@ -1180,6 +1335,10 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     TFB_CUDA(cudaSetDevice(c->desc.device));
     solver_of(c);
     if (dist_setup(c)) return -1;
+    solver_of(m->ctx)->precond_single = (o->reserved[2] & 1) == 1;
+    solver_of(m->ctx)->inner_its = std::min(24, (o->reserved[2] >> 8) & 0xff);   // d_scal slice holds 2k+3 <= 56 doubles
+    solver_of(m->ctx)->inner_total = 0;
+    if (const char* e = getenv("TFB_INNER_TOL")) solver_of(m->ctx)->inner_tol = atof(e);
     if (o->reserved[1] == 1) return bicgstab_run(m, b, x, o, info);
     if (o->reserved[0] == 1) return fgmres_run<float>(m, b, x, o, info);
     return fgmres_run<double>(m, b, x, o, info);

@@ -369,6 +369,8 @@ class Interface:
         # arithmetic fp64, cycles restart from the true residual); default fp64
         o.reserved[0] = int(its.get('Basis Precision', 'double') == 'single')
         o.reserved[1] = int(str(its.get('Method', 'FGMRES')).lower() == 'bicgstab')
+        o.reserved[2] = int(its.get('Preconditioner Precision', 'double') == 'single') \
+            | (min(24, max(0, int(its.get('Velocity Iterations', 0)))) << 8)
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
