@@ -208,3 +208,62 @@ def test_alternative_krylov_options_reach_the_same_solution(options):
     y = it.solve(jac, g['b'])
     assert it.last_solve['converged'], it.last_solve
     assert numpy.abs(y - g['y']).max() <= 1e-8 * numpy.abs(g['y']).max()
+
+
+@pytest.mark.parametrize('case', [
+    ({'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100.0, 'Lid Velocity': 1.0}, 8, 8, 1, 0.0),
+    ({'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 50.0, 'Lid Velocity': 1.0}, 6, 6, 6, 0.0),
+    ({'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100.0, 'Lid Velocity': 1.0}, 8, 8, 1, -30.0),
+    ({'Problem Type': 'Differentially Heated Cavity', 'Rayleigh Number': 1e4, 'Prandtl Number': 1000.0,
+      'Reynolds Number': 1.0}, 8, 8, 1, 0.0),
+    ({'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 1000.0, 'Prandtl Number': 10.0, 'Biot Number': 1.0,
+      'X-max': 10.0}, 16, 8, 1, 0.0),
+])
+def test_eigs_matches_dense_generalized_eigenvalues(case):
+    """Interface.eigs (BaseInterface.py:363-386): eigenvalues of J v = lambda M v closest to the target, through
+    the device solver, against scipy.linalg.eig on the oracle's pinned (J, M) pencil."""
+    import scipy.linalg
+    from oracle.tf_oracle import Oracle
+    from transiflow_b200 import Interface
+    params, nx, ny, nz, target = case
+    params = dict(params)
+    o = Oracle(dict(params), nx, ny, nz)
+    state = 0.05 * numpy.random.default_rng(3).standard_normal(o.n)
+    J = o.jacobian_csr(state).tolil()
+    J[o.dim, :] = 0
+    J[:, o.dim] = 0
+    J[o.dim, o.dim] = -1
+    mco, mj, mb = o.mass_matrix()
+    M = numpy.zeros(o.n)
+    M[mj] = mco
+    lam = scipy.linalg.eig(J.toarray(), numpy.diag(M), right=False)
+    lam = lam[numpy.isfinite(lam)]
+    num = 4
+    want = lam[numpy.argsort(numpy.abs(lam - target))[:num]]
+    params['Eigenvalue Solver'] = {'Target': target, 'Number of Eigenvalues': num, 'Tolerance': 1e-8}
+    it = Interface(params, nx, ny, nz)
+    got, vec = it.eigs(state, return_eigenvectors=True)
+    assert numpy.all(numpy.diff(got.real) <= 1e-12)                 # sorted by descending real part
+    dist = numpy.abs(want[:num - 1, None] - got[None, :]).min(axis=1)
+    assert dist.max() <= 1e-6 * max(1.0, numpy.abs(want).max())
+    Jc = J.tocsr()
+    for i in range(num - 1):
+        r = Jc @ vec[:, i] - got[i] * (M * vec[:, i])
+        assert numpy.linalg.norm(r) <= 1e-6 * numpy.linalg.norm(Jc @ vec[:, i]) + 1e-9
+
+
+def test_eigs_reference_configuration_ldc_6x6_re2000():
+    """The reference's own eigenvalue test configuration (tests/jada_fixtures.py:19-85, test_jada.py:108-122):
+    6x6 lid-driven cavity continued to Re = 2000, 10 eigenvalues closest to zero; golden = ARPACK/dense QZ on the
+    reference's matrices (tests/golden/make_golden_eigs.py); tolerances as in the reference (atol = 100 tol)."""
+    from transiflow_b200 import Interface
+    g = numpy.load(os.path.join(GEN, 'eigs_ldc2d_6_re2000.npz'))
+    num, tol = 10, 1e-7
+    params = {'Reynolds Number': float(g['reynolds']),
+              'Eigenvalue Solver': {'Number of Eigenvalues': num, 'Tolerance': tol}}
+    it = Interface(params, 6, 6)
+    got = it.eigs(g['x'])
+    got = numpy.array(sorted(got, key=lambda z: abs(z)))
+    want = g['eigs_dense']
+    numpy.testing.assert_allclose(got.real, want.real, rtol=0, atol=100 * tol)
+    numpy.testing.assert_allclose(abs(got.imag), abs(want.imag), rtol=0, atol=100 * tol)

@@ -392,7 +392,43 @@ class Interface:
         return y1, (y2.item() if numpy.ndim(y2) else y2)
 
     def eigs(self, state, return_eigenvectors=False, enable_recycling=False):
-        raise NotImplementedError('eigs needs jadapy (absent in this environment)')
+        '''Generalized eigenvalues of ``J(state) v = lambda M v`` closest to
+        ``parameters['Eigenvalue Solver']['Target']`` (default 0), sorted by descending real part
+        -- the contract of BaseInterface.eigs / _eigs (BaseInterface.py:294-386).  The reference
+        runs jadapy's JDQZ there; this backend runs a shift-and-invert Arnoldi process whose
+        operator ``(J - sigma M)^-1 M`` is one device Krylov solve per step (transiflow_b200/eigs.py).
+        Real targets only.'''
+        from .eigs import shift_invert_arnoldi
+        prm = self.parameters.get('Eigenvalue Solver', {})
+        target = prm.get('Target', 0.0)
+        if numpy.iscomplexobj(target) and complex(target).imag != 0.0:
+            raise NotImplementedError('complex eigenvalue targets are not supported by the B200 backend')
+        target = float(numpy.real(target))
+        num = int(prm.get('Number of Eigenvalues', 5))
+        tol = float(prm.get('Tolerance', 1e-7))
+        max_dim = int(prm.get('Maximum Subspace Dimension', 60))
+        recycle = prm.get('Recycle Subspaces', enable_recycling)
+        jac = self.jacobian(state)
+        mass = self.mass_matrix()
+        shifted = jac if target == 0.0 else jac - target * mass
+        failures = []
+
+        def apply_op(v):
+            y = self.solve(shifted, mass @ v)
+            if not self.last_solve['converged']:
+                failures.append(self.last_solve['relres'])
+            return y
+
+        v0 = self._eig_start if (recycle and getattr(self, '_eig_start', None) is not None) else None
+        lam, vec, ok = shift_invert_arnoldi(apply_op, self.n_local, num=num, target=target, tol=tol,
+                                            max_dim=max_dim, v0=v0)
+        if failures or not ok:
+            import warnings
+            warnings.warn('eigs: %d inner solves did not converge; Arnoldi converged: %s' % (len(failures), ok))
+        self._eig_start = numpy.real(vec.sum(axis=1)) if recycle else None
+        if return_eigenvectors:
+            return lam, vec
+        return lam
 
     # ---- save / load (BaseInterface.py:106-215) ----
     def save_state(self, name, x):
