@@ -63,6 +63,20 @@ def main():
                 ok = ok and good
                 # all ranks advance the same global state (gather through the oracle's full solution)
                 x = x + want
+            # the optional Krylov / preconditioner variants must reach the same update on z-slabs
+            # (fp32 FDM sub-solves transpose fp32 pencils through the all-to-all)
+            jac, f = it.jacobian_rhs(x[r0:r1].copy())
+            want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
+            for opts in ({'Preconditioner Precision': 'single'}, {'Method': 'BiCGStab'}, {'Velocity Iterations': 3},
+                         {'Basis Precision': 'single'}):
+                it.parameters['Iterative Solver'] = dict(opts)
+                dx = it.solve(jac, -f)
+                err = numpy.abs(dx - want[r0:r1]).max() / numpy.abs(want).max()
+                good = err <= 1e-8 and it.last_solve['converged']
+                print('rank %d/%d distributed solve %s: %d its, relres %.1e, err %.1e -> %s' % (
+                    rank, world, opts, it.last_solve['iterations'], it.last_solve['relres'], err, 'ok' if good else 'MISMATCH'), flush=True)
+                ok = ok and good
+            it.parameters.pop('Iterative Solver')
     dist.barrier()
     sys.exit(0 if ok else 1)
 
