@@ -211,16 +211,17 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
 // z-marching variant for true 3-D grids: a CTA owns a (TI x TJ) column of cells and sweeps KCH
 // planes.  The state planes live in a 4-slot shared-memory ring (k-1,k,k+1 in use, one slot
 // being refilled), so every plane is fetched from HBM/L2 once per column instead of three
-// times.  The loads of plane k+3 are issued BEFORE the rows of plane k are computed and wait
-// in registers (software prefetch) until they are deposited one step later; the CSR spans
-// leave through double-buffered TMA bulk stores.  One __syncthreads per plane.
+// times.  Plane k+3 is requested with cp.async (global -> shared, zero-fill for everything the
+// padded-state rules blank) BEFORE the rows of plane k are computed and has to land two steps
+// later, so no register holds data in flight; the CSR spans leave through double-buffered TMA
+// bulk stores.  One __syncthreads per plane.
 // =====================================================================================
 template <class Cfg, int TJ>
 struct TfbMarch {
     static constexpr int W = TFB_TI + 2, H = TJ + 2, HW = H * W;
     static constexpr int DSTR = HW + ((4 - HW % 16) + 16) % 16;   // = 4 (mod 16): conflict-free transpose stores
     static constexpr int SLOT = Cfg::DOF * DSTR;                  // doubles per ring slot (one plane)
-    static constexpr int NSLOT = 4;
+    static constexpr int NSLOT = 5;   // planes k-1, k, k+1 in use, k+2 landed, k+3 in flight
     static constexpr int LINE_CAP = TFB_TI * Cfg::CELL_SLOTS + 2;
     __host__ __device__ static constexpr int smem_doubles(bool do_j) { return NSLOT * SLOT + (do_j ? 2 * TJ * LINE_CAP : 0); }
 };
@@ -245,6 +246,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     double* sm_out = smem + M::NSLOT * SLOT;   // SLOT is even (DSTR multiple of 4)
     __shared__ int sm_span[2][TJ][2];
     __shared__ double sm_mx[TFB_NMET][TFB_TI], sm_my[TFB_NMET + 2][TJ], sm_mz[TFB_NMET][KCH];
+    __shared__ int sm_pstart[KCH + 1];   // first CSR offset of every plane of the chunk
 
     const TfbGrid& g = a.g;
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
@@ -273,17 +275,20 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
         if (d == 2) l_flags |= 1u << (8 + t);
         if (exists) l_flags |= 1u << (16 + t);
     }
-    auto fetch = [&](int kglob, double (&v)[NPT]) {
+    // asynchronous copy of one state plane into a ring slot; src-size 0 zero-fills (outside the domain,
+    // wall-normal velocities on the far walls)
+    auto request = [&](int kglob, int slot) {
         const double* pl = a.state + (long long)(kglob + kofs) * plane;   // ghost planes are zero at the domain ends
-#pragma unroll
-        for (int t = 0; t < NPT; t++) v[t] = ((l_flags >> t) & 1u) ? pl[l_src[t]] : 0.0;
-    };
-    auto deposit = [&](int kglob, int slot, const double (&v)[NPT]) {
         const bool zero_w = !g.zfold && kglob == g.nz - 1;                // utils.py:131
-        double* dst = ring + slot * SLOT;
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(ring + slot * SLOT);
 #pragma unroll
         for (int t = 0; t < NPT; t++)
-            if ((l_flags >> (16 + t)) & 1u) dst[l_dst[t]] = (zero_w && ((l_flags >> (8 + t)) & 1u)) ? 0.0 : v[t];
+            if ((l_flags >> (16 + t)) & 1u) {
+                const bool take = ((l_flags >> t) & 1u) && !(zero_w && ((l_flags >> (8 + t)) & 1u));
+                const unsigned nbytes = take ? 8u : 0u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+                             ::"r"(dst0 + 8u * (unsigned)l_dst[t]), "l"(pl + l_src[t]), "r"(nbytes) : "memory");
+            }
     };
 
     // ---- prologue: metrics of the column, first three planes, first CSR spans ----
@@ -301,14 +306,15 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
         const int mm = e / KCH, zz = e % KCH;
         sm_mz[mm][zz] = (kbeg + zz < a.nzl) ? g.met[2][mm * g.nz + a.k0 + kbeg + zz] : 0.0;
     }
-    double pre[NPT];   // plane in flight: fetched one step before it is deposited
+    if (DO_J)
+        for (int e = tid; e <= KCH; e += NT) sm_pstart[e] = a.row_ptr[(long long)min(kbeg + e, a.nzl) * plane];
     {
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
-            fetch(a.k0 + kbeg - 1 + p, pre);
-            deposit(a.k0 + kbeg - 1 + p, p, pre);
-        }
-        if (kbeg + 1 < kend) fetch(a.k0 + kbeg + 2, pre);
+        for (int p = 0; p < 3; p++) request(a.k0 + kbeg - 1 + p, p);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (kbeg + 1 < kend) request(a.k0 + kbeg + 2, 3);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
     }
     const int i = i0 + il, j = j0 + jl;
     const bool valid = i < g.nx && j < g.ny;
@@ -340,16 +346,28 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     for (int kl = kbeg; kl < kend; kl++, step++) {
         const int k = a.k0 + kl;
         const bool more = kl + 1 < kend;
-        const int s1 = (s0 + 1) & 3, s2 = (s0 + 2) & 3, s3 = (s0 + 3) & 3;
-        // ---- plane k+2 (in registers since the previous step) goes to the free slot; prefetch k+3 ----
+        const int s1 = s0 + 1 >= 5 ? s0 - 4 : s0 + 1, s2 = s0 + 2 >= 5 ? s0 - 3 : s0 + 2, s4 = s0 + 4 >= 5 ? s0 - 1 : s0 + 4;
+        // ---- request plane k+3 into the slot plane k-2 has left (everyone passed the last barrier) ----
         int rp_next = 0, span_next0 = 0, span_next1 = 0;
+        if (kl + 2 < kend) request(k + 3, s4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (more) {
-            deposit(k + 2, s3, pre);
-            if (kl + 2 < kend) fetch(k + 3, pre);
-            if (DO_J && valid) rp_next = a.row_ptr[row + plane];
-            if (leader) {
-                span_next0 = a.row_ptr[r0 + plane];
-                span_next1 = a.row_ptr[r0 + plane + rlen];
+            // The row lengths of a plane depend on k only through its wall flags, so two consecutive planes
+            // with equal flags have identical layouts: the CSR offsets of plane k+1 are those of plane k
+            // shifted by the plane's size.  row_ptr is only read where the flags change (the z walls).
+            const bool same_layout = (k == 0) == (k + 1 == 0) && (k == g.nz - 1) == (k + 1 == g.nz - 1) &&
+                                     (k == kfar2) == (k + 1 == kfar2);
+            if (same_layout) {
+                const int shift = sm_pstart[kl - kbeg + 1] - sm_pstart[kl - kbeg];
+                rp_next = rp + shift;
+                span_next0 = sm_span[step & 1][jl][0] + shift;
+                span_next1 = sm_span[step & 1][jl][1] + shift;
+            } else {
+                if (DO_J && valid) rp_next = a.row_ptr[row + plane];
+                if (leader) {
+                    span_next0 = a.row_ptr[r0 + plane];
+                    span_next1 = a.row_ptr[r0 + plane + rlen];
+                }
             }
         }
         // ---- rows of plane k ----
@@ -401,6 +419,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
         // the previous plane must have drained its staging buffer before anyone refills it.
         if (DO_J) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // plane k+2 (requested one step ago) has landed
         __syncthreads();
         if (leader) {
             // one TMA bulk store per line (smem -> global), double-buffered staging

@@ -330,6 +330,8 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
                 if (variant == 32) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);
                 if (variant == 33) return launch_march_v<Cfg, DO_J, DO_F, 4, TFB_KCH, 1>(c, m);
                 if (variant == 34) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3>(c, m);
+                if (variant == 35) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 4>(c, m);
+                if (variant == 36) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2>(c, m);
             }
             return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);   // dof 5: 160 registers, no spills
         }
