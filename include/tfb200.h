@@ -119,7 +119,9 @@ typedef struct {
     int32_t precond;        /* TFB_PREC_* */
     int32_t verbose;
     int32_t reserved[3];    /* reserved[0] = 1: fp32 storage of the GMRES basis (arithmetic fp64); reserved[1] = 1: BiCGStab;
-                       reserved[2] = 1: FDM sub-solves of the preconditioner in fp32 */
+                       reserved[2] bit 0: FDM sub-solves of the preconditioner in fp32; bit 1: do not use the coupled
+                       (w, scalar) solve even if tfb_joint_set was called; bits 8..15: inner GMRES steps of the
+                       velocity / (velocity, scalar) sub-solve */
 } tfb_solve_opts;
 typedef struct {
     int32_t iters, converged;
@@ -137,6 +139,17 @@ int tfb_fdm_set(tfb_ctx* ctx, int var, int axis, int m, const double* Q, const d
 /* A scalar whose diffusion operator is singular (zero-flux on every wall) is pinned at `cell`
  * with diagonal `sign`, like the reference's "fix one salinity value" (Discretization.py:690-701). */
 int tfb_fdm_pin(tfb_ctx* ctx, int var, int64_t cell, double sign);
+/* Coupled (vertical velocity, scalar) solve of the preconditioner for buoyancy-driven 3-D problems whose
+ * scalar is stratified along z (Rayleigh-Benard): replaces "scalar first, velocities after" by one solve of
+ * the (velocity, scalar) block in which w and the scalar are solved together, line by line along z, after
+ * the x/y fast-diagonalisation transforms.  zops = 8 x nz table (row-major): lower / diagonal / upper / mass
+ * of the w stencil along z (nz-1 faces, zero padded), then the same for the scalar
+ * (hostprep.joint_z_operators); the vertical couplings are read off each Jacobian.  There is no
+ * counterpart in the reference (SciPy.py:131-162 factorises the whole matrix with SuperLU). */
+int tfb_joint_set(tfb_ctx* ctx, int wvar, int svar, int nz, const double* zops);
+/* diagnostics: the coupled solve alone with host vectors (other variables' rows come back zero);
+ * table_out (optional, 12 x nz): the coefficient table after reading the couplings from `mat` */
+int tfb_joint_apply(tfb_mat* mat, const double* r, double* z, double* table_out);
 /* z = P^-1 r with host vectors (diagnostics / tests of the preconditioner alone) */
 int tfb_precond_apply(tfb_mat* mat, const double* r, double* z, int pressure_row);
 

@@ -28,6 +28,7 @@ int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
 int tfb_alltoallv_bytes(tfb_ctx* c, const void* send, const long long* scount, const long long* sdispl, void* recv,
                         const long long* rcount, const long long* rdispl, int elem_bytes);
 
+#include "tfb_joint.h"
 #define TFB_MAXVAR 6
 
 struct FdmVar {
@@ -59,7 +60,16 @@ struct SubCsr {
 
 struct tfb_solver_state {
     FdmVar var[TFB_MAXVAR];
-    SubCsr subG, subD, subB;
+    SubCsr subG, subD, subB, subC;
+    // coupled (vertical velocity, scalar) solve of the Rayleigh-Benard preconditioner (tfb_joint.h)
+    bool joint_ready = false;     // tfb_joint_set was called
+    bool joint_on = false;        // this solve uses it
+    int joint_w = -1, joint_s = -1;
+    double* d_jz = nullptr;       // TFB_JZ_ROWS x nz coefficient table
+    double* jbuf[2] = {nullptr, nullptr};   // 2 x ncell each: [w planes | T planes]
+    double* jab = nullptr;        // 4 x ncell: the two upper bands of the line factorisations
+    const tfb_mat* jz_owner = nullptr;
+    uint64_t jz_version = ~0ull;
     int sub_prow = -2;
     double* d_mass = nullptr;     // velocity mass diagonal (LSC scaling), n_local
     double* comp[3] = {};         // SoA work arrays, ncell each
@@ -93,7 +103,8 @@ void tfb_solver_free(tfb_solver_state* s) {
     if (!s) return;
     for (auto& v : s->var)
         for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); cudaFree(v.Qf[a]); cudaFree(v.lamf[a]); }
-    for (SubCsr* q : {&s->subG, &s->subD, &s->subB}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
+    for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
+    cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab);
     cudaFree(s->d_mass);
     for (auto p : s->comp) cudaFree(p);
     for (auto p : s->vec) cudaFree(p);
@@ -242,6 +253,9 @@ __global__ void k_scale_to(long long n, const double* __restrict__ scal, int idx
     const double a = 1.0 / scal[idx];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = a * x[i];
 }
+__global__ void k_rowdiv(long long n, const double* __restrict__ d, double* __restrict__ y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] /= d[i];
+}
 __global__ void k_sub(long long n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = a[i] - b[i];
 }
@@ -357,6 +371,7 @@ static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned
     S.owner = nullptr;
     return 0;
 }
+static int joint_refresh(tfb_ctx* c, tfb_mat* m);
 static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
     tfb_solver_state* s = c->solver;
     const int dof = c->desc.dof, dim = c->desc.dim;
@@ -365,15 +380,18 @@ static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
         if (sub_build(c, s->subG, prow, velmask, pmask)) return -1;
         if (sub_build(c, s->subD, prow, pmask, velmask)) return -1;
         if (smask && sub_build(c, s->subB, prow, velmask, smask)) return -1;
+        if (smask && s->joint_ready && sub_build(c, s->subC, prow, smask, velmask)) return -1;
         s->sub_prow = prow;
     }
-    for (SubCsr* q : {&s->subG, &s->subD, &s->subB}) {
+    if (smask && s->joint_ready && !s->subC.row_ptr && sub_build(c, s->subC, prow, smask, velmask)) return -1;
+    for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) {
         if (!q->row_ptr || q->nnz == 0) continue;
         if (q->owner == m && q->version == m->version) continue;
         k_sub_gather<<<vec_blocks(q->nnz), 256, 0, c->stream>>>(q->nnz, q->src, m->d_vals, q->vals);
         TFB_LAUNCHED();
         q->owner = m; q->version = m->version;
     }
+    if (s->joint_ready && joint_refresh(c, m)) return -1;
     TFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -736,6 +754,115 @@ template <class BT> static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const
 template <class BT> __global__ void k_store_scaled(long long n, const double* __restrict__ scal, int idx, const double* __restrict__ x, BT* __restrict__ y);
 
 // y = x on the rows of the selected variables, 0 elsewhere
+// ------------------------------------------------------------------------------------
+// Coupled (vertical velocity, scalar) solve -- Rayleigh-Benard (tfb_joint.h)
+// ------------------------------------------------------------------------------------
+// Horizontal means of the vertical couplings, read off the Jacobian: for every (w, T) entry of a
+// w-row and every (T, w) entry of a T-row in the SAME column of cells, value / (hx hy) / (nx ny)
+// is added to the table row of its z-offset.  One thread per matrix row.
+__global__ void k_joint_couplings(long long nrows, long long row0, int dof, int wv, int sv, int nx, int ny, int nz,
+                                  const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ vals,
+                                  const double* __restrict__ hx, const double* __restrict__ hy, double* __restrict__ jz) {
+    const long long rl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rl >= nrows) return;
+    const long long row = row0 + rl;
+    const int rv = (int)(row % dof);
+    if (rv != wv && rv != sv) return;
+    const long long cell = row / dof, plane = (long long)nx * ny;
+    const int i = (int)(cell % nx), j = (int)((cell / nx) % ny), k = (int)(cell / plane);
+    if (rv == wv && k >= nz - 1) return;                 // wall row
+    const double scale = 1.0 / (hx[i] * hy[j] * (double)plane);
+    const int other = rv == wv ? sv : wv;
+    double acc0 = 0.0, acc1 = 0.0;                       // same plane / neighbouring plane
+    for (int e = row_ptr[rl]; e < row_ptr[rl + 1]; e++) {
+        const long long cc = col[e];
+        if ((int)(cc % dof) != other) continue;
+        const long long ccell = cc / dof;
+        if (ccell % plane != cell % plane) continue;
+        const int dk = (int)(ccell / plane) - k;
+        if (rv == sv && (int)(ccell / plane) >= nz - 1) continue;   // wall face: not an unknown
+        if (dk == 0) acc0 += vals[e];
+        else if (dk == (rv == wv ? 1 : -1)) acc1 += vals[e];
+    }
+    if (rv == wv) { atomicAdd(jz + TFB_JZ_B0 * nz + k, acc0 * scale); atomicAdd(jz + TFB_JZ_BP * nz + k, acc1 * scale); }
+    else          { atomicAdd(jz + TFB_JZ_C0 * nz + k, acc0 * scale); atomicAdd(jz + TFB_JZ_CM * nz + k, acc1 * scale); }
+}
+
+// one thread per horizontal mode (a, b): banded solve along z
+__global__ void __launch_bounds__(128)
+k_joint_lines(int ex, int ey, int jofs, int nz, const double* __restrict__ zc, const double* __restrict__ lx,
+              const double* __restrict__ ly, double cv, double cT, double* __restrict__ w, double* __restrict__ T,
+              double* __restrict__ al, double* __restrict__ be) {
+    extern __shared__ double s_zc[];
+    for (int q = threadIdx.x; q < TFB_JZ_ROWS * nz; q += blockDim.x) s_zc[q] = zc[q];
+    __syncthreads();
+    const long long modes = (long long)ex * ey;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= modes) return;
+    const double mu = lx[m % ex] + ly[jofs + m / ex];
+    tfb_joint_line(nz, s_zc, mu, cv, cT, modes, w + m, T + m, al + m, be + m);
+}
+
+__global__ void k_negate_var(long long ncell, int dof, int v, const double* __restrict__ r, double* __restrict__ z) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x)
+        z[i * dof + v] = -r[i * dof + v];
+}
+
+static int joint_refresh(tfb_ctx* c, tfb_mat* m) {
+    tfb_solver_state* s = c->solver;
+    if (s->jz_owner == m && s->jz_version == m->version) return 0;
+    const int nz = c->desc.nz;
+    TFB_CUDA(cudaMemsetAsync(s->d_jz + TFB_JZ_B0 * nz, 0, sizeof(double) * 4 * nz, c->stream));
+    k_joint_couplings<<<(unsigned)((c->n_local + 255) / 256), 256, 0, c->stream>>>(
+        c->n_local, c->row0, c->desc.dof, s->joint_w, s->joint_s, c->desc.nx, c->desc.ny, nz, c->d_row_ptr, c->d_col,
+        m->d_vals, c->d_met[0], c->d_met[1], s->d_jz);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    if (tfb_allreduce_sum(c, s->d_jz + TFB_JZ_B0 * nz, 4 * nz)) return -1;
+    s->jz_owner = m; s->jz_version = m->version;
+    return 0;
+}
+
+// (z_w, z_T) = Fwt^-1 (r_w, r_T) on interleaved vectors: the x/y transforms of the scalar's
+// fast-diagonalisation basis, one banded solve per horizontal mode, transforms back.
+static int joint_solve(tfb_ctx* c, const double* r, double* z) {
+    tfb_solver_state* s = c->solver;
+    TFB_CHECK(c->nranks == 1, "the coupled (w, T) solve is not implemented for z-slab runs");
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, dof = c->desc.dof;
+    const int wv = s->joint_w, sv = s->joint_s;
+    const FdmVar& f = s->var[sv];
+    TFB_CHECK(f.present && f.m[0] == nx && f.m[1] == ny, "scalar FDM basis missing");
+    const long long plane = (long long)nx * ny, ncell = plane * nz;
+    if (!s->jbuf[0]) {
+        TFB_CUDA(cudaMalloc(&s->jbuf[0], sizeof(double) * 2 * ncell));
+        TFB_CUDA(cudaMalloc(&s->jbuf[1], sizeof(double) * 2 * ncell));
+        TFB_CUDA(cudaMalloc(&s->jab, sizeof(double) * 4 * ncell));
+    }
+    double *a = s->jbuf[0], *b = s->jbuf[1];
+    const unsigned vb = vec_blocks(ncell);
+    k_deinterleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, wv, r, a);
+    k_deinterleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, sv, r, a + ncell);
+    TFB_LAUNCHED(); TFB_LAUNCHED();
+    if (axis_gemm<double>(c, false, a, b, f.Q[0], nx, ny * nz * 2, nx, nx, nx, 1, 0, 1)) return -1;
+    if (axis_gemm<double>(c, false, b, a, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nz * 2)) return -1;
+    const unsigned nb = (unsigned)((plane + 127) / 128);
+    k_joint_lines<<<nb, 128, sizeof(double) * TFB_JZ_ROWS * nz, c->stream>>>(
+        nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], s->var[wv].coef, f.coef, a, a + ncell, s->jab, s->jab + 2 * ncell);
+    TFB_LAUNCHED();
+    if (axis_gemm<double>(c, true, a, b, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nz * 2)) return -1;
+    if (axis_gemm<double>(c, true, b, a, f.Q[0], nx, ny * nz * 2, nx, nx, nx, 1, 0, 1)) return -1;
+    k_interleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, wv, a, z, 1.0);
+    k_interleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, sv, a + ncell, z, 1.0);
+    TFB_LAUNCHED(); TFB_LAUNCHED();
+    // the top-wall rows of w carry a -1 diagonal
+    const long long top = (ncell - plane) * dof;
+    k_negate_var<<<vec_blocks(plane), 256, 0, c->stream>>>(plane, dof, wv, r + top, z + top);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
 __global__ void k_mask_copy(long long n, int dof, unsigned mask, const double* __restrict__ x, double* __restrict__ y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = ((mask >> (int)(i % dof)) & 1u) ? x[i] : 0.0;
@@ -743,19 +870,31 @@ __global__ void k_mask_copy(long long n, int dof, unsigned mask, const double* _
 
 // z(velocity rows) += FDM_v^-1 r_v for every velocity component (the diffusion part of the block)
 template <class FT>
-static int velocity_fdm(tfb_ctx* c, const double* r, double* z) {
+static int velocity_fdm(tfb_ctx* c, const double* r, double* z, int skip = -1) {
     tfb_solver_state* s = c->solver;
     const int dof = c->desc.dof, dim = c->desc.dim;
     const long long ncell = c->n_local / dof;
     FT *c0 = (FT*)s->comp[0], *c1 = (FT*)s->comp[1], *c2 = (FT*)s->comp[2];
     const unsigned vb = vec_blocks(ncell);
     for (int v = 0; v < dim; v++) {
+        if (v == skip) continue;
         k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, r, c0);
         if (fdm_solve<FT>(c, v, c0, c1, c2)) return -1;
         k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, c2, z, 1.0);
         TFB_LAUNCHED(); TFB_LAUNCHED();
     }
     return 0;
+}
+
+// Approximate inverse of the block the velocity sub-solve works on.  Default: the velocity block,
+// one FDM (diffusion) solve per component.  Coupled mode (Rayleigh-Benard): the (velocity, scalar)
+// block -- horizontal components by FDM, (w, T) by the coupled line solve.
+template <class FT>
+static int block_fdm(tfb_ctx* c, const double* r, double* z) {
+    tfb_solver_state* s = c->solver;
+    if (!s->joint_on) return velocity_fdm<FT>(c, r, z);
+    if (velocity_fdm<FT>(c, r, z, s->joint_w)) return -1;
+    return joint_solve(c, r, z);
 }
 
 // Velocity sub-solve  z_u = F^-1 r_u  of the block preconditioner.  F = the velocity-velocity block
@@ -768,8 +907,8 @@ static int velocity_solve(tfb_ctx* c, tfb_mat* m, int prow, const double* ru, do
     tfb_solver_state* s = c->solver;
     const int dof = c->desc.dof, dim = c->desc.dim;
     const long long n = c->n_local;
-    const unsigned velmask = (1u << dim) - 1u;
-    if (s->inner_its <= 0) return velocity_fdm<FT>(c, ru, z);
+    const unsigned velmask = ((1u << dim) - 1u) | (s->joint_on ? 1u << s->joint_s : 0u);   // the block's variables
+    if (s->inner_its <= 0) return block_fdm<FT>(c, ru, z);
     const int k = s->inner_its;
     if (k > s->inner_cap) {
         cudaFree(s->d_Vi); cudaFree(s->d_Zi);
@@ -801,7 +940,7 @@ static int velocity_solve(tfb_ctx* c, tfb_mat* m, int prow, const double* ru, do
     for (; j < k; j++) {
         double* zj = Z + (size_t)j * n;
         TFB_CUDA(cudaMemsetAsync(zj, 0, sizeof(double) * n, c->stream));
-        if (velocity_fdm<FT>(c, V + (size_t)j * n, zj)) return -1;
+        if (block_fdm<FT>(c, V + (size_t)j * n, zj)) return -1;
         if (spmv(c, m, zj, w, prow, velmask, velmask)) return -1;
         if (multi_dot<double>(c, V, j + 1, w, d_hh)) return -1;
         if (multi_axpy<double>(c, V, j + 1, d_hh, -1.0, w, d_hh + k + 1)) return -1;
@@ -853,7 +992,8 @@ static int apply_precond_t(tfb_ctx* c, tfb_mat* m, int prow, const double* r, do
     TFB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * n, c->stream));
     // ---- scalars: s = At^-1 r_s ; ru = r - B s (velocity rows) ----
     TFB_CUDA(cudaMemcpyAsync(ru, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    if (smask) {
+    const bool joint = s->joint_on;
+    if (smask && !joint) {
         for (int v = pv + 1; v < dof; v++) {
             k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, v, r, c0);
             if (s->var[v].pin_cell >= 0) {
@@ -873,7 +1013,23 @@ static int apply_precond_t(tfb_ctx* c, tfb_mat* m, int prow, const double* r, do
     k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, c2, ta, 1.0);
     TFB_LAUNCHED(); TFB_LAUNCHED();
     if (sub_spmv(c, s->subG, ta, tb, s->d_mass)) return -1;              // M^-1 G t
-    if (spmv(c, m, tb, tc, prow, velmask, velmask, s->d_mass)) return -1; // M^-1 A (.)
+    if (!joint) {
+        if (spmv(c, m, tb, tc, prow, velmask, velmask, s->d_mass)) return -1; // M^-1 A (.)
+    } else {
+        // scalar eliminated: the commutator sees  A - B At^-1 C  (At^-1: the scalar's diffusion solve)
+        const int sv = s->joint_s;
+        if (spmv(c, m, tb, tc, prow, velmask, velmask)) return -1;
+        if (sub_spmv(c, s->subC, tb, ta)) return -1;
+        k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, sv, ta, c0);
+        if (fdm_solve<FT>(c, sv, c0, c1, c2)) return -1;
+        TFB_CUDA(cudaMemsetAsync(ta, 0, sizeof(double) * n, c->stream));
+        k_interleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, sv, c2, ta, 1.0);
+        TFB_LAUNCHED(); TFB_LAUNCHED();
+        if (sub_spmv(c, s->subB, ta, tb)) return -1;
+        k_axpy<<<vec_blocks(n), 256, 0, c->stream>>>(n, -1.0, tb, tc);
+        k_rowdiv<<<vec_blocks(n), 256, 0, c->stream>>>(n, s->d_mass, tc);
+        TFB_LAUNCHED(); TFB_LAUNCHED();
+    }
     if (sub_spmv(c, s->subD, tc, ta)) return -1;                         // D (.)
     k_deinterleave<FT><<<vb, 256, 0, c->stream>>>(ncell, dof, pv, ta, c0);
     if (poisson_solve<FT>(c, pv, pin_cell, c0, c1, c2)) return -1;
@@ -930,6 +1086,22 @@ extern "C" int tfb_fdm_pin(tfb_ctx* c, int var, int64_t cell, double sign) {
     tfb_solver_state* s = solver_of(c);
     s->var[var].pin_cell = cell;
     s->var[var].pin_sign = sign;
+    return 0;
+}
+
+extern "C" int tfb_joint_set(tfb_ctx* c, int wvar, int svar, int nz, const double* zops) {
+    TFB_CHECK(c && zops && nz == c->desc.nz && nz > 2, "bad arguments");
+    TFB_CHECK(c->desc.dim == 3 && wvar == 2 && svar > c->desc.dim && svar < c->desc.dof, "coupled solve: w and a scalar of a 3-D problem");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    tfb_solver_state* s = solver_of(c);
+    if (!s->d_jz) {
+        TFB_CUDA(cudaMalloc(&s->d_jz, sizeof(double) * TFB_JZ_ROWS * nz));
+        TFB_CUDA(cudaMemset(s->d_jz, 0, sizeof(double) * TFB_JZ_ROWS * nz));
+    }
+    TFB_CUDA(cudaMemcpy(s->d_jz, zops, sizeof(double) * 8 * nz, cudaMemcpyHostToDevice));
+    s->joint_w = wvar; s->joint_s = svar;
+    s->joint_ready = true;
+    s->jz_owner = nullptr;
     return 0;
 }
 
@@ -1017,9 +1189,30 @@ extern "C" int tfb_precond_apply(tfb_mat* m, const double* r, double* z, int pre
     if (dist_setup(c)) return -1;
     tfb_solver_state* s = c->solver;
     TFB_CUDA(cudaMemcpyAsync(s->vec[4], r, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    s->joint_on = s->joint_ready && c->nranks == 1;
     if (sub_refresh(c, m, pressure_row)) return -1;
     if (apply_precond(c, m, pressure_row, s->vec[4], s->vec[5])) return -1;
     TFB_CUDA(cudaMemcpyAsync(z, s->vec[5], sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// diagnostics: the coupled (w, T) solve alone, host vectors; rows of other variables come back zero.
+// table_out (optional): the TFB_JZ_ROWS x nz coefficient table after the refresh from `m`.
+extern "C" int tfb_joint_apply(tfb_mat* m, const double* r, double* z, double* table_out) {
+    TFB_CHECK(m && r && z, "null argument");
+    tfb_ctx* c = m->ctx;
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    if (ensure_buffers(c, 0)) return -1;
+    tfb_solver_state* s = c->solver;
+    TFB_CHECK(s->joint_ready, "tfb_joint_set was not called");
+    TFB_CUDA(cudaMemcpyAsync(s->vec[4], r, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    TFB_CUDA(cudaMemsetAsync(s->vec[5], 0, sizeof(double) * c->n_local, c->stream));
+    if (joint_refresh(c, m)) return -1;
+    if (joint_solve(c, s->vec[4], s->vec[5])) return -1;
+    TFB_CUDA(cudaMemcpyAsync(z, s->vec[5], sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
+    if (table_out)
+        TFB_CUDA(cudaMemcpyAsync(table_out, s->d_jz, sizeof(double) * TFB_JZ_ROWS * c->desc.nz, cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1338,6 +1531,8 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     solver_of(m->ctx)->precond_single = (o->reserved[2] & 1) == 1;
     solver_of(m->ctx)->inner_its = std::min(24, (o->reserved[2] >> 8) & 0xff);   // d_scal slice holds 2k+3 <= 56 doubles
     solver_of(m->ctx)->inner_total = 0;
+    // reserved[2] bit 1: 'Scalar Coupling': 'none' (block-triangular treatment of the scalars)
+    solver_of(m->ctx)->joint_on = solver_of(m->ctx)->joint_ready && !(o->reserved[2] & 2) && m->ctx->nranks == 1;
     if (const char* e = getenv("TFB_INNER_TOL")) solver_of(m->ctx)->inner_tol = atof(e);
     if (o->reserved[1] == 1) return bicgstab_run(m, b, x, o, info);
     if (o->reserved[0] == 1) return fgmres_run<float>(m, b, x, o, info);

@@ -231,7 +231,8 @@ def fold_coefficients(cfg, prm):
     return out
 
 
-def _pencil(kind, met, n, s_near, s_far):
+def _pencil_km(kind, met, n, s_near, s_far):
+    '''Dense symmetric tridiagonal stiffness K and diagonal mass M of one variable along one axis.'''
     hc, hu, rhc, rhp, rhm, rhu = met[0], met[1], met[2], met[3], met[4], met[5]
     if kind == 'own':       # velocity along its own axis (_u_xx): faces 0..n-2, the wall face is not an unknown
         m = n - 1
@@ -247,9 +248,37 @@ def _pencil(kind, met, n, s_near, s_far):
     if m > 1:
         K += numpy.diag(upper[:m - 1], 1) + numpy.diag(lower[1:], -1)
     K = (K + K.T) / 2       # symmetric by construction (1/hp[i] == 1/hc[i+1], 1/hu[i] == 1/hm[i+1])
+    return K, numpy.array(M, dtype=numpy.float64)
+
+
+def _pencil(kind, met, n, s_near, s_far):
+    K, M = _pencil_km(kind, met, n, s_near, s_far)
     ms = 1 / numpy.sqrt(M)
     lam, Y = numpy.linalg.eigh(ms[:, None] * K * ms[None, :])
     return numpy.ascontiguousarray(ms[:, None] * Y), numpy.ascontiguousarray(lam)
+
+
+def joint_z_operators(cfg, prm, mets, nz):
+    '''(8, nz) table for tfb_joint_set: the tridiagonal z-stencils (lower, diagonal, upper) and masses of
+    the vertical velocity (nz-1 faces, zero padded) and of the temperature, rows ordered as the
+    TFB_JZ_* enum of csrc/tfb_joint.h.  The coupled (w, T) line solve of the Rayleigh-Benard
+    preconditioner is built from these and from the vertical couplings read off the Jacobian.'''
+    folds = fold_coefficients(cfg, prm)
+    w = cfg.dim - 1
+    Kw, Mw = _pencil_km('own', mets[2], nz, 0.0, 0.0)
+    KT, MT = _pencil_km('cen', mets[2], nz, folds.get((cfg.T, 2, 0), 0.0), folds.get((cfg.T, 2, 1), 0.0))
+    out = numpy.zeros((8, nz))
+    m = nz - 1
+    out[0, 1:m] = numpy.diag(Kw, -1)
+    out[1, :m] = numpy.diag(Kw)
+    out[2, :m - 1] = numpy.diag(Kw, 1)
+    out[3, :m] = Mw
+    out[4, 1:] = numpy.diag(KT, -1)
+    out[5] = numpy.diag(KT)
+    out[6, :nz - 1] = numpy.diag(KT, 1)
+    out[7] = MT
+    assert w == 2
+    return numpy.ascontiguousarray(out)
 
 
 def fdm_operators(cfg, prm, mets, nx, ny, nz):

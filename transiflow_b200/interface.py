@@ -260,6 +260,13 @@ class Interface:
             check(_lib.lib().tfb_fdm_set(self._ctx, v, a, m, ptr(Q), ptr(lam), ctypes.c_double(coef)))
         if self.problem == recipes.AMOC:
             check(_lib.lib().tfb_fdm_pin(self._ctx, self.config.S, ctypes.c_int64(0), ctypes.c_double(-1.0)))
+        # Rayleigh-Benard on a true 3-D grid: w and T are solved together along z (csrc/tfb_joint.h);
+        # single GPU only -- z-slab runs keep the block-triangular treatment of the scalar
+        self._joint = (self.problem in (recipes.RB, recipes.RBP) and self.dim == 3 and self.nz > 2
+                       and self.dof == 5 and self.slab == (0, self.nz))
+        if self._joint:
+            zops = hostprep.joint_z_operators(self.config, self._prm, self._mets, self.nz)
+            check(_lib.lib().tfb_joint_set(self._ctx, self.dim - 1, self.config.T, self.nz, ptr(zops)))
         self._fdm_key = self._param_key
 
     # ---- vectors (SciPy.py:37-38; BaseInterface.py:84-92) ----
@@ -369,8 +376,12 @@ class Interface:
         # arithmetic fp64, cycles restart from the true residual); default fp64
         o.reserved[0] = int(its.get('Basis Precision', 'double') == 'single')
         o.reserved[1] = int(str(its.get('Method', 'FGMRES')).lower() == 'bicgstab')
+        # 'Scalar Coupling': 'joint' (default where available: 3-D Rayleigh-Benard) solves w and T together and
+        # iterates on the (velocity, temperature) block; 'none' is the block-triangular preconditioner
+        joint = getattr(self, '_joint', False) and str(its.get('Scalar Coupling', 'joint')).lower() != 'none'
+        inner = int(its.get('Velocity Iterations', 8 if joint else 0))
         o.reserved[2] = int(its.get('Preconditioner Precision', 'double') == 'single') \
-            | (min(24, max(0, int(its.get('Velocity Iterations', 0)))) << 8)
+            | (0 if joint else 2) | (min(24, max(0, inner)) << 8)
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
