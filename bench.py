@@ -177,7 +177,8 @@ def main():
     if args.problem == 'rb':
         PARAMS.clear()
         PARAMS.update(RB_PARAMS)
-        args.newton_steps = 0
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            args.newton_steps = 0      # the coupled (w, T) solve of the RB preconditioner is single-GPU
     two_d = PROBLEMS_2D.get(args.problem)
     if two_d:
         PARAMS.clear()
@@ -315,6 +316,15 @@ def main():
             ms5 = ctypes.c_float()
             check(L.tfb_event_elapsed_ms(it._ctx, 4, 5, ctypes.byref(ms5)))
             x = x + dx
+            if args.problem == 'rb' and k == 0:
+                # Newton from zero lands on the conduction state in one (linear) step; the timed steps start from
+                # that state plus a smooth roll-like perturbation so that they are genuine Newton steps
+                c3 = numpy.indices((it.nz, it.ny, it.nx)).astype(float)
+                roll = numpy.sin(numpy.pi * (c3[0] + 1) / it.nz) * numpy.cos(6 * numpy.pi * (c3[2] + 0.5) / it.nx)
+                xs = x.reshape(it.nz, it.ny, it.nx, it.dof)
+                xs[..., 2] += 1e-2 * roll
+                xs[-1, :, :, 2] = 0.0
+                xs[..., 4] += 1e-2 * roll
             hist.append({'ms': max_over_ranks(ms5.value), 'wall_ms': 1e3 * (time.perf_counter() - t0),
                          'fnorm': float(numpy.sqrt(max_over_ranks(float(f @ f)) if world > 1 else f @ f)),
                          'iterations': it.last_solve['iterations'], 'relres': it.last_solve['relres'],
@@ -325,7 +335,8 @@ def main():
                   'krylov_iterations': [h['iterations'] for h in timed], 'relres': [h['relres'] for h in timed],
                   'fnorm_before': [h['fnorm'] for h in timed], 'all_converged': all(h['converged'] for h in hist),
                   'tolerance': 1e-10, 'unknowns': it.n,
-                  'solver': 'FGMRES + LSC block preconditioner (FDM sub-solves), host vectors in/out'
+                  'solver': ('FGMRES + LSC block preconditioner, coupled (w,T) line solve + inner GMRES on the (u,T) block'
+                             if args.problem == 'rb' else 'FGMRES + LSC block preconditioner (FDM sub-solves)') + ', host vectors in/out'
                             + ('; z-slabs: NCCL halo exchange, all-reduce, all-to-all transposes' if world > 1 else '')}
         # the same linear system with the opt-in mixed-precision storage (fp32 Krylov basis and fp32 FDM
         # sub-solves; all reductions, the operator and the convergence test on the true residual stay fp64)
@@ -356,7 +367,8 @@ def main():
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
     # capture of this kernel on this workload (profiles/r1_ncu_assemble_march_128.csv)
-    ncu_traffic = {(128, 1): 105.420288e6 + 970.983680e6}.get((grid, world))
+    # dram read + write of one launch from the committed `ncu --set full` capture (profiles/), per workload
+    ncu_traffic = {('ldc', 128, 1): 105.420288e6 + 970.983680e6}.get((args.problem, grid, world))
     line = {
         'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
@@ -368,7 +380,8 @@ def main():
                    'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': ncu_traffic, 'peak_source': peak_src,
-                     'kernel': 'tfb_assemble_march_kernel<Cfg_ldc3d,J=1,F=1,TJ=2,KCH=16>',
+                     'kernel': ('tfb_assemble_kernel (2-D tile kernel)' if two_d else
+                                'tfb_assemble_march_kernel<Cfg_%s,J=1,F=1>' % ('rb3d' if args.problem == 'rb' else 'ldc3d')),
                      'algorithmic_bytes_per_launch': alg_bytes},
         'e2e': {'value': total_cells / (e2e_ms * 1e-3), 'unit': 'cells/s', 'ms_per_step': e2e_ms,
                 'h2d_bytes_per_step': 8 * n_local, 'd2h_bytes_per_step': 8 * n_local},

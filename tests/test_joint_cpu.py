@@ -39,7 +39,7 @@ class JointModel:
         self.mets = mets = [hostprep.axis_metrics(v, m) for v, m in ((orc.x, nx), (orc.y, ny), (orc.z, nz))]
         self.ops = hostprep.fdm_operators(cfg, prm, mets, nx, ny, nz)
         self.cv, self.cT = prm.c_visc, prm.c_T
-        tparts = sorted([o for o in self.ops if o[0] == cfg.T], key=lambda o: o[1])
+        tparts = sorted([o for o in self.ops if o[0] == 2], key=lambda o: o[1])     # w's horizontal basis
         self.Qx, self.Qy = tparts[0][3], tparts[1][3]
         self.lx, self.ly = tparts[0][4], tparts[1][4]
         self.zc = numpy.zeros((12, nz))

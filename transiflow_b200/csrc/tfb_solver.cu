@@ -823,15 +823,18 @@ static int joint_refresh(tfb_ctx* c, tfb_mat* m) {
     return 0;
 }
 
-// (z_w, z_T) = Fwt^-1 (r_w, r_T) on interleaved vectors: the x/y transforms of the scalar's
+// (z_w, z_T) = Fwt^-1 (r_w, r_T) on interleaved vectors: the x/y transforms of the vertical velocity's
 // fast-diagonalisation basis, one banded solve per horizontal mode, transforms back.
 static int joint_solve(tfb_ctx* c, const double* r, double* z) {
     tfb_solver_state* s = c->solver;
     TFB_CHECK(c->nranks == 1, "the coupled (w, T) solve is not implemented for z-slab runs");
     const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, dof = c->desc.dof;
     const int wv = s->joint_w, sv = s->joint_s;
-    const FdmVar& f = s->var[sv];
-    TFB_CHECK(f.present && f.m[0] == nx && f.m[1] == ny, "scalar FDM basis missing");
+    // horizontal basis: the vertical velocity's (exact for the viscous block; the scalar block then sees w's
+    // side-wall folds, a boundary-layer-sized defect the Krylov iteration absorbs).  With Pr > 1 the viscous
+    // block dominates, and the scalar's own basis was measurably worse at low Rayleigh numbers.
+    const FdmVar& f = s->var[wv];
+    TFB_CHECK(f.present && s->var[sv].present && f.m[0] == nx && f.m[1] == ny, "FDM basis of the vertical velocity missing");
     const long long plane = (long long)nx * ny, ncell = plane * nz;
     if (!s->jbuf[0]) {
         TFB_CUDA(cudaMalloc(&s->jbuf[0], sizeof(double) * 2 * ncell));
@@ -847,7 +850,7 @@ static int joint_solve(tfb_ctx* c, const double* r, double* z) {
     if (axis_gemm<double>(c, false, b, a, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nz * 2)) return -1;
     const unsigned nb = (unsigned)((plane + 127) / 128);
     k_joint_lines<<<nb, 128, sizeof(double) * TFB_JZ_ROWS * nz, c->stream>>>(
-        nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], s->var[wv].coef, f.coef, a, a + ncell, s->jab, s->jab + 2 * ncell);
+        nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, a, a + ncell, s->jab, s->jab + 2 * ncell);
     TFB_LAUNCHED();
     if (axis_gemm<double>(c, true, a, b, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nz * 2)) return -1;
     if (axis_gemm<double>(c, true, b, a, f.Q[0], nx, ny * nz * 2, nx, nx, nx, 1, 0, 1)) return -1;
