@@ -222,7 +222,14 @@ struct TfbMarch {
     static constexpr int DSTR = HW + ((4 - HW % 16) + 16) % 16;   // = 4 (mod 16): conflict-free transpose stores
     static constexpr int SLOT = Cfg::DOF * DSTR;                  // doubles per ring slot (one plane)
     static constexpr int NSLOT = 5;   // planes k-1, k, k+1 in use, k+2 landed, k+3 in flight
-    static constexpr int LINE_CAP = TFB_TI * Cfg::CELL_SLOTS + 2;
+    // Staging of a line's CSR span: lane il (cell il of the line) stores slot s of its row at
+    // (cell start) + (row offset) + s, i.e. the lanes of one store instruction are CELL_SLOTS doubles
+    // apart.  57 (lid-driven cavity) is odd: 16 distinct 8-byte banks, conflict-free.  72 (Rayleigh-Benard,
+    // heated cavity) = 8 mod 16: two banks, 16-way conflicts (ncu: 74 M conflict cycles, short-scoreboard
+    // the top stall).  PAIRPAD shifts every PAIR of cells by 2 more doubles (16 bytes, so each pair is still
+    // a legal bulk-copy source): 8 distinct banks, and the line leaves as 16 bulk stores instead of one.
+    static constexpr bool PAIRPAD = (Cfg::CELL_SLOTS % 8) == 0;
+    static constexpr int LINE_CAP = TFB_TI * Cfg::CELL_SLOTS + 2 + (PAIRPAD ? TFB_TI : 0);
     __host__ __device__ static constexpr int smem_doubles(bool do_j) { return NSLOT * SLOT + (do_j ? 2 * TJ * LINE_CAP : 0); }
 };
 
@@ -241,6 +248,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     constexpr int DOF = Cfg::DOF, W = M::W, H = M::H, DSTR = M::DSTR, SLOT = M::SLOT, LINE_CAP = M::LINE_CAP;
     constexpr int NT = 32 * DOF * TJ;
     constexpr int ROWLEN = W * DOF, NEL = H * ROWLEN, NPT = (NEL + NT - 1) / NT;
+    constexpr bool PAIRPAD = M::PAIRPAD;
     extern __shared__ __align__(16) double smem[];
     double* ring = smem;
     double* sm_out = smem + M::NSLOT * SLOT;   // SLOT is even (DSTR multiple of 4)
@@ -319,6 +327,8 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     const int i = i0 + il, j = j0 + jl;
     const bool valid = i < g.nx && j < g.ny;
     const bool leader = DO_J && d1 == 0 && il == 0 && j < g.ny;
+    const bool storer = PAIRPAD ? (DO_J && d1 == 0 && j < g.ny) : leader;   // threads that issue bulk stores
+    const int padl = PAIRPAD ? (il & ~1) : 0;                               // staging shift of this lane's cell
     const int ilast = min(i0 + TFB_TI, g.nx);
     long long row = (((long long)kbeg * g.ny + j) * g.nx + i) * DOF + d1;              // local row of this thread
     long long r0 = (((long long)kbeg * g.ny + j) * g.nx + i0) * DOF;                  // span of this line
@@ -392,7 +402,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
             P.pl[2] = ring + s2 * SLOT + cell_off;
             double f = 0.0;
             if (xy_interior && !(c.near[2] | c.far[2] | c.far2[2])) {
-                TfbSmemSink sink{out + (rp - galign)};
+                TfbSmemSink sink{out + (rp - galign) + padl};
                 Cfg::template row<DO_J, DO_F, 0>(d1, a.prm, c, P, sink, f);
             } else {
                 double J[Cfg::MAXSLOT];
@@ -400,7 +410,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
                 Cfg::template row<DO_J, DO_F, 2>(d1, a.prm, c, P, sink, f);
                 if (DO_J) {
                     const unsigned m = Cfg::mask(d1, c);
-                    int pos = rp - galign;
+                    int pos = rp - galign + padl;
 #pragma unroll
                     for (int s = 0; s < Cfg::MAXSLOT; s++)
                         if ((m >> s) & 1u) out[pos++] = J[s];
@@ -418,10 +428,31 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
         // staged CSR values -> async proxy; deposited plane + spans -> everyone.  The bulk store of
         // the previous plane must have drained its staging buffer before anyone refills it.
         if (DO_J) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // plane k+2 (requested one step ago) has landed
         __syncthreads();
-        if (leader) {
+        if (PAIRPAD) {
+            if (storer) {
+                // one bulk store per pair of cells (even lanes of the line's first warp); rp of these lanes is
+                // the CSR offset at which their cell starts
+                const int ncl = ilast - i0;
+                const int rp2 = __shfl_down_sync(0xffffffffu, rp, 2);
+                if (!(il & 1) && il < ncl) {
+                    const int rel0 = rp - galign, rel1 = (il + 2 < ncl ? rp2 : gend) - galign;
+                    const int head = rel0 & 1, b0 = rel0 + head, b1 = rel1 & ~1;
+                    if (b1 > b0) {
+                        const unsigned src = (unsigned)__cvta_generic_to_shared(out + b0 + il);
+                        double* dstp = a.vals + galign + b0;
+                        const unsigned bytes = (unsigned)(b1 - b0) * 8u;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(dstp), "r"(src), "r"(bytes) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (head) a.vals[galign + rel0] = out[rel0 + il];
+                    if (rel1 & 1) a.vals[galign + rel1 - 1] = out[rel1 - 1 + il];
+                }
+            }
+        } else if (leader) {
             // one TMA bulk store per line (smem -> global), double-buffered staging
             const int head = gbase - galign, cnt = gend - galign;
             const int body0 = head ? 2 : 0, body1 = cnt & ~1;
@@ -441,7 +472,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
         r0 += plane;
         s0 = s1;
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ---- pattern discovery: structural row lengths, then global column indices ----
