@@ -177,8 +177,6 @@ def main():
     if args.problem == 'rb':
         PARAMS.clear()
         PARAMS.update(RB_PARAMS)
-        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
-            args.newton_steps = 0      # the coupled (w, T) solve of the RB preconditioner is single-GPU
     two_d = PROBLEMS_2D.get(args.problem)
     if two_d:
         PARAMS.clear()
@@ -207,8 +205,10 @@ def main():
     # weak scaling: every rank owns `grid` planes of a (grid x grid x world*grid) domain
     nz = grid * world if args.scaling == 'weak' else grid
     params = dict(PARAMS)
-    if world > 1 and args.scaling == 'weak':
+    if world > 1 and args.scaling == 'weak' and args.problem != 'rb':
         params['Z-max'] = float(world)      # the cavity grows with the GPU count: cells stay cubic
+    # (Rayleigh-Benard keeps its unit layer height -- a taller layer is a different, far more supercritical
+    # problem: the effective Rayleigh number grows with height^3 -- and refines z instead)
     if two_d:
         if world > 1:
             raise SystemExit('2-D configurations are single-GPU ("replicas only", DESIGN.md section 5)')
@@ -319,11 +319,13 @@ def main():
             if args.problem == 'rb' and k == 0:
                 # Newton from zero lands on the conduction state in one (linear) step; the timed steps start from
                 # that state plus a smooth roll-like perturbation so that they are genuine Newton steps
-                c3 = numpy.indices((it.nz, it.ny, it.nx)).astype(float)
-                roll = numpy.sin(numpy.pi * (c3[0] + 1) / it.nz) * numpy.cos(6 * numpy.pi * (c3[2] + 0.5) / it.nx)
-                xs = x.reshape(it.nz, it.ny, it.nx, it.dof)
+                k0s, k1s = it.slab
+                c3 = numpy.indices((k1s - k0s, it.ny, it.nx)).astype(float)
+                roll = numpy.sin(numpy.pi * (c3[0] + k0s + 1) / it.nz) * numpy.cos(6 * numpy.pi * (c3[2] + 0.5) / it.nx)
+                xs = x.reshape(k1s - k0s, it.ny, it.nx, it.dof)
                 xs[..., 2] += 1e-2 * roll
-                xs[-1, :, :, 2] = 0.0
+                if k1s == it.nz:
+                    xs[-1, :, :, 2] = 0.0
                 xs[..., 4] += 1e-2 * roll
             hist.append({'ms': max_over_ranks(ms5.value), 'wall_ms': 1e3 * (time.perf_counter() - t0),
                          'fnorm': float(numpy.sqrt(max_over_ranks(float(f @ f)) if world > 1 else f @ f)),

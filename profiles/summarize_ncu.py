@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+'''Turns an `ncu --set full` report (gpurun_out/*.ncu-rep, scratch) into the small CSV summaries kept in
+profiles/:   python profiles/summarize_ncu.py REPORT.ncu-rep "comment line" "command line" > profiles/NAME.csv'''
+import csv
+import subprocess
+import sys
+
+KEEP = [
+    'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+    'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+    'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+    'launch__occupancy_limit_shared_mem', 'launch__shared_mem_per_block_dynamic',
+    'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+]
+
+
+def main():
+    rep, comment, command = sys.argv[1], sys.argv[2], sys.argv[3]
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, val = rows[0], rows[1], rows[2]
+    print('# ' + comment)
+    print('# command: ' + command)
+    stalls = []
+    for h, u, v in zip(hdr, units, val):
+        if h in KEEP:
+            print('%s,%s,%s' % (h, u, v))
+        elif 'issue_stalled' in h and h.endswith('per_issue_active.ratio'):
+            stalls.append((float(v.replace(',', '')), h))
+    for v, h in sorted(stalls, reverse=True)[:8]:
+        print('%s,ratio,%.3f' % (h, v))
+
+
+if __name__ == '__main__':
+    main()

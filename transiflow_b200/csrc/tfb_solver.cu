@@ -827,44 +827,70 @@ static int joint_refresh(tfb_ctx* c, tfb_mat* m) {
 // fast-diagonalisation basis, one banded solve per horizontal mode, transforms back.
 static int joint_solve(tfb_ctx* c, const double* r, double* z) {
     tfb_solver_state* s = c->solver;
-    TFB_CHECK(c->nranks == 1, "the coupled (w, T) solve is not implemented for z-slab runs");
-    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, dof = c->desc.dof;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl, dof = c->desc.dof;
     const int wv = s->joint_w, sv = s->joint_s;
     // horizontal basis: the vertical velocity's (exact for the viscous block; the scalar block then sees w's
     // side-wall folds, a boundary-layer-sized defect the Krylov iteration absorbs).  With Pr > 1 the viscous
     // block dominates, and the scalar's own basis was measurably worse at low Rayleigh numbers.
     const FdmVar& f = s->var[wv];
     TFB_CHECK(f.present && s->var[sv].present && f.m[0] == nx && f.m[1] == ny, "FDM basis of the vertical velocity missing");
-    const long long plane = (long long)nx * ny, ncell = plane * nz;
+    const long long plane = (long long)nx * ny, ncell = plane * nzl;
+    const bool dist = c->nranks > 1;
+    if (dist && dist_setup(c)) return -1;
+    const int cyme = dist ? s->j0s[c->rank + 1] - s->j0s[c->rank] : ny;
+    const long long lines = (long long)cyme * nx, npen = lines * nz;
     if (!s->jbuf[0]) {
         TFB_CUDA(cudaMalloc(&s->jbuf[0], sizeof(double) * 2 * ncell));
         TFB_CUDA(cudaMalloc(&s->jbuf[1], sizeof(double) * 2 * ncell));
-        TFB_CUDA(cudaMalloc(&s->jab, sizeof(double) * 4 * ncell));
+        TFB_CUDA(cudaMalloc(&s->jab, sizeof(double) * 4 * std::max(ncell, npen)));
     }
     double *a = s->jbuf[0], *b = s->jbuf[1];
     const unsigned vb = vec_blocks(ncell);
     k_deinterleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, wv, r, a);
     k_deinterleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, sv, r, a + ncell);
     TFB_LAUNCHED(); TFB_LAUNCHED();
-    if (axis_gemm<double>(c, false, a, b, f.Q[0], nx, ny * nz * 2, nx, nx, nx, 1, 0, 1)) return -1;
-    if (axis_gemm<double>(c, false, b, a, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nz * 2)) return -1;
-    const unsigned nb = (unsigned)((plane + 127) / 128);
-    k_joint_lines<<<nb, 128, sizeof(double) * TFB_JZ_ROWS * nz, c->stream>>>(
-        nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, a, a + ncell, s->jab, s->jab + 2 * ncell);
-    TFB_LAUNCHED();
-    if (axis_gemm<double>(c, true, a, b, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nz * 2)) return -1;
-    if (axis_gemm<double>(c, true, b, a, f.Q[0], nx, ny * nz * 2, nx, nx, nx, 1, 0, 1)) return -1;
+    if (axis_gemm<double>(c, false, a, b, f.Q[0], nx, ny * nzl * 2, nx, nx, nx, 1, 0, 1)) return -1;
+    if (axis_gemm<double>(c, false, b, a, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nzl * 2)) return -1;
+    const size_t jsmem = sizeof(double) * TFB_JZ_ROWS * nz;
+    if (!dist) {
+        k_joint_lines<<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(
+            nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, a, a + ncell, s->jab, s->jab + 2 * ncell);
+        TFB_LAUNCHED();
+    } else {
+        // the lines run through every slab: transpose w and T to the pencil layout (all z, my y-chunk) with
+        // one all-to-all each, solve, transpose back -- the same exchange the FDM z-transform uses
+        TfbChunks ch;
+        ch.n = c->nranks;
+        for (int q = 0; q <= c->nranks; q++) ch.j0[q] = s->j0s[q];
+        for (int q = 0; q < c->nranks; q++) ch.dsp[q] = s->a2a_dsp_slab[q];
+        for (int h = 0; h < 2; h++) {
+            k_a2a_pack<true, double><<<vb, 256, 0, c->stream>>>(nx, ny, nzl, ch, a + h * ncell, s->sbuf);
+            TFB_LAUNCHED();
+            if (tfb_alltoallv_bytes(c, s->sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, s->pen[h], s->a2a_cnt_pen, s->a2a_dsp_pen, (int)sizeof(double))) return -1;
+        }
+        k_joint_lines<<<(unsigned)((lines + 127) / 128), 128, jsmem, c->stream>>>(
+            nx, cyme, s->j0s[c->rank], nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, s->pen[0], s->pen[1],
+            s->jab, s->jab + 2 * npen);
+        TFB_LAUNCHED();
+        for (int h = 0; h < 2; h++) {
+            if (tfb_alltoallv_bytes(c, s->pen[h], s->a2a_cnt_pen, s->a2a_dsp_pen, s->rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, (int)sizeof(double))) return -1;
+            k_a2a_pack<false, double><<<vb, 256, 0, c->stream>>>(nx, ny, nzl, ch, a + h * ncell, s->rbuf);
+            TFB_LAUNCHED();
+        }
+    }
+    if (axis_gemm<double>(c, true, a, b, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nzl * 2)) return -1;
+    if (axis_gemm<double>(c, true, b, a, f.Q[0], nx, ny * nzl * 2, nx, nx, nx, 1, 0, 1)) return -1;
     k_interleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, wv, a, z, 1.0);
     k_interleave<double><<<vb, 256, 0, c->stream>>>(ncell, dof, sv, a + ncell, z, 1.0);
     TFB_LAUNCHED(); TFB_LAUNCHED();
-    // the top-wall rows of w carry a -1 diagonal
-    const long long top = (ncell - plane) * dof;
-    k_negate_var<<<vec_blocks(plane), 256, 0, c->stream>>>(plane, dof, wv, r + top, z + top);
-    TFB_LAUNCHED();
+    if (c->desc.k0 + nzl == nz) {   // the top-wall rows of w carry a -1 diagonal (the slab that owns the last plane)
+        const long long top = (ncell - plane) * dof;
+        k_negate_var<<<vec_blocks(plane), 256, 0, c->stream>>>(plane, dof, wv, r + top, z + top);
+        TFB_LAUNCHED();
+    }
     TFB_CUDA(cudaGetLastError());
     return 0;
 }
-
 
 __global__ void k_mask_copy(long long n, int dof, unsigned mask, const double* __restrict__ x, double* __restrict__ y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1192,7 +1218,7 @@ extern "C" int tfb_precond_apply(tfb_mat* m, const double* r, double* z, int pre
     if (dist_setup(c)) return -1;
     tfb_solver_state* s = c->solver;
     TFB_CUDA(cudaMemcpyAsync(s->vec[4], r, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
-    s->joint_on = s->joint_ready && c->nranks == 1;
+    s->joint_on = s->joint_ready;
     if (sub_refresh(c, m, pressure_row)) return -1;
     if (apply_precond(c, m, pressure_row, s->vec[4], s->vec[5])) return -1;
     TFB_CUDA(cudaMemcpyAsync(z, s->vec[5], sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
@@ -1535,7 +1561,7 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     solver_of(m->ctx)->inner_its = std::min(24, (o->reserved[2] >> 8) & 0xff);   // d_scal slice holds 2k+3 <= 56 doubles
     solver_of(m->ctx)->inner_total = 0;
     // reserved[2] bit 1: 'Scalar Coupling': 'none' (block-triangular treatment of the scalars)
-    solver_of(m->ctx)->joint_on = solver_of(m->ctx)->joint_ready && !(o->reserved[2] & 2) && m->ctx->nranks == 1;
+    solver_of(m->ctx)->joint_on = solver_of(m->ctx)->joint_ready && !(o->reserved[2] & 2);
     if (const char* e = getenv("TFB_INNER_TOL")) solver_of(m->ctx)->inner_tol = atof(e);
     if (o->reserved[1] == 1) return bicgstab_run(m, b, x, o, info);
     if (o->reserved[0] == 1) return fgmres_run<float>(m, b, x, o, info);

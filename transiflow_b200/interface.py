@@ -260,10 +260,8 @@ class Interface:
             check(_lib.lib().tfb_fdm_set(self._ctx, v, a, m, ptr(Q), ptr(lam), ctypes.c_double(coef)))
         if self.problem == recipes.AMOC:
             check(_lib.lib().tfb_fdm_pin(self._ctx, self.config.S, ctypes.c_int64(0), ctypes.c_double(-1.0)))
-        # Rayleigh-Benard on a true 3-D grid: w and T are solved together along z (csrc/tfb_joint.h);
-        # single GPU only -- z-slab runs keep the block-triangular treatment of the scalar
-        self._joint = (self.problem in (recipes.RB, recipes.RBP) and self.dim == 3 and self.nz > 2
-                       and self.dof == 5 and self.slab == (0, self.nz))
+        # Rayleigh-Benard on a true 3-D grid: w and T are solved together along z (csrc/tfb_joint.h)
+        self._joint = self.problem in (recipes.RB, recipes.RBP) and self.dim == 3 and self.nz > 2 and self.dof == 5
         if self._joint:
             zops = hostprep.joint_z_operators(self.config, self._prm, self._mets, self.nz)
             check(_lib.lib().tfb_joint_set(self._ctx, self.dim - 1, self.config.T, self.nz, ptr(zops)))
