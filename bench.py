@@ -166,7 +166,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
-    ap.add_argument('--newton-steps', type=int, default=2, help='timed Newton steps (0 = skip the solver leg)')
+    ap.add_argument('--newton-steps', type=int, default=3, help='timed Newton steps (0 = skip the solver leg)')
     ap.add_argument('--grid', type=int, default=128)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -330,10 +330,12 @@ def main():
             hist.append({'ms': max_over_ranks(ms5.value), 'wall_ms': 1e3 * (time.perf_counter() - t0),
                          'fnorm': float(numpy.sqrt(max_over_ranks(float(f @ f)) if world > 1 else f @ f)),
                          'iterations': it.last_solve['iterations'], 'relres': it.last_solve['relres'],
+                         'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
                          'converged': bool(it.last_solve['converged'])})
         timed = hist[2:]
         nms = sum(h['ms'] for h in timed) / len(timed)
         newton = {'steps_per_s': 1e3 / nms, 'ms_per_step': nms, 'timed_steps': len(timed),
+                  'ms_of_each_step': [round(h['ms'], 1) for h in timed], 'solve_ms_of_each_step': [round(h['solve_ms'], 1) for h in timed],
                   'krylov_iterations': [h['iterations'] for h in timed], 'relres': [h['relres'] for h in timed],
                   'fnorm_before': [h['fnorm'] for h in timed], 'all_converged': all(h['converged'] for h in hist),
                   'tolerance': 1e-10, 'unknowns': it.n,
@@ -352,6 +354,12 @@ def main():
                                                'relres': it.last_solve['relres'],
                                                'converged': bool(it.last_solve['converged']),
                                                'default_newton_step_ms': max_over_ranks(hist[-1]['ms'])}
+            it.parameters['Iterative Solver'] = dict(saved or {}, **{'Preconditioner Precision': 'tf32'})
+            it.solve(jac, -f)
+            newton['tf32_preconditioner_solve'] = {'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
+                                                   'iterations': it.last_solve['iterations'],
+                                                   'relres': it.last_solve['relres'],
+                                                   'converged': bool(it.last_solve['converged'])}
             if saved is None:
                 it.parameters.pop('Iterative Solver')
             else:

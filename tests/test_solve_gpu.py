@@ -192,7 +192,7 @@ def test_implicit_euler_matches_reference_time_integration():
 
 
 @pytest.mark.parametrize('options', [{'Method': 'BiCGStab'}, {'Basis Precision': 'single', 'Restart': 40},
-                                     {'Preconditioner Precision': 'single'},
+                                     {'Preconditioner Precision': 'single'}, {'Preconditioner Precision': 'tf32'},
                                      {'Preconditioner Precision': 'single', 'Basis Precision': 'single'},
                                      {'Velocity Iterations': 3}])
 def test_alternative_krylov_options_reach_the_same_solution(options):

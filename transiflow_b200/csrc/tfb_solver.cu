@@ -556,6 +556,7 @@ static struct {
     cublasHandle_t_ h;
     int (*Create)(cublasHandle_t_*);
     int (*SetStream)(cublasHandle_t_, cudaStream_t);
+    int (*SetMathMode)(cublasHandle_t_, int);
     int (*DgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const double*, const double*, int, long long,
                                const double*, int, long long, const double*, double*, int, long long, int);
     int (*SgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const float*, const float*, int, long long,
@@ -575,6 +576,7 @@ static bool blas_ready(tfb_ctx* c) {
             if (g_blas.lib) {
                 *(void**)(&g_blas.Create) = dlsym(g_blas.lib, "cublasCreate_v2");
                 *(void**)(&g_blas.SetStream) = dlsym(g_blas.lib, "cublasSetStream_v2");
+                *(void**)(&g_blas.SetMathMode) = dlsym(g_blas.lib, "cublasSetMathMode");
                 *(void**)(&g_blas.DgemmStridedBatched) = dlsym(g_blas.lib, "cublasDgemmStridedBatched");
                 *(void**)(&g_blas.SgemmStridedBatched) = dlsym(g_blas.lib, "cublasSgemmStridedBatched");
                 if (g_blas.Create && g_blas.SetStream && g_blas.DgemmStridedBatched && g_blas.SgemmStridedBatched &&
@@ -1560,6 +1562,10 @@ extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve
     solver_of(m->ctx)->precond_single = (o->reserved[2] & 1) == 1;
     solver_of(m->ctx)->inner_its = std::min(24, (o->reserved[2] >> 8) & 0xff);   // d_scal slice holds 2k+3 <= 56 doubles
     solver_of(m->ctx)->inner_total = 0;
+    // reserved[2] bit 2: the fp32 FDM transforms may run on the tensor cores in TF32 (cuBLAS math mode); they are
+    // plain dense GEMMs and only ever feed the flexible preconditioner
+    if (blas_ready(m->ctx) && g_blas.SetMathMode)
+        g_blas.SetMathMode(g_blas.h, (o->reserved[2] & 5) == 5 ? 3 /* CUBLAS_TF32_TENSOR_OP_MATH */ : 0 /* CUBLAS_DEFAULT_MATH */);
     // reserved[2] bit 1: 'Scalar Coupling': 'none' (block-triangular treatment of the scalars)
     solver_of(m->ctx)->joint_on = solver_of(m->ctx)->joint_ready && !(o->reserved[2] & 2);
     if (const char* e = getenv("TFB_INNER_TOL")) solver_of(m->ctx)->inner_tol = atof(e);
@@ -1578,14 +1584,14 @@ extern "C" int tfb_spmv_bench(tfb_mat* m, int reps, int masked, float* ms_out) {
     tfb_solver_state* s = c->solver;
     const int dim = c->desc.dim;
     const unsigned velmask = (1u << dim) - 1u;
-    TFB_CUDA(cudaMemsetAsync(s->vec[0], 0, sizeof(double) * c->n_local, c->stream));
+    TFB_CUDA(cudaMemcpyAsync(s->vec[0], s->d_mass, sizeof(double) * c->n_local, cudaMemcpyDeviceToDevice, c->stream));   // any non-zero x
     cudaEvent_t e0, e1;
     TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
     for (int w = 0; w < 3; w++)
-        if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, velmask, nullptr)) return -1;
+        if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, masked ? velmask : 0u, nullptr)) return -1;
     TFB_CUDA(cudaEventRecord(e0, c->stream));
     for (int r = 0; r < reps; r++)
-        if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, velmask, nullptr)) return -1;
+        if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, masked ? velmask : 0u, nullptr)) return -1;
     TFB_CUDA(cudaEventRecord(e1, c->stream));
     TFB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

@@ -378,7 +378,10 @@ class Interface:
         # iterates on the (velocity, temperature) block; 'none' is the block-triangular preconditioner
         joint = getattr(self, '_joint', False) and str(its.get('Scalar Coupling', 'joint')).lower() != 'none'
         inner = int(its.get('Velocity Iterations', 8 if joint else 0))
-        o.reserved[2] = int(its.get('Preconditioner Precision', 'double') == 'single') \
+        # 'Preconditioner Precision': 'single' runs the FDM sub-solves in fp32, 'tf32' additionally lets their dense
+        # transforms use the tensor cores in TF32 (FGMRES is flexible: the outer iteration and the tolerance stay fp64)
+        pprec = str(its.get('Preconditioner Precision', 'double')).lower()
+        o.reserved[2] = (1 if pprec in ('single', 'tf32') else 0) | (4 if pprec == 'tf32' else 0) \
             | (0 if joint else 2) | (min(24, max(0, inner)) << 8)
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
