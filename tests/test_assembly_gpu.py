@@ -197,3 +197,51 @@ def test_64_cubed_matches_oracle():
     coA, jcoA, begA = orc.jacobian(state)
     assert numpy.array_equal(csr.indptr, begA) and numpy.array_equal(csr.indices, jcoA)
     assert numpy.array_equal(csr.data, coA)
+
+
+RB_PARAMS = {'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 1000.0, 'Prandtl Number': 10.0, 'Biot Number': 1.0,
+             'X-max': 10, 'Y-max': 10}
+
+
+def test_full_size_rayleigh_benard_128_cubed_properties():
+    '''BASELINE config 4 (3-D Rayleigh-Benard 128^3, dof 5, 10.5 M unknowns, 149 M non-zeros): the structural nnz
+    polynomial fitted on the reference, linearity of J, finite-difference consistency of J with
+    F (tests/test_jacobian.py:139-230), fused == separate launches.'''
+    N = 128
+    it = _iface(RB_PARAMS, N, N, N, None, None)
+    assert it.nnz == 72 * N**3 - 110 * N**2 + 36 * N
+    rng = numpy.random.default_rng(0)
+    x = rng.uniform(-0.5, 0.5, it.n)
+    p = rng.uniform(-0.5, 0.5, it.n)
+    q = rng.uniform(-0.5, 0.5, it.n)
+    for v in (x, p):
+        g = v.reshape(N, N, N, 5)
+        g[:, :, N - 1, 0] = 0
+        g[:, N - 1, :, 1] = 0
+        g[N - 1, :, :, 2] = 0
+    jac, f0 = it.jacobian_rhs(x)
+    jp, jq = jac @ p, jac @ q
+    lin = jac @ (2.0 * p - 3.0 * q)
+    assert numpy.abs(lin - (2.0 * jp - 3.0 * jq)).max() <= 1e-12 * numpy.abs(lin).max()
+    errs = []
+    for eps in (1e-3, 1e-5):
+        fd = (it.rhs(x + eps * p) - f0) / eps
+        errs.append(numpy.linalg.norm(fd - jp) / numpy.linalg.norm(jp))
+    assert errs[0] < 1e-2 and errs[1] < 1e-4 and errs[1] < errs[0] / 30, errs
+    assert numpy.array_equal(it.rhs(x), f0)
+
+
+@pytest.mark.parametrize('nx,ny,nz', [(64, 48, 40), (33, 35, 37)])
+def test_rayleigh_benard_matches_oracle_across_tiles(nx, ny, nz):
+    '''Several 32-cell tiles in x, odd line counts and more planes than one z-chunk: every staged pair of cells of the
+    72-slot rows (pair-padded staging, csrc/tfb_assemble.cuh) must land on its CSR offset -- bit-identical to the oracle.'''
+    from oracle.tf_oracle import Oracle
+    it = _iface(RB_PARAMS, nx, ny, nz, None, None)
+    orc = Oracle(dict(RB_PARAMS), nx, ny, nz)
+    state = make_state(5, it.n)
+    jac, f = it.jacobian_rhs(state)
+    assert numpy.array_equal(f, orc.rhs(state))
+    csr = jac.tocsr()
+    coA, jcoA, begA = orc.jacobian(state)
+    assert numpy.array_equal(csr.indptr, begA) and numpy.array_equal(csr.indices, jcoA)
+    assert numpy.array_equal(csr.data, coA)
