@@ -1,0 +1,26 @@
+'''Solver-option scan on one Newton system of the 3-D cavity (diagnostic script, not a test):
+python tests/solve_scan.py [grid]'''
+import sys, time, numpy
+sys.path.insert(0, '.')
+import transiflow_b200 as tb
+
+g = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+p = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1}
+it = tb.Interface(p, g, g, g)
+x = it.vector()
+for k in range(2):
+    jac, f = it.jacobian_rhs(x)
+    x = x + it.solve(jac, -f)
+jac, f = it.jacobian_rhs(x)
+ref = it.solve(jac, -f)
+variants = [{}, {'Restart': 100}, {'Restart': 60}, {'Restart': 40}, {'Basis Precision': 'single'},
+            {'Basis Precision': 'single', 'Restart': 80}, {'Velocity Iterations': 2}, {'Velocity Iterations': 2, 'Restart': 60},
+            {'Method': 'BiCGStab'}]
+for v in variants:
+    p['Iterative Solver'] = v
+    t0 = time.perf_counter()
+    y = it.solve(jac, -f)
+    w = (time.perf_counter() - t0) * 1e3
+    err = numpy.abs(y - ref).max() / numpy.abs(ref).max()
+    print('%-55s its %4d  device %.1f ms  wall %.1f ms  relres %.2e  diff %.1e' % (v, it.last_solve['iterations'],
+          it.last_solve['solve_ms'], w, it.last_solve['relres'], err), flush=True)

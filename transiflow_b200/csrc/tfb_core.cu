@@ -99,6 +99,7 @@ extern "C" void tfb_destroy(tfb_ctx* c) {
     cudaFree(c->d_row_ptr);
     cudaFree(c->d_col);
     cudaFree(c->d_flush);
+    for (double* p : c->vals_pool) cudaFree(p);
     tfb_solver_free(c->solver);
     for (int e = 0; e < 16; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -201,13 +202,23 @@ extern "C" int tfb_get_pattern(tfb_ctx* c, int64_t* row_ptr, int64_t* col_idx) {
     return 0;
 }
 
+// versions are unique across matrices: the solver's caches are keyed on (address, version) and a new tfb_mat can
+// land on the address of a destroyed one
+uint64_t tfb_next_version() { static uint64_t v = 0; return ++v; }
+
 extern "C" int tfb_mat_create(tfb_ctx* c, tfb_mat** out) {
     TFB_CHECK(c && out && c->have_pattern, "no pattern");
     TFB_CUDA(cudaSetDevice(c->desc.device));
     tfb_mat* m = new tfb_mat();
     m->ctx = c;
     // +2: the structured SpMV fetches whole 16-byte pairs and may read one element past the last span
-    TFB_CUDA(cudaMalloc(&m->d_vals, sizeof(double) * ((size_t)c->nnz + 2)));
+    if (!c->vals_pool.empty()) {
+        m->d_vals = c->vals_pool.back();
+        c->vals_pool.pop_back();
+    } else {
+        cudaError_t e = cudaMalloc(&m->d_vals, sizeof(double) * ((size_t)c->nnz + 2));
+        if (e != cudaSuccess) { delete m; return tfb_fail(__FILE__, __LINE__, "cudaMalloc(values)", cudaGetErrorString(e)); }
+    }
     TFB_CUDA(cudaMemset(m->d_vals, 0, sizeof(double) * ((size_t)c->nnz + 2)));
     *out = m;
     return 0;
@@ -215,8 +226,14 @@ extern "C" int tfb_mat_create(tfb_ctx* c, tfb_mat** out) {
 
 extern "C" void tfb_mat_destroy(tfb_mat* m) {
     if (!m) return;
-    cudaSetDevice(m->ctx->desc.device);
-    cudaFree(m->d_vals);
+    tfb_ctx* c = m->ctx;
+    cudaSetDevice(c->desc.device);
+    if (m->d_vals && c->vals_pool.size() < 2) {
+        cudaDeviceSynchronize();            // what cudaFree did implicitly: nothing in flight still reads the buffer
+        c->vals_pool.push_back(m->d_vals);
+    } else {
+        cudaFree(m->d_vals);
+    }
     delete m;
 }
 
@@ -233,7 +250,7 @@ extern "C" int tfb_mat_set_values(tfb_mat* m, const double* in) {
     TFB_CUDA(cudaSetDevice(m->ctx->desc.device));
     TFB_CUDA(cudaMemcpyAsync(m->d_vals, in, sizeof(double) * (size_t)m->ctx->nnz, cudaMemcpyHostToDevice, m->ctx->stream));
     TFB_CUDA(cudaStreamSynchronize(m->ctx->stream));
-    m->version++;
+    m->version = tfb_next_version();
     return 0;
 }
 
@@ -366,7 +383,7 @@ extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f)
         int rc = tfb_halo_exchange(c, c->d_state);
         if (rc) return rc;
     }
-    if (do_j) m->version++;
+    if (do_j) m->version = tfb_next_version();
     return dispatch_assemble(c, m, do_j, do_f);
 }
 
@@ -423,7 +440,7 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
                                  cudaMemcpyHostToDevice, c->s_h2d));
         TFB_CUDA(cudaEventRecord(c->ev_up[ch], c->s_h2d));
     }
-    m->version++;
+    m->version = tfb_next_version();
     for (int ch = 0; ch < nch; ch++) {
         const int p0 = ch * TFB_KCH, p1 = std::min(p0 + TFB_KCH, c->nzl);
         TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[std::min(ch + 1, nch - 1)], 0));   // needs the first plane of the next chunk
@@ -601,7 +618,7 @@ extern "C" int tfb_mat_add_diag(tfb_mat* dst, const tfb_mat* src, double alpha, 
     TFB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(dd);
     cudaFree(dmiss);
-    dst->version++;
+    dst->version = tfb_next_version();
     TFB_CHECK(miss == 0, "a row with a non-zero diagonal update has no structural diagonal");
     return 0;
 }

@@ -60,6 +60,9 @@ struct tfb_ctx {
     cudaEvent_t ev_up[TFB_MAX_CHUNKS] = {}, ev_k[TFB_MAX_CHUNKS] = {};
     int chunk0 = -1, chunkn = 0;
     tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
+    // value buffers of destroyed matrices, kept for the next tfb_mat_create: a Newton loop makes one Jacobian per
+    // step and cudaMalloc/cudaFree of ~1 GB next to a 60 GB Krylov basis cost up to 0.6 s per call (measured)
+    std::vector<double*> vals_pool;
     // multi-GPU
     int nranks = 1, rank = 0;
     int slab_k0[TFB_MAX_RANKS + 1] = {};   // first plane of every rank's slab (after tfb_comm_init)
@@ -73,6 +76,7 @@ struct tfb_mat {
     uint64_t version = 0;       // bumped whenever values change (invalidates the preconditioner)
 };
 
+uint64_t tfb_next_version();
 int tfb_build_pattern(tfb_ctx* ctx);
 int tfb_spmv_structured(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
                         int prow, unsigned rowmask, unsigned colmask, const double* rowscale);
