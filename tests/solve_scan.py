@@ -13,9 +13,16 @@ for k in range(2):
     x = x + it.solve(jac, -f)
 jac, f = it.jacobian_rhs(x)
 ref = it.solve(jac, -f)
-variants = [{}, {'Restart': 100}, {'Restart': 60}, {'Restart': 40}, {'Basis Precision': 'single'},
-            {'Basis Precision': 'single', 'Restart': 80}, {'Velocity Iterations': 2}, {'Velocity Iterations': 2, 'Restart': 60},
-            {'Method': 'BiCGStab'}]
+variants = [{}, {'Preconditioner Precision': 'tf32'}, {'Preconditioner Precision': 'single'},
+            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 2},
+            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 3},
+            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 4},
+            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 6},
+            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 4, 'Basis Precision': 'single'},
+            {'Velocity Iterations': 4}]
+if len(sys.argv) > 2:
+    variants = eval(sys.argv[2])
+p['Verbose'] = True
 for v in variants:
     p['Iterative Solver'] = v
     t0 = time.perf_counter()

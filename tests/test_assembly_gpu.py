@@ -139,6 +139,11 @@ def test_matvec_matches_scipy():
     want = jac.tocsr() @ v
     got = jac @ v
     assert numpy.allclose(got, want, rtol=1e-13, atol=1e-13 * numpy.abs(want).max())
+    # complex vectors (JaDa's operators, JaDa.py:24-34): real and imaginary parts separately
+    vc = v + 1j * make_state(3, it.n)
+    wantc = jac.tocsr() @ vc
+    gotc = jac @ vc
+    assert numpy.iscomplexobj(gotc) and numpy.allclose(gotc, wantc, rtol=1e-13, atol=1e-13 * numpy.abs(wantc).max())
 
 
 def test_unsupported_configurations_fail_loudly():

@@ -109,6 +109,24 @@ def test_bordered_solve():
     assert numpy.linalg.norm(r1) <= 1e-8 * numpy.linalg.norm(b) and abs(r2) < 1e-8
 
 
+def test_complex_right_hand_side_is_solved_by_parts():
+    '''SciPy.Interface._lu_solve (SciPy.py:194-202): a complex rhs with the real Jacobian -> real and imaginary solves.'''
+    it = _iface({'Reynolds Number': 50}, 6, 6, 6)
+    x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
+    jac = it.jacobian(x)
+    rng = numpy.random.default_rng(2)
+    b = rng.uniform(-1, 1, it.n) + 1j * rng.uniform(-1, 1, it.n)
+    b[3] = 0
+    y = it.solve(jac, b)
+    assert numpy.iscomplexobj(y) and it.last_solve['converged']
+    J = jac.tocsr().tolil()
+    J[3, :] = 0
+    J[:, 3] = 0
+    J[3, 3] = -1
+    assert numpy.linalg.norm(J.tocsr() @ y - b) <= 1e-8 * numpy.linalg.norm(b)
+    assert numpy.array_equal(y.real, it.solve(jac, b.real.copy()))
+
+
 def test_time_integration_operators():
     """TimeIntegration._newton (TimeIntegration.py:40-73) builds `jacobian(x) - mass / (theta*dt)` and
     `mass @ v` with the backend's matrix types and hands the result to solve()."""

@@ -24,6 +24,7 @@ struct TfbAsmArgs {
     double* rhs;
     int k0, nzl;
     int kc0;                  // first z-chunk handled by this launch (pipelined host path)
+    int kstep;                // planes per z-chunk of this launch (<= KCH; the host pipeline uses half chunks)
 };
 
 template <class Cfg>
@@ -260,7 +261,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
     const int tid = (jl * DOF + d1) * 32 + il;
     const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
-    const int kbeg = (blockIdx.z + a.kc0) * KCH, kend = min(kbeg + KCH, a.nzl);   // local planes
+    const int kbeg = (blockIdx.z + a.kc0) * a.kstep, kend = min(kbeg + a.kstep, a.nzl);   // local planes
     const int kofs = 1 - a.k0;
     const long long plane = (long long)g.nx * g.ny * DOF;
 

@@ -268,6 +268,7 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     a.k0 = c->desc.k0;
     a.nzl = c->nzl;
     a.kc0 = 0;
+    a.kstep = 1;
     constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
     size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
     auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ, MINB>;
@@ -298,7 +299,8 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     a.rhs = c->d_rhs;
     a.k0 = c->desc.k0;
     a.nzl = c->nzl;
-    const int nchunks = (c->nzl + KCH - 1) / KCH;
+    a.kstep = (c->chunk0 >= 0 && c->chunk_planes > 0) ? std::min(c->chunk_planes, KCH) : KCH;
+    const int nchunks = (c->nzl + a.kstep - 1) / a.kstep;
     a.kc0 = c->chunk0 >= 0 ? c->chunk0 : 0;
     const int nlaunch = c->chunk0 >= 0 ? std::min(c->chunkn, nchunks - a.kc0) : nchunks;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
@@ -421,7 +423,10 @@ static int dispatch_assemble(tfb_ctx* c, tfb_mat* m, int do_j, int do_f) { retur
 // of F(x) are pipelined over z-chunks on three streams (PCIe is full duplex), so the call costs
 // about max(H2D, D2H) instead of H2D + kernel + D2H.
 static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, double* rhs_out) {
-    const int nch = (c->nzl + TFB_KCH - 1) / TFB_KCH;
+    // pipeline granularity: half a marching chunk.  Finer pieces shorten the fill (first kernel waits for one
+    // piece) and the drain (last download) of the pipeline; the kernel time is hidden behind PCIe either way.
+    const int PCH = TFB_KCH / 2;
+    const int nch = (c->nzl + PCH - 1) / PCH;
     if (!c->s_h2d) {
         TFB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         TFB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
@@ -434,19 +439,22 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
     TFB_CUDA(cudaEventRecord(c->ev_k[TFB_MAX_CHUNKS - 1], c->stream));
     TFB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[TFB_MAX_CHUNKS - 1], 0));
     const size_t pr = (size_t)c->plane_rows;
+    // upload pieces are shifted by one plane: piece ch ends with the first plane of chunk ch+1, which is the
+    // only plane of the next chunk the kernel of chunk ch reads
     for (int ch = 0; ch < nch; ch++) {
-        const int p0 = ch * TFB_KCH, p1 = std::min(p0 + TFB_KCH, c->nzl);
-        TFB_CUDA(cudaMemcpyAsync(c->d_state + pr * (p0 + 1), state + pr * p0, sizeof(double) * pr * (p1 - p0),
-                                 cudaMemcpyHostToDevice, c->s_h2d));
+        const int u0 = ch == 0 ? 0 : ch * PCH + 1, u1 = std::min((ch + 1) * PCH + 1, c->nzl);
+        if (u1 > u0)
+            TFB_CUDA(cudaMemcpyAsync(c->d_state + pr * (u0 + 1), state + pr * u0, sizeof(double) * pr * (u1 - u0),
+                                     cudaMemcpyHostToDevice, c->s_h2d));
         TFB_CUDA(cudaEventRecord(c->ev_up[ch], c->s_h2d));
     }
     m->version = tfb_next_version();
     for (int ch = 0; ch < nch; ch++) {
-        const int p0 = ch * TFB_KCH, p1 = std::min(p0 + TFB_KCH, c->nzl);
-        TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[std::min(ch + 1, nch - 1)], 0));   // needs the first plane of the next chunk
-        c->chunk0 = ch; c->chunkn = 1;
+        const int p0 = ch * PCH, p1 = std::min(p0 + PCH, c->nzl);
+        TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[ch], 0));
+        c->chunk0 = ch; c->chunkn = 1; c->chunk_planes = PCH;
         int rc = dispatch_assemble(c, m, 1, rhs_out != nullptr);
-        c->chunk0 = -1;
+        c->chunk0 = -1; c->chunk_planes = 0;
         if (rc) return rc;
         if (rhs_out) {
             TFB_CUDA(cudaEventRecord(c->ev_k[ch], c->stream));
@@ -464,8 +472,8 @@ extern "C" int tfb_jacobian(tfb_ctx* c, const double* state, tfb_mat* m, double*
     TFB_CHECK(c && state && m && m->ctx == c, "bad arguments");
     TFB_CHECK(c->have_params, "tfb_set_params has not been called");
     TFB_CUDA(cudaSetDevice(c->desc.device));
-    const int nch = (c->nzl + TFB_KCH - 1) / TFB_KCH;
-    if (c->nranks == 1 && c->desc.nz > 1 && c->desc.dim == 3 && nch >= 2 && nch < TFB_MAX_CHUNKS && !getenv("TFB_NO_PIPELINE"))
+    const int nch = (c->nzl + TFB_KCH / 2 - 1) / (TFB_KCH / 2);
+    if (c->nranks == 1 && c->desc.nz > 1 && c->desc.dim == 3 && nch >= 2 && nch < TFB_MAX_CHUNKS - 1 && !getenv("TFB_NO_PIPELINE"))
         return jacobian_pipelined(c, state, m, rhs_out);
     int rc = tfb_state_upload(c, state);
     if (rc) return rc;

@@ -58,7 +58,7 @@ struct tfb_ctx {
     // pipelined host path of tfb_jacobian: copy streams, per-chunk events, z-chunk window of a launch
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[TFB_MAX_CHUNKS] = {}, ev_k[TFB_MAX_CHUNKS] = {};
-    int chunk0 = -1, chunkn = 0;
+    int chunk0 = -1, chunkn = 0, chunk_planes = 0;
     tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
     // value buffers of destroyed matrices, kept for the next tfb_mat_create: a Newton loop makes one Jacobian per
     // step and cudaMalloc/cudaFree of ~1 GB next to a 60 GB Krylov basis cost up to 0.6 s per call (measured)

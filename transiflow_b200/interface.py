@@ -96,9 +96,12 @@ class DeviceMatrix:
         return self.tocsr().tocsc()
 
     def __matmul__(self, x):
-        x = as_f64(x)
-        if x.ndim != 1 or numpy.iscomplexobj(x):
+        if numpy.iscomplexobj(x) and numpy.ndim(x) == 1:
+            x = numpy.asarray(x)
+            return (self @ numpy.ascontiguousarray(x.real)) + 1j * (self @ numpy.ascontiguousarray(x.imag))
+        if numpy.ndim(x) != 1:
             return self.tocsr() @ x
+        x = as_f64(x)
         y = numpy.empty_like(x)
         check(_lib.lib().tfb_spmv(self._h, ptr(x), ptr(y)))
         return y
@@ -352,6 +355,19 @@ class Interface:
         return self._solve1(jac, rhs)
 
     def _solve1(self, jac, rhs):
+        if numpy.iscomplexobj(rhs):
+            # real matrix, complex right-hand side (eigen-solver glue): the real and imaginary parts are
+            # solved separately, exactly what SciPy.Interface._lu_solve does (SciPy.py:194-202)
+            rhs = numpy.asarray(rhs)
+            y = numpy.empty(rhs.shape, dtype=numpy.complex128)
+            y.real = self._solve1(jac, numpy.ascontiguousarray(rhs.real))
+            first = self.last_solve
+            y.imag = self._solve1(jac, numpy.ascontiguousarray(rhs.imag))
+            self.last_solve = dict(self.last_solve, iterations=first['iterations'] + self.last_solve['iterations'],
+                                   converged=first['converged'] and self.last_solve['converged'],
+                                   relres=max(first['relres'], self.last_solve['relres']),
+                                   solve_ms=first['solve_ms'] + self.last_solve['solve_ms'])
+            return y
         self._sync_solver()
         b = as_f64(rhs).copy()
         prow = -1
