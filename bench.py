@@ -339,8 +339,11 @@ def main():
                   'krylov_iterations': [h['iterations'] for h in timed], 'relres': [h['relres'] for h in timed],
                   'fnorm_before': [h['fnorm'] for h in timed], 'all_converged': all(h['converged'] for h in hist),
                   'tolerance': 1e-10, 'unknowns': it.n,
+                  'krylov_method': it.last_solve.get('method'),
                   'solver': ('FGMRES + LSC block preconditioner, coupled (w,T) line solve + inner GMRES on the (u,T) block'
-                             if args.problem == 'rb' else 'FGMRES + LSC block preconditioner (FDM sub-solves)') + ', host vectors in/out'
+                             if args.problem == 'rb' else
+                             ('IDR(8)' if it.last_solve.get('method') == 'IDR' else 'FGMRES')
+                             + ' + LSC block preconditioner (FDM sub-solves)') + ', host vectors in/out'
                             + ('; z-slabs: NCCL halo exchange, all-reduce, all-to-all transposes' if world > 1 else '')}
         # the same linear system with the opt-in mixed-precision storage (fp32 Krylov basis and fp32 FDM
         # sub-solves; all reductions, the operator and the convergence test on the true residual stay fp64)

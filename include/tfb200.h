@@ -118,7 +118,8 @@ typedef struct {
     int32_t pressure_row;
     int32_t precond;        /* TFB_PREC_* */
     int32_t verbose;
-    int32_t reserved[3];    /* reserved[0] = 1: fp32 storage of the GMRES basis (arithmetic fp64); reserved[1] = 1: BiCGStab;
+    int32_t reserved[3];    /* reserved[0] = 1: fp32 storage of the GMRES basis (arithmetic fp64); reserved[1] = 1: BiCGStab,
+                       2 | (s << 8): IDR(s) (s = 0 -> 8; fixed preconditioner only);
                        reserved[2] bit 0: FDM sub-solves of the preconditioner in fp32; bit 1: do not use the coupled
                        (w, scalar) solve even if tfb_joint_set was called; bit 2 (with bit 0): TF32 tensor-core math for those
                        fp32 transforms; bits 8..15: inner GMRES steps of the

@@ -13,13 +13,7 @@ for k in range(2):
     x = x + it.solve(jac, -f)
 jac, f = it.jacobian_rhs(x)
 ref = it.solve(jac, -f)
-variants = [{}, {'Preconditioner Precision': 'tf32'}, {'Preconditioner Precision': 'single'},
-            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 2},
-            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 3},
-            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 4},
-            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 6},
-            {'Preconditioner Precision': 'tf32', 'Velocity Iterations': 4, 'Basis Precision': 'single'},
-            {'Velocity Iterations': 4}]
+variants = [{'Method': 'FGMRES'}, {}, {'Method': 'IDR', 'IDR Dimension': 4}]
 if len(sys.argv) > 2:
     variants = eval(sys.argv[2])
 p['Verbose'] = True

@@ -157,6 +157,8 @@ class Interface:
     '''B200 backend.  Constructor arguments as ``transiflow.interface.SciPy.Interface``
     (SciPy.py:25-26) plus ``device``.'''
 
+    AUTO_IDR_MIN_UNKNOWNS = 500000   # 'Method': 'auto' picks IDR(8) from this many unknowns on (3-D grids)
+
     def __init__(self, parameters, nx, ny, nz=1, dim=None, dof=None,
                  x=None, y=None, z=None, boundary_conditions=None, device=0, slab=None):
         if boundary_conditions is not None:
@@ -389,7 +391,11 @@ class Interface:
         # 'Basis Precision': 'single' stores the Krylov basis in fp32 (compressed-basis GMRES, all
         # arithmetic fp64, cycles restart from the true residual); default fp64
         o.reserved[0] = int(its.get('Basis Precision', 'double') == 'single')
-        o.reserved[1] = int(str(its.get('Method', 'FGMRES')).lower() == 'bicgstab')
+        # 'Method': 'FGMRES' | 'IDR' | 'BiCGStab'.  Default ('auto'): IDR(8) for large true 3-D grids with a fixed
+        # preconditioner (the orthogonalisation against an un-restarted basis is 45 % of an FGMRES solve at 128^3),
+        # FGMRES otherwise and as the fallback whenever IDR does not reach the tolerance
+        method = str(its.get('Method', 'auto')).lower()
+        o.reserved[1] = int(method == 'bicgstab')
         # 'Scalar Coupling': 'joint' (default where available: 3-D Rayleigh-Benard) solves w and T together and
         # iterates on the (velocity, temperature) block; 'none' is the block-triangular preconditioner
         joint = getattr(self, '_joint', False) and str(its.get('Scalar Coupling', 'joint')).lower() != 'none'
@@ -399,12 +405,32 @@ class Interface:
         pprec = str(its.get('Preconditioner Precision', 'double')).lower()
         o.reserved[2] = (1 if pprec in ('single', 'tf32') else 0) | (4 if pprec == 'tf32' else 0) \
             | (0 if joint else 2) | (min(24, max(0, inner)) << 8)
+        auto = method == 'auto'
+        if auto:
+            big3d = self.dim == 3 and self.nz > 1 and self.n >= self.AUTO_IDR_MIN_UNKNOWNS   # global size: same choice on every rank
+            method = 'idr' if (big3d and inner == 0 and 'Basis Precision' not in its and pprec == 'double') else 'fgmres'
+        if method.startswith('idr'):
+            # IDR(s): short recurrences instead of a Krylov basis; needs a fixed preconditioner, so the variants with
+            # inner iterations keep FGMRES
+            if inner > 0:
+                raise ValueError("'Method': 'IDR' cannot be combined with inner iterations ('Velocity Iterations', "
+                                 "coupled scalar solve); use FGMRES or 'Scalar Coupling': 'none'")
+            o.reserved[1] = 2 | (max(1, min(16, int(its.get('IDR Dimension', 8)))) << 8)
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
-        self.last_solve = {'iterations': info.iters, 'relres': info.relres, 'converged': rc == 0,
-                           'setup_ms': info.setup_ms, 'solve_ms': info.solve_ms}
-        self._debug_print('FGMRES: %d iterations, relres %.3e' % (info.iters, info.relres))
+        spent_its, spent_ms = 0, 0.0
+        if rc != 0 and auto and method == 'idr':
+            # IDR stagnated or broke down: the un-restarted FGMRES is the robust path
+            self._debug_print('IDR: relres %.3e after %d products, falling back to FGMRES' % (info.relres, info.iters))
+            spent_its, spent_ms = info.iters, info.solve_ms
+            method, o.reserved[1] = 'fgmres', 0
+            y = numpy.zeros(self.n_local)
+            rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
+        self.last_solve = {'iterations': info.iters + spent_its, 'relres': info.relres, 'converged': rc == 0,
+                           'setup_ms': info.setup_ms, 'solve_ms': info.solve_ms + spent_ms,
+                           'method': 'IDR' if method.startswith('idr') else ('BiCGStab' if method == 'bicgstab' else 'FGMRES')}
+        self._debug_print('%s: %d iterations, relres %.3e' % (self.last_solve['method'], info.iters, info.relres))
         return y
 
     def _bordered_solve(self, jac, rhs, rhs2, V, W, C):
