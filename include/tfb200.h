@@ -122,7 +122,8 @@ typedef struct {
                        2 | (s << 8): IDR(s) (s = 0 -> 8; fixed preconditioner only);
                        reserved[2] bit 0: FDM sub-solves of the preconditioner in fp32; bit 1: do not use the coupled
                        (w, scalar) solve even if tfb_joint_set was called; bit 2 (with bit 0): TF32 tensor-core math for those
-                       fp32 transforms; bits 8..15: inner GMRES steps of the
+                       fp32 transforms; bit 3: scaled-mass Schur complement instead of the
+                       least-squares commutator; bits 8..15: inner GMRES steps of the
                        velocity / (velocity, scalar) sub-solve */
 } tfb_solve_opts;
 typedef struct {

@@ -5,7 +5,9 @@ sys.path.insert(0, '.')
 import transiflow_b200 as tb
 
 g = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-p = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100, 'Lid Velocity': 1}
+p = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': float(__import__('os').environ.get('RE', 100)), 'Lid Velocity': 1}
+if __import__('os').environ.get('STRETCH'):
+    p['Grid Stretching Factor'] = 1.5
 it = tb.Interface(p, g, g, g)
 x = it.vector()
 for k in range(2):
@@ -13,7 +15,7 @@ for k in range(2):
     x = x + it.solve(jac, -f)
 jac, f = it.jacobian_rhs(x)
 ref = it.solve(jac, -f)
-variants = [{'Method': 'FGMRES'}, {}, {'Method': 'IDR', 'IDR Dimension': 4}]
+variants = [{}, {'Schur Complement': 'Scaled Mass'}, {'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'}]
 if len(sys.argv) > 2:
     variants = eval(sys.argv[2])
 p['Verbose'] = True

@@ -212,9 +212,12 @@ def test_implicit_euler_matches_reference_time_integration():
 @pytest.mark.parametrize('options', [{'Method': 'BiCGStab'}, {'Basis Precision': 'single', 'Restart': 40},
                                      {'Preconditioner Precision': 'single'}, {'Preconditioner Precision': 'tf32'},
                                      {'Preconditioner Precision': 'single', 'Basis Precision': 'single'},
-                                     {'Velocity Iterations': 3}])
+                                     {'Velocity Iterations': 3}, {'Method': 'IDR'}, {'Method': 'IDR', 'IDR Dimension': 4},
+                                     {'Method': 'FGMRES'}, {'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'},
+                                     {'Schur Complement': 'Scaled Mass', 'Method': 'IDR'}])
 def test_alternative_krylov_options_reach_the_same_solution(options):
-    """BiCGStab and the fp32-stored GMRES basis must deliver the same 1e-10 true residual / SuperLU parity."""
+    """Every Krylov method / storage / preconditioner option must deliver the same 1e-10 true residual and the
+    SuperLU parity of the default."""
     name = 'ldc3d_12_str'
     params, nx, ny, nz = NEWTON_CASES[name]
     g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
@@ -225,6 +228,24 @@ def test_alternative_krylov_options_reach_the_same_solution(options):
     jac = it.jacobian(g['x'])
     y = it.solve(jac, g['b'])
     assert it.last_solve['converged'], it.last_solve
+    assert numpy.abs(y - g['y']).max() <= 1e-8 * numpy.abs(g['y']).max()
+    if 'Method' in options:
+        assert it.last_solve['method'].lower() == options['Method'].lower()
+
+
+def test_automatic_method_uses_idr_on_large_grids():
+    """'Method': 'auto' -> IDR(8) from AUTO_IDR_MIN_UNKNOWNS unknowns on 3-D grids, FGMRES below."""
+    from transiflow_b200 import Interface
+    name = 'ldc3d_12_str'
+    params, nx, ny, nz = NEWTON_CASES[name]
+    g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
+    it = Interface(dict(params), nx, ny, nz)
+    jac = it.jacobian(g['x'])
+    it.solve(jac, g['b'])
+    assert it.last_solve['method'] == 'FGMRES'            # small grid
+    it.AUTO_IDR_MIN_UNKNOWNS = 1000
+    y = it.solve(jac, g['b'])
+    assert it.last_solve['method'] == 'IDR' and it.last_solve['converged']
     assert numpy.abs(y - g['y']).max() <= 1e-8 * numpy.abs(g['y']).max()
 
 

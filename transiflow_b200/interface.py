@@ -405,6 +405,13 @@ class Interface:
         pprec = str(its.get('Preconditioner Precision', 'double')).lower()
         o.reserved[2] = (1 if pprec in ('single', 'tf32') else 0) | (4 if pprec == 'tf32' else 0) \
             | (0 if joint else 2) | (min(24, max(0, inner)) << 8)
+        # 'Schur Complement': 'LSC' (least-squares commutator, two Poisson solves and a product with the velocity block)
+        # or 'Scaled Mass' (dp = gamma r_p / cell volume, gamma estimated per matrix from the velocity block's spectrum)
+        schur = str(its.get('Schur Complement', 'LSC')).lower()
+        if schur not in ('lsc', 'scaled mass'):
+            raise ValueError("'Schur Complement' must be 'LSC' or 'Scaled Mass'")
+        if schur == 'scaled mass':
+            o.reserved[2] |= 8
         auto = method == 'auto'
         if auto:
             big3d = self.dim == 3 and self.nz > 1 and self.n >= self.AUTO_IDR_MIN_UNKNOWNS   # global size: same choice on every rank
