@@ -357,12 +357,15 @@ def main():
                                                'relres': it.last_solve['relres'],
                                                'converged': bool(it.last_solve['converged']),
                                                'default_newton_step_ms': max_over_ranks(hist[-1]['ms'])}
-            it.parameters['Iterative Solver'] = dict(saved or {}, **{'Preconditioner Precision': 'tf32'})
-            it.solve(jac, -f)
-            newton['tf32_preconditioner_solve'] = {'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
-                                                   'iterations': it.last_solve['iterations'],
-                                                   'relres': it.last_solve['relres'],
-                                                   'converged': bool(it.last_solve['converged'])}
+            if args.problem != 'rb':
+                # (not for Rayleigh-Benard: TF32 transforms inside the inner GMRES of the coupled (u, T) block stall the
+                # outer iteration at ~1e-4 -- measured 128^3: 1000 iterations, not converged -- so the option is not offered there)
+                it.parameters['Iterative Solver'] = dict(saved or {}, **{'Preconditioner Precision': 'tf32'})
+                it.solve(jac, -f)
+                newton['tf32_preconditioner_solve'] = {'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
+                                                       'iterations': it.last_solve['iterations'],
+                                                       'relres': it.last_solve['relres'],
+                                                       'converged': bool(it.last_solve['converged'])}
             if saved is None:
                 it.parameters.pop('Iterative Solver')
             else:

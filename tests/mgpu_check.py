@@ -68,7 +68,8 @@ def main():
             jac, f = it.jacobian_rhs(x[r0:r1].copy())
             want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
             for opts in ({'Preconditioner Precision': 'single'}, {'Method': 'BiCGStab'}, {'Velocity Iterations': 3},
-                         {'Basis Precision': 'single'}):
+                         {'Basis Precision': 'single'}, {'Method': 'IDR'}, {'Method': 'IDR', 'IDR Dimension': 4},
+                         {'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'}):
                 it.parameters['Iterative Solver'] = dict(opts)
                 dx = it.solve(jac, -f)
                 err = numpy.abs(dx - want[r0:r1]).max() / numpy.abs(want).max()

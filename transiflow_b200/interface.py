@@ -403,6 +403,10 @@ class Interface:
         # 'Preconditioner Precision': 'single' runs the FDM sub-solves in fp32, 'tf32' additionally lets their dense
         # transforms use the tensor cores in TF32 (FGMRES is flexible: the outer iteration and the tolerance stay fp64)
         pprec = str(its.get('Preconditioner Precision', 'double')).lower()
+        if pprec == 'tf32' and joint:
+            # measured at 128^3 Rayleigh-Benard: the outer iteration stalls at ~1e-4 (1000 iterations, not converged)
+            raise ValueError("'Preconditioner Precision': 'tf32' is not available with the coupled (w, T) solve; "
+                             "use 'single' or 'Scalar Coupling': 'none'")
         o.reserved[2] = (1 if pprec in ('single', 'tf32') else 0) | (4 if pprec == 'tf32' else 0) \
             | (0 if joint else 2) | (min(24, max(0, inner)) << 8)
         # 'Schur Complement': 'LSC' (least-squares commutator, two Poisson solves and a product with the velocity block)
