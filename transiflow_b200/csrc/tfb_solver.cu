@@ -1713,6 +1713,51 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
     double relres = 1.0, prev_true = 1e300;
     std::vector<double> M((size_t)S * S), f(S), cf(S), d(S), al(S);
     auto Mx = [&](int i, int j) -> double& { return M[(size_t)i * S + j]; };
+    // One application of the fixed preconditioner is ~45 short launches (30 of them cuBLAS calls whose host side costs
+    // about as much as the 20 us kernel they start) between two host synchronisations of the recurrence: on one GPU,
+    // with no inner iteration, it has no host dependence, so the second application with the same (in, out) pair is
+    // captured into a CUDA graph and replayed for the rest of the solve.  The first one runs eagerly (cuBLAS workspace,
+    // lazy module loads).  Slot 0: v -> vh, slot 1: r -> vh.  TFB_NO_GRAPH=1 keeps the eager path.
+    static int graphs_allowed = -1;
+    if (graphs_allowed < 0) { const char* e = getenv("TFB_NO_GRAPH"); graphs_allowed = !(e && e[0] == '1'); }
+    bool use_graph = graphs_allowed && c->nranks == 1 && s->inner_its <= 0 && !s->joint_on;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int64_t gnodes[2] = {0, 0};
+    int gseen[2] = {0, 0};
+    auto precond = [&](const double* in, double* out, int slot) -> int {
+        if (!use_graph) return apply_precond(c, m, prow, in, out);
+        if (gexec[slot]) {
+            TFB_CUDA(cudaGraphLaunch(gexec[slot], c->stream));
+            g_tfb_launches += gnodes[slot];
+            return 0;
+        }
+        if (gseen[slot]++ == 0) return apply_precond(c, m, prow, in, out);
+        const int64_t before = g_tfb_launches;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            use_graph = false;
+            return apply_precond(c, m, prow, in, out);
+        }
+        const int rc = apply_precond(c, m, prow, in, out);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc == 0 && e == cudaSuccess && g) e = cudaGraphInstantiate(&gexec[slot], g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (rc != 0 || e != cudaSuccess || !gexec[slot]) {     // not capturable here: eager for the rest of the solve
+            cudaGetLastError();
+            gexec[slot] = nullptr;
+            use_graph = false;
+            g_tfb_launches = before;
+            return apply_precond(c, m, prow, in, out);
+        }
+        gnodes[slot] = g_tfb_launches - before;
+        TFB_CUDA(cudaGraphLaunch(gexec[slot], c->stream));
+        return 0;
+    };
+    struct GraphGuard {
+        cudaGraphExec_t* g;
+        ~GraphGuard() { for (int i = 0; i < 2; i++) if (g[i]) cudaGraphExecDestroy(g[i]); }
+    } graph_guard{gexec};
     while (its < o->maxit && !converged) {
         // (re)start from the true residual
         if (its == 0) TFB_CUDA(cudaMemcpyAsync(r, d_b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
@@ -1747,7 +1792,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
                 // v = r - sum_{i>=k} c_i G_i
                 if (put(d_coef, cf.data() + k, S - k)) return -1;
                 if (multi_axpy<double>(c, G + (size_t)k * n, S - k, d_coef, -1.0, v, nullptr, r, 1.0, 0.0)) return -1;
-                if (apply_precond(c, m, prow, v, vh)) return -1;
+                if (precond(v, vh, 0)) return -1;
                 // U_k = om * vh + sum_{i>=k} c_i U_i   (the old U_k is part of the sum)
                 double* Uk = U + (size_t)k * n;
                 double* Gk = G + (size_t)k * n;
@@ -1788,7 +1833,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
             }
             if (done || breakdown || its >= o->maxit) break;
             // dimension-reduction step: r <- (I - om A Minv) r
-            if (apply_precond(c, m, prow, r, vh)) return -1;
+            if (precond(r, vh, 1)) return -1;
             if (spmv(c, m, vh, t, prow)) return -1;
             its++;
             double pr2[2], rn2 = 0.0;
