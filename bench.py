@@ -343,7 +343,9 @@ def main():
                   'solver': ('FGMRES + LSC block preconditioner, coupled (w,T) line solve + inner GMRES on the (u,T) block'
                              if args.problem == 'rb' else
                              ('IDR(8)' if it.last_solve.get('method') == 'IDR' else 'FGMRES')
-                             + ' + LSC block preconditioner (FDM sub-solves)') + ', host vectors in/out'
+                             + (' + block preconditioner (FDM velocity solves, scaled-mass Schur complement)'
+                                if it.last_solve.get('schur') == 'Scaled Mass' else ' + LSC block preconditioner (FDM sub-solves)'))
+                            + ', host vectors in/out'
                             + ('; z-slabs: NCCL halo exchange, all-reduce, all-to-all transposes' if world > 1 else '')}
         # the same linear system with the opt-in mixed-precision storage (fp32 Krylov basis and fp32 FDM
         # sub-solves; all reductions, the operator and the convergence test on the true residual stay fp64)

@@ -242,11 +242,29 @@ def test_automatic_method_uses_idr_on_large_grids():
     it = Interface(dict(params), nx, ny, nz)
     jac = it.jacobian(g['x'])
     it.solve(jac, g['b'])
-    assert it.last_solve['method'] == 'FGMRES'            # small grid
+    assert it.last_solve['method'] == 'FGMRES' and it.last_solve['schur'] == 'LSC'          # small grid
     it.AUTO_IDR_MIN_UNKNOWNS = 1000
     y = it.solve(jac, g['b'])
-    assert it.last_solve['method'] == 'IDR' and it.last_solve['converged']
+    assert it.last_solve['method'] == 'IDR' and it.last_solve['schur'] == 'Scaled Mass' and it.last_solve['converged']
     assert numpy.abs(y - g['y']).max() <= 1e-8 * numpy.abs(g['y']).max()
+
+
+@pytest.mark.parametrize('name,params', [('ldc3d_20_re100', {'Reynolds Number': 100}),
+                                         ('ldc3d_16_re400_str', {'Reynolds Number': 400, 'Grid Stretching Factor': 1.5})])
+def test_newton_with_the_large_grid_defaults_reaches_the_spsolve_state(name, params):
+    """The solver configuration that 'auto' selects on large 3-D grids (IDR(8), scaled-mass Schur complement, CUDA-graph
+    replay of the preconditioner), forced onto grids where SuperLU is still feasible: Newton from zero converges in the
+    same number of steps to the state of the spsolve path (tests/golden/make_golden_newton_oracle.py) within 1e-8."""
+    from transiflow_b200 import Interface
+    g = numpy.load(os.path.join(GEN, 'newton_oracle_' + name + '.npz'))
+    N = int(g['N'])
+    it = Interface(dict(params), N, N, N)
+    it.AUTO_IDR_MIN_UNKNOWNS = 1000
+    x, k = newton(it, it.vector(), tol=1e-12, maxit=12)
+    assert it.last_solve['method'] == 'IDR' and it.last_solve['schur'] == 'Scaled Mass'
+    assert k == int(g['steps'])
+    assert numpy.linalg.norm(it.rhs(x)) < 1e-12
+    assert numpy.abs(x - g['x']).max() <= 1e-8 * numpy.abs(g['x']).max()
 
 
 @pytest.mark.parametrize('case', [
