@@ -432,6 +432,10 @@ class Interface:
             if inner > 0:
                 raise ValueError("'Method': 'IDR' cannot be combined with inner iterations ('Velocity Iterations', "
                                  "coupled scalar solve); use FGMRES or 'Scalar Coupling': 'none'")
+            if pprec == 'tf32':
+                # measured at 128^3: TF32 transforms perturb the preconditioner beyond what the short recurrences tolerate
+                # (diverges); fp32 sub-solves ('single') are fine with IDR
+                raise ValueError("'Method': 'IDR' cannot be combined with 'Preconditioner Precision': 'tf32'; use 'single' or FGMRES")
             o.reserved[1] = 2 | (max(1, min(16, int(its.get('IDR Dimension', 8)))) << 8)
         info = _lib.TfbSolveInfo()
         y = numpy.zeros(self.n_local)
