@@ -96,3 +96,45 @@ def pinned_array(n):
     buf = (ctypes.c_double * n).from_address(p.value)
     arr = numpy.frombuffer(buf, dtype=numpy.float64)
     return arr
+
+
+class _PinnedBlock:
+    """One page-locked buffer lent out as the base object of a numpy array; when the last array (or view) referring to it
+    is collected the buffer goes back to its pool -- never earlier, so a returned vector is not aliased by a later one."""
+
+    def __init__(self, pool, address, n):
+        self._pool, self._address = pool, address
+        self.__array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (address, False), 'version': 3}
+
+    def __del__(self):
+        pool = self._pool
+        if pool is not None:
+            pool._free.append(self._address)
+
+
+class PinnedPool:
+    """Recycled page-locked result vectors of one length (the device-to-host copy of a result into fresh pageable memory
+    costs 8 ms of staging + page faults per 67 MB vector at 128^3, against 1.3 ms into a pinned buffer).  At most `limit`
+    buffers are kept; beyond that, and if the allocation fails, `empty()` returns an ordinary numpy array."""
+
+    def __init__(self, n, limit=6):
+        self.n, self.limit = n, limit
+        self._free, self._owned = [], []
+
+    def empty(self):
+        if not self._free and len(self._owned) < self.limit:
+            p = ctypes.c_void_p()
+            if lib().tfb_pinned_alloc(ctypes.c_size_t(8 * max(self.n, 1)), ctypes.byref(p)) == 0 and p.value:
+                self._owned.append(p.value)
+                self._free.append(p.value)
+        if not self._free:
+            return numpy.empty(self.n)
+        return numpy.asarray(_PinnedBlock(self, self._free.pop(), self.n))
+
+    def close(self):
+        """Frees the buffers that are not lent out; lent ones are released with the process."""
+        if _LIB is not None:
+            for a in self._free:
+                _LIB.tfb_pinned_free(ctypes.c_void_p(a))
+                self._owned.remove(a)
+        self._free = []

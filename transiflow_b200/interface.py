@@ -212,11 +212,19 @@ class Interface:
         self._pattern = None
         self._param_key = None
         self.last_solve = None
+        # result vectors of rhs / jacobian_rhs / solve come from recycled page-locked buffers on large grids
+        self._pool = _lib.PinnedPool(self.n_local) if self.n_local >= (1 << 20) else None
 
     def __del__(self):
         ctx, self._ctx = getattr(self, '_ctx', None), None
+        pool, self._pool = getattr(self, '_pool', None), None
+        if pool is not None:
+            pool.close()
         if ctx and _lib._LIB is not None:
             _lib._LIB.tfb_destroy(ctx)
+
+    def _result_vector(self):
+        return self._pool.empty() if self._pool is not None else numpy.empty(self.n_local)
 
     # ---- parameters (BaseInterface.py:84-104; Discretization.py:145-184) ----
     def _debug_print(self, *args):
@@ -296,7 +304,7 @@ class Interface:
         '''F(x); replaces Discretization.rhs (Discretization.py:367-390).'''
         self._sync_params()
         state = as_f64(state)
-        out = numpy.empty(self.n_local)
+        out = self._result_vector()
         check(_lib.lib().tfb_rhs(self._ctx, ptr(state), ptr(out)))
         return out
 
@@ -313,7 +321,7 @@ class Interface:
         self._sync_params()
         state = as_f64(state)
         mat = DeviceMatrix(self)
-        out = numpy.empty(self.n_local)
+        out = self._result_vector()
         check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
         return mat, out
 
@@ -371,12 +379,25 @@ class Interface:
                                    solve_ms=first['solve_ms'] + self.last_solve['solve_ms'])
             return y
         self._sync_solver()
-        b = as_f64(rhs).copy()
-        prow = -1
+        b = as_f64(rhs)
+        prow, pin_local, pin_saved = -1, -1, 0.0
         if self.dof > self.dim:
             prow = self.pressure_row            # global row; lives on the slab that owns cell 0
             if self.row0 <= prow < self.row0 + self.n_local:
-                b[prow - self.row0] = 0
+                # rhs[dim] = 0 (SciPy.py:216) without a copy of the vector: the caller's entry is put back after the solve
+                pin_local = prow - self.row0
+                if b is rhs and not b.flags.writeable:
+                    b = b.copy()
+                pin_saved = float(b[pin_local])
+        try:
+            if pin_local >= 0:
+                b[pin_local] = 0
+            return self._solve_pinned(jac, b, prow)
+        finally:
+            if pin_local >= 0:
+                b[pin_local] = pin_saved
+
+    def _solve_pinned(self, jac, b, prow):
         its = self.parameters.get('Iterative Solver', {})
         o = _lib.TfbSolveOpts()
         o.tol = its.get('Convergence Tolerance', 1e-10)
@@ -438,7 +459,7 @@ class Interface:
                 raise ValueError("'Method': 'IDR' cannot be combined with 'Preconditioner Precision': 'tf32'; use 'single' or FGMRES")
             o.reserved[1] = 2 | (max(1, min(16, int(its.get('IDR Dimension', 8)))) << 8)
         info = _lib.TfbSolveInfo()
-        y = numpy.zeros(self.n_local)
+        y = self._result_vector()          # tfb_solve writes every entry (the solvers start from x = 0 on the device)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
         spent_its, spent_ms = 0, 0.0
         if rc != 0 and auto and method == 'idr':
@@ -449,7 +470,6 @@ class Interface:
             if auto_schur:
                 schur = 'lsc'
                 o.reserved[2] &= ~8
-            y = numpy.zeros(self.n_local)
             rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
         self.last_solve = {'iterations': info.iters + spent_its, 'relres': info.relres, 'converged': rc == 0,
                            'setup_ms': info.setup_ms, 'solve_ms': info.solve_ms + spent_ms,
