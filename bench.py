@@ -107,6 +107,36 @@ def cpu_port_cells_per_s(grid, planes, repeats=1):
     return grid * grid * planes / best, lib().tfo_num_threads(), best
 
 
+def python_reference_sample(n=16):
+    '''The UNMODIFIED Python reference (SciPy backend, pip-installed under baseline/_ref) on a small instance of the
+    same problem, on this box's host: Interface.rhs + Interface.jacobian (single-threaded Python) and Interface.solve
+    (SuperLU).  About 10 s; None when the package is not there.'''
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'transiflow')):
+        return None
+    sys.path.insert(0, ref)
+    try:
+        from transiflow import Interface as RefInterface
+        params = {k: v for k, v in PARAMS.items() if k != 'Iterative Solver'}
+        it = RefInterface(dict(params), n, n, n)
+        x = numpy.random.default_rng(0).uniform(-0.1, 0.1, n * n * n * 4)
+        t0 = time.perf_counter()
+        f = it.rhs(x)
+        t1 = time.perf_counter()
+        jac = it.jacobian(x)
+        t2 = time.perf_counter()
+        it.solve(jac, -f)
+        t3 = time.perf_counter()
+        return {'grid': [n, n, n], 'rhs_s': t1 - t0, 'jacobian_s': t2 - t1, 'solve_s': t3 - t2,
+                'assembly_cells_per_s': n ** 3 / (t2 - t0), 'newton_steps_per_s': 1.0 / (t3 - t0), 'cores': 1,
+                'note': 'unmodified reference, SciPy backend (Python assembly on one core, SuperLU solve); its cost per cell is '
+                        'size-independent for the assembly, the direct solve is infeasible beyond ~64^3'}
+    except Exception as e:     # noqa: BLE001
+        return {'error': str(e)}
+    finally:
+        sys.path.remove(ref)
+
+
 def parity_gate(device, flat):
     '''Correctness gate reported with every perf number: a small instance of the same
     problem against the CPU oracle -- pattern after compress, CSR values, RHS, Newton update.'''
@@ -158,6 +188,9 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    pyref = python_reference_sample()
+    if pyref is not None:
+        out['cpu_baseline']['python_reference'] = pyref
     print(json.dumps(out), flush=True)
 
 
@@ -414,6 +447,9 @@ def main():
         v, cores, dt = cpu_port_cells_per_s(grid, planes, repeats=2)
         line['cpu_baseline'] = {'value': v, 'unit': 'cells/s', 'cores': cores, 'kind': 'port',
                                 'sample': '%dx%dx%d slab of the workload, Jacobian+RHS, oracle C port with OpenMP' % (grid, grid, planes)}
+        pyref = python_reference_sample()
+        if pyref is not None:
+            line['cpu_baseline']['python_reference'] = pyref
     print(json.dumps(line), flush=True)
 
 
