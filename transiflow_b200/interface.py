@@ -347,7 +347,7 @@ class Interface:
     # ---- linear solve (SciPy.py:204-315) ----
     def solve(self, jac, rhs, rhs2=None, V=None, W=None, C=None):
         '''Solve ``J y = rhs`` (pressure pinned at row ``dim`` when dof > dim, SciPy.py:212-216)
-        with the preconditioned FGMRES on the device.  With a border (``rhs2, V, W, C``) the
+        with the preconditioned Krylov solver on the device (IDR(s) / FGMRES / BiCGStab, see ``_solve_pinned``).  With a border (``rhs2, V, W, C``) the
         bordered system is reduced to two solves with J and a 1x1 Schur complement.'''
         if not isinstance(jac, DeviceMatrix):
             # host matrices built from ours (TimeIntegration's J - M/(theta dt), real shifts):
