@@ -69,7 +69,8 @@ def main():
             want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
             for opts in ({'Preconditioner Precision': 'single'}, {'Method': 'BiCGStab'}, {'Velocity Iterations': 3},
                          {'Basis Precision': 'single'}, {'Method': 'IDR'}, {'Method': 'IDR', 'IDR Dimension': 4},
-                         {'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'}):
+                         {'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'},
+                         {'Schur Complement': 'Scaled Mass', 'Method': 'IDR'}):     # what 'auto' selects on large grids
                 it.parameters['Iterative Solver'] = dict(opts)
                 dx = it.solve(jac, -f)
                 err = numpy.abs(dx - want[r0:r1]).max() / numpy.abs(want).max()
