@@ -67,3 +67,59 @@ def test_allocation_failure_falls_back_to_numpy(monkeypatch):
     pool = _lib.PinnedPool(64)
     a = pool.empty()
     assert a.shape == (64,) and a.base is None
+
+
+def _bare_interface(n=12, dim=3, dof=4, row0=0):
+    from transiflow_b200.interface import Interface
+    it = Interface.__new__(Interface)          # no device: only the host logic around the solver call is exercised
+    it.dim, it.dof, it.pressure_row, it.row0, it.n_local, it.n = dim, dof, dim, row0, n, n
+    it._ctx = None
+    it._pool = None
+    it._sync_solver = lambda: None
+    return it
+
+
+def test_pressure_pin_is_applied_in_place_and_undone():
+    """rhs[dim] = 0 for the solve (SciPy.py:216) without copying the vector; the caller's array is unchanged afterwards,
+    also when the solver raises, and a read-only array is never written."""
+    it = _bare_interface()
+    seen = {}
+
+    def fake(jac, b, prow):
+        seen['b'], seen['prow'], seen['same'] = b.copy(), prow, b
+        return b * 2
+
+    it._solve_pinned = fake
+    rhs = numpy.arange(1.0, 13.0)
+    y = it._solve1(None, rhs)
+    assert seen['prow'] == 3 and seen['b'][3] == 0.0 and seen['same'] is rhs
+    assert numpy.array_equal(rhs, numpy.arange(1.0, 13.0))          # restored
+    assert y[3] == 0.0 and y[4] == 10.0
+
+    def boom(jac, b, prow):
+        raise RuntimeError('x')
+
+    it._solve_pinned = boom
+    try:
+        it._solve1(None, rhs)
+    except RuntimeError:
+        pass
+    assert numpy.array_equal(rhs, numpy.arange(1.0, 13.0))
+
+    it._solve_pinned = fake
+    ro = numpy.arange(1.0, 13.0)
+    ro.flags.writeable = False
+    it._solve1(None, ro)
+    assert seen['same'] is not ro and seen['b'][3] == 0.0 and ro[3] == 4.0
+
+    # the slab that does not own the pinned row passes the vector through untouched
+    it2 = _bare_interface(row0=48)
+    it2._solve_pinned = fake
+    it2._solve1(None, rhs)
+    assert seen['prow'] == 3 and numpy.array_equal(seen['b'], rhs) and seen['same'] is rhs
+
+    # no pressure unknown (dof == dim): nothing is pinned
+    it3 = _bare_interface(dim=3, dof=3)
+    it3._solve_pinned = fake
+    it3._solve1(None, rhs)
+    assert seen['prow'] == -1 and numpy.array_equal(seen['b'], rhs)
