@@ -110,21 +110,27 @@ int tfb_spmv(tfb_mat* mat, const double* x, double* y);
 int tfb_spmv_bench(tfb_mat* mat, int reps, int masked, float* ms_out);
 
 /* Interface.solve (interface/SciPy.py:204-315): solve mat * x = b with the pressure pinned at
- * local row `pressure_row` (<0: no pin) by preconditioned FGMRES to ||r||/||b|| <= tol.
+ * global row `pressure_row` (<0: no pin) by a preconditioned Krylov method to ||r||/||b|| <= tol.
  * Returns 0 converged, 1 not converged (x holds the best iterate). */
+enum { TFB_METHOD_FGMRES = 0, TFB_METHOD_BICGSTAB = 1, TFB_METHOD_IDR = 2 };
+/* tfb_solve_opts.precond_flags */
+#define TFB_PREC_FP32 1         /* FDM sub-solves of the preconditioner in fp32 (SIMT transforms) */
+#define TFB_PREC_NO_JOINT 2     /* do not use the coupled (w, scalar) solve even if tfb_joint_set was called */
+#define TFB_PREC_SCALED_MASS 8  /* scaled-mass Schur complement instead of the least-squares commutator */
+#define TFB_PREC_TENSOR 16      /* x/y transforms of the FDM solves on the tensor cores (tcgen05, 3xTF32 split, fp32
+                                   storage) and Thomas sweeps along z; needs tfb_fdm_set_pencil for the z axis */
 typedef struct {
     double tol;
     int32_t maxit, restart;
     int32_t pressure_row;
-    int32_t precond;        /* TFB_PREC_* */
+    int32_t precond;         /* reserved, 0 */
     int32_t verbose;
-    int32_t reserved[3];    /* reserved[0] = 1: fp32 storage of the GMRES basis (arithmetic fp64); reserved[1] = 1: BiCGStab,
-                       2 | (s << 8): IDR(s) (s = 0 -> 8; fixed preconditioner only);
-                       reserved[2] bit 0: FDM sub-solves of the preconditioner in fp32; bit 1: do not use the coupled
-                       (w, scalar) solve even if tfb_joint_set was called; bit 2 (with bit 0): TF32 tensor-core math for those
-                       fp32 transforms; bit 3: scaled-mass Schur complement instead of the
-                       least-squares commutator; bits 8..15: inner GMRES steps of the
-                       velocity / (velocity, scalar) sub-solve */
+    int32_t basis_fp32;      /* 1: fp32 storage of the GMRES basis (all arithmetic fp64) */
+    int32_t method;          /* TFB_METHOD_* */
+    int32_t idr_s;           /* dimension of the IDR(s) shadow space, 0 -> 8 (fixed preconditioner only) */
+    int32_t precond_flags;   /* TFB_PREC_* bits */
+    int32_t inner_its;       /* inner GMRES steps of the velocity / (velocity, scalar) sub-solve, 0..24 */
+    int32_t stall_cycles;    /* restart cycles without a 2x residual reduction before giving up, 0 -> 3 */
 } tfb_solve_opts;
 typedef struct {
     int32_t iters, converged;
@@ -139,6 +145,11 @@ int tfb_solve(tfb_mat* mat, const double* b, double* x, const tfb_solve_opts* op
  * (c_visc, c_T, c_S; -1 for the pressure Poisson operator D M^-1 G).  Computed by the host
  * (hostprep.fdm_operators) whenever grid or parameters change. */
 int tfb_fdm_set(tfb_ctx* ctx, int var, int axis, int m, const double* Q, const double* lam, double coef);
+/* The 1-D stencils behind those eigen-decompositions (hostprep._pencil_km): K = tridiag(lower, diag, upper), mass M
+ * diagonal, m entries each.  With them the tensor-core path (TFB_PREC_TENSOR) solves the z direction by Thomas sweeps
+ * per horizontal mode instead of two dense transforms. */
+int tfb_fdm_set_pencil(tfb_ctx* ctx, int var, int axis, int m, const double* lower, const double* diag,
+                       const double* upper, const double* mass);
 /* A scalar whose diffusion operator is singular (zero-flux on every wall) is pinned at `cell`
  * with diagonal `sign`, like the reference's "fix one salinity value" (Discretization.py:690-701). */
 int tfb_fdm_pin(tfb_ctx* ctx, int var, int64_t cell, double sign);
@@ -155,6 +166,8 @@ int tfb_joint_set(tfb_ctx* ctx, int wvar, int svar, int nz, const double* zops);
 int tfb_joint_apply(tfb_mat* mat, const double* r, double* z, double* table_out);
 /* z = P^-1 r with host vectors (diagnostics / tests of the preconditioner alone) */
 int tfb_precond_apply(tfb_mat* mat, const double* r, double* z, int pressure_row);
+/* the same with the preconditioner variant chosen by opts (precond_flags, inner_its, pressure_row) */
+int tfb_precond_apply_opts(tfb_mat* mat, const double* r, double* z, const tfb_solve_opts* opts);
 
 /* NCCL plumbing for z-slab runs (one process per GPU). */
 int tfb_nccl_unique_id(uint8_t id[128]);

@@ -29,8 +29,13 @@ class TfbSolveOpts(ctypes.Structure):
     _fields_ = [
         ('tol', ctypes.c_double), ('maxit', ctypes.c_int32), ('restart', ctypes.c_int32),
         ('pressure_row', ctypes.c_int32), ('precond', ctypes.c_int32), ('verbose', ctypes.c_int32),
-        ('reserved', ctypes.c_int32 * 3),
+        ('basis_fp32', ctypes.c_int32), ('method', ctypes.c_int32), ('idr_s', ctypes.c_int32),
+        ('precond_flags', ctypes.c_int32), ('inner_its', ctypes.c_int32), ('stall_cycles', ctypes.c_int32),
     ]
+
+
+METHOD_FGMRES, METHOD_BICGSTAB, METHOD_IDR = 0, 1, 2
+PREC_FP32, PREC_NO_JOINT, PREC_SCALED_MASS, PREC_TENSOR = 1, 2, 8, 16
 
 
 class TfbSolveInfo(ctypes.Structure):
@@ -45,7 +50,7 @@ EXPORTS = [
     'tfb_sizes', 'tfb_get_pattern', 'tfb_mat_create', 'tfb_mat_destroy', 'tfb_mat_get_values',
     'tfb_mat_set_values', 'tfb_mat_add_diag', 'tfb_rhs', 'tfb_jacobian', 'tfb_mass_diag', 'tfb_state_upload',
     'tfb_assemble_resident', 'tfb_rhs_download', 'tfb_sync', 'tfb_event_record', 'tfb_event_elapsed_ms',
-    'tfb_flush_l2', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_spmv_bench', 'tfb_solve', 'tfb_fdm_set', 'tfb_fdm_pin', 'tfb_joint_set', 'tfb_joint_apply', 'tfb_precond_apply', 'tfb_nccl_unique_id', 'tfb_comm_init',
+    'tfb_flush_l2', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_spmv_bench', 'tfb_solve', 'tfb_fdm_set', 'tfb_fdm_set_pencil', 'tfb_fdm_pin', 'tfb_joint_set', 'tfb_joint_apply', 'tfb_precond_apply', 'tfb_precond_apply_opts', 'tfb_nccl_unique_id', 'tfb_comm_init',
 ]
 
 

@@ -29,7 +29,11 @@ int tfb_alltoallv_bytes(tfb_ctx* c, const void* send, const long long* scount, c
                         const long long* rcount, const long long* rdispl, int elem_bytes);
 
 #include "tfb_joint.h"
+#include "tfb_fdm_tc.cuh"
 #define TFB_MAXVAR 6
+// tensor-core plane transforms (tfb_fdm_tc.cuh): K-chunk / pipeline depth of the kernel instantiation in use
+#define TFB_TC_KC 32
+#define TFB_TC_STAGES 3
 
 struct FdmVar {
     bool present = false;
@@ -42,6 +46,17 @@ struct FdmVar {
     double maxden = 0.0;
     long long pin_cell = -1;      // singular (all-Neumann) scalar operators are pinned at one cell
     double pin_sign = 1.0;        // diagonal of the pinned row (+1 identity, -1 for the AMOC salinity pin)
+    // tensor-core path (tfb_fdm_tc.cuh): pre-split, pre-swizzled copies of Q^T (forward) and Q (backward) for the
+    // x and y axes, the 1-D stencils (lower, diagonal, upper of K, then M; 4 x n doubles) of every axis, and the
+    // Thomas factors of the z direction for the current (eigenvalues, coefficient, shift)
+    float* tcA[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [axis][0 forward | 1 backward]
+    double* pencil[3] = {nullptr, nullptr, nullptr};
+    int pencil_n[3] = {0, 0, 0};
+    float* th_inv = nullptr;
+    float* th_cp = nullptr;
+    long long th_cap = 0;         // floats allocated per array
+    bool th_dirty = true;
+    double shift = 0.0;           // operator + shift * mass (time stepping, shifted eigenproblems)
 };
 
 // Compact copy of the entries of J with (row variable, column variable) in given masks: the
@@ -90,6 +105,9 @@ struct tfb_solver_state {
     long long a2a_cnt_pen[TFB_MAX_RANKS] = {}, a2a_dsp_pen[TFB_MAX_RANKS] = {};     // pencil side (planes of each rank)
     bool dist_ready = false;
     bool precond_single = false;  // apply the FDM sub-solves in fp32 (FGMRES keeps the outer iteration exact)
+    bool precond_tc = false;      // x/y transforms on the tensor cores (3xTF32), Thomas sweeps along z
+    float* tc32[2] = {nullptr, nullptr};   // fp32 SoA work arrays, TFB_MAXVAR x ncell (pencil-sized with z-slabs) each
+    long long tc32_cap = 0;
     // velocity sub-solve: inner GMRES on the convection-diffusion block, preconditioned by the FDM solve
     int inner_its = 0;            // 0: one FDM (diffusion-only) solve
     double inner_tol = 1e-2;
@@ -106,8 +124,12 @@ struct tfb_solver_state {
 
 void tfb_solver_free(tfb_solver_state* s) {
     if (!s) return;
-    for (auto& v : s->var)
-        for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); cudaFree(v.Qf[a]); cudaFree(v.lamf[a]); }
+    for (auto& v : s->var) {
+        for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); cudaFree(v.Qf[a]); cudaFree(v.lamf[a]); cudaFree(v.pencil[a]); }
+        for (int a = 0; a < 2; a++) { cudaFree(v.tcA[a][0]); cudaFree(v.tcA[a][1]); }
+        cudaFree(v.th_inv); cudaFree(v.th_cp);
+    }
+    for (auto& p : s->tc32) cudaFree(p);
     for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
     cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab);
     cudaFree(s->d_mass);
@@ -557,74 +579,10 @@ __global__ void k_pin_shift(long long n, FT* q, long long pc, const double* __re
 template <class FT>
 __global__ void k_copy1(const FT* src, double* dst) { *dst = (double)*src; }
 
-// ---- optional cuBLAS path for the FDM transforms (they are plain dense GEMMs) ----
-// libcublas is dlopen'ed; when it is absent the hand-written k_axis_gemm above is used.
-#include <dlfcn.h>
-typedef void* cublasHandle_t_;
-static struct {
-    int state;   // 0 untried, 1 ok, -1 unavailable
-    void* lib;
-    cublasHandle_t_ h;
-    int (*Create)(cublasHandle_t_*);
-    int (*SetStream)(cublasHandle_t_, cudaStream_t);
-    int (*SetMathMode)(cublasHandle_t_, int);
-    int (*DgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const double*, const double*, int, long long,
-                               const double*, int, long long, const double*, double*, int, long long, int);
-    int (*SgemmStridedBatched)(cublasHandle_t_, int, int, int, int, int, const float*, const float*, int, long long,
-                               const float*, int, long long, const float*, float*, int, long long, int);
-} g_blas;
-
-static bool blas_ready(tfb_ctx* c) {
-    if (g_blas.state == 0) {
-        g_blas.state = -1;
-        const char* off = getenv("TFB_NO_CUBLAS");
-        if (!(off && off[0] == '1')) {
-            const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
-            for (const char* nme : names) {
-                g_blas.lib = dlopen(nme, RTLD_NOW | RTLD_LOCAL);
-                if (g_blas.lib) break;
-            }
-            if (g_blas.lib) {
-                *(void**)(&g_blas.Create) = dlsym(g_blas.lib, "cublasCreate_v2");
-                *(void**)(&g_blas.SetStream) = dlsym(g_blas.lib, "cublasSetStream_v2");
-                *(void**)(&g_blas.SetMathMode) = dlsym(g_blas.lib, "cublasSetMathMode");
-                *(void**)(&g_blas.DgemmStridedBatched) = dlsym(g_blas.lib, "cublasDgemmStridedBatched");
-                *(void**)(&g_blas.SgemmStridedBatched) = dlsym(g_blas.lib, "cublasSgemmStridedBatched");
-                if (g_blas.Create && g_blas.SetStream && g_blas.DgemmStridedBatched && g_blas.SgemmStridedBatched &&
-                    g_blas.Create(&g_blas.h) == 0)
-                    g_blas.state = 1;
-            }
-        }
-    }
-    if (g_blas.state == 1) g_blas.SetStream(g_blas.h, c->stream);
-    return g_blas.state == 1;
-}
-
-static inline int blas_gemm(int ta, int tb, int m, int n, int k, const double* A, int lda, long long sa, const double* B,
-                            int ldb, long long sbb, double* C, int ldc, long long sc, int batches) {
-    const double one = 1.0, zero = 0.0;
-    return g_blas.DgemmStridedBatched(g_blas.h, ta, tb, m, n, k, &one, A, lda, sa, B, ldb, sbb, &zero, C, ldc, sc, batches);
-}
-static inline int blas_gemm(int ta, int tb, int m, int n, int k, const float* A, int lda, long long sa, const float* B,
-                            int ldb, long long sbb, float* C, int ldc, long long sc, int batches) {
-    const float one = 1.f, zero = 0.f;
-    return g_blas.SgemmStridedBatched(g_blas.h, ta, tb, m, n, k, &one, A, lda, sa, B, ldb, sbb, &zero, C, ldc, sc, batches);
-}
-
+// One dense transform along an axis (fp64 / fp32 SIMT path; the large 3-D solves use tfb_fdm_tc.cuh instead).
 template <class FT>
 static int axis_gemm(tfb_ctx* c, bool trans, const FT* A, FT* C, const FT* Q, int ldq, int M, int K, int N,
                      long long sm, long long sk, long long sb, int batches) {
-    if (blas_ready(c)) {
-        int rc;
-        enum { OP_N = 0, OP_T = 1 };
-        if (sk == 1)   // rows of A are the lines: C_cm(N x M) = op(Q_cm) * A_cm(K x M)
-            rc = blas_gemm(trans ? OP_T : OP_N, OP_N, N, M, K, Q, ldq, 0, A, (int)sm, sb, C, (int)sm, sb, batches);
-        else           // columns of A_cm are the lines' entries: C_cm(M x N) = A_cm(M x K) * op(Q_cm)
-            rc = blas_gemm(OP_N, trans ? OP_N : OP_T, M, N, K, A, (int)sk, sb, Q, ldq, 0, C, (int)sk, sb, batches);
-        TFB_LAUNCHED();
-        TFB_CHECK(rc == 0, "cublas gemmStridedBatched failed");
-        return 0;
-    }
     dim3 grid((M + 63) / 64, (N + 63) / 64, batches);
     if (trans) k_axis_gemm<true, FT><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
     else k_axis_gemm<false, FT><<<grid, 256, 0, c->stream>>>(A, C, Q, ldq, M, K, N, sm, sk, sb);
@@ -731,6 +689,172 @@ static int fdm_solve(tfb_ctx* c, int v, FT* in, FT* tmp, FT* out) {
         k_fdm_walls<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, k0, mx, my, mz, in, out);
         TFB_LAUNCHED();
     }
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// Tensor-core path of the FDM solves (tfb_fdm_tc.cuh): x/y transforms of whole planes as 3xTF32 tcgen05
+// contractions, the z direction as precomputed Thomas sweeps.  fp32 storage; used for preconditioning only.
+// ------------------------------------------------------------------------------------
+using TcGeo = tfbtc::Geo<TFB_TC_KC>;
+static int g_tc_grid_per_sm = 0;
+
+static bool tc_ready(const tfb_ctx* c, int v) {
+    const tfb_solver_state* s = c->solver;
+    const FdmVar& f = s->var[v];
+    return c->desc.dim == 3 && c->desc.nz > 1 && f.present && f.tcA[0][0] && f.tcA[1][0] && f.pencil[2] &&
+           f.pencil_n[2] == c->desc.nz;
+}
+
+static int tc_buffers(tfb_ctx* c) {
+    tfb_solver_state* s = c->solver;
+    long long need = c->n_local / c->desc.dof;
+    if (c->nranks > 1) {
+        const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
+        need = std::max(need, (long long)c->desc.nz * cyme * c->desc.nx);
+    }
+    if (need > s->tc32_cap) {
+        for (auto& p : s->tc32) { cudaFree(p); p = nullptr; }
+        for (auto& p : s->tc32) TFB_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)need * TFB_MAXVAR));
+        s->tc32_cap = need;
+    }
+    return 0;
+}
+
+// out[q] = Qy'(bvar[q]) * in[q] * Qx'(bvar[q])^T on every plane of the local slab (forward: transposed eigenvector
+// matrices, backward: the matrices)
+static int tc_planes(tfb_ctx* c, int nv, const int* bvar, float* const* in, float* const* out, bool backward) {
+    tfb_solver_state* s = c->solver;
+    const int nx = c->desc.nx, ny = c->desc.ny;
+    tfbtc::PlaneArgs a{};
+    TFB_CHECK(nv <= tfbtc::MAXQ, "too many arrays");
+    for (int q = 0; q < nv; q++) {
+        const FdmVar& f = s->var[bvar[q]];
+        a.in[q] = in[q]; a.out[q] = out[q];
+        a.A1[q] = f.tcA[0][backward ? 1 : 0];
+        a.A2[q] = f.tcA[1][backward ? 1 : 0];
+    }
+    a.narr = nv; a.nplanes = c->nzl; a.rows = ny; a.cols = nx; a.plane_stride = (long long)nx * ny;
+    a.k1pad = (nx + TFB_TC_KC - 1) / TFB_TC_KC * TFB_TC_KC;
+    a.k2pad = (ny + TFB_TC_KC - 1) / TFB_TC_KC * TFB_TC_KC;
+    a.n1 = (ny + 15) / 16 * 16; a.n2 = (nx + 15) / 16 * 16;
+    const long long items = (long long)nv * c->nzl;
+    const int grid = (int)std::min<long long>(items, 148ll * std::max(g_tc_grid_per_sm, 1));
+    tfbtc::tfb_fdm_plane_kernel<TFB_TC_KC, TFB_TC_STAGES><<<grid, tfbtc::THREADS, tfbtc::plane_kernel_smem<TFB_TC_KC, TFB_TC_STAGES>(), c->stream>>>(a);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Thomas factors of variable v for the current eigenvalues / coefficient / shift; modes = ex * ey columns
+static int tc_thomas_setup(tfb_ctx* c, int v) {
+    tfb_solver_state* s = c->solver;
+    FdmVar& f = s->var[v];
+    if (!f.th_dirty) return 0;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz;
+    const bool dist = c->nranks > 1;
+    const int ey = dist ? s->j0s[c->rank + 1] - s->j0s[c->rank] : ny, jofs = dist ? s->j0s[c->rank] : 0;
+    const long long modes = (long long)nx * ey, need = modes * nz;
+    if (need > f.th_cap) {
+        cudaFree(f.th_inv); cudaFree(f.th_cp);
+        f.th_inv = f.th_cp = nullptr;
+        TFB_CUDA(cudaMalloc(&f.th_inv, sizeof(float) * (size_t)need));
+        TFB_CUDA(cudaMalloc(&f.th_cp, sizeof(float) * (size_t)need));
+        f.th_cap = need;
+    }
+    tfbtc::ThomasVar t;
+    t.lx = f.lam[0]; t.ly = f.lam[1]; t.zk = f.pencil[2]; t.inv = f.th_inv; t.cp = f.th_cp;
+    t.coef = f.coef; t.shift = f.shift; t.mz = f.m[2]; t.mx = f.m[0]; t.my = f.m[1];
+    const double thresh = 1e-12 * fabs(f.coef) * f.maxden;
+    tfbtc::tfb_thomas_setup_kernel<<<(unsigned)((modes + 127) / 128), 128, 0, c->stream>>>(t, nx, ey, jofs, nz, thresh);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    f.th_dirty = false;
+    return 0;
+}
+
+// in-place tridiagonal solves along z of nv arrays laid out [k][modes]
+static int tc_thomas(tfb_ctx* c, int nv, const int* vars, float* const* x, long long modes) {
+    tfb_solver_state* s = c->solver;
+    tfbtc::ThomasArgs a{};
+    for (int q = 0; q < nv; q++) {
+        const FdmVar& f = s->var[vars[q]];
+        a.x[q] = x[q]; a.inv[q] = f.th_inv; a.cp[q] = f.th_cp; a.zk[q] = f.pencil[2]; a.coef[q] = f.coef; a.mz[q] = f.m[2];
+    }
+    a.narr = nv; a.nz = c->desc.nz; a.modes = modes;
+    dim3 grid((unsigned)((modes + 127) / 128), nv);
+    tfbtc::tfb_thomas_kernel<8><<<grid, 128, 0, c->stream>>>(a);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// a[q] <- Op_{vars[q]}^-1 a[q] for nv SoA fp32 arrays of the local slab; b[q] is scratch.  The x/y basis of
+// array q is that of variable bvar[q] (normally vars[q]).
+static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* a, float* const* b) {
+    tfb_solver_state* s = c->solver;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl;
+    for (int q = 0; q < nv; q++) {
+        TFB_CHECK(tc_ready(c, vars[q]), "tensor-core FDM data missing for a variable");
+        if (tc_thomas_setup(c, vars[q])) return -1;
+    }
+    if (tc_planes(c, nv, vars, a, b, false)) return -1;
+    if (c->nranks == 1) {
+        if (tc_thomas(c, nv, vars, b, (long long)nx * ny)) return -1;
+    } else {
+        // the z lines cross the slabs: transpose to pencils (all z, a chunk of y), sweep, transpose back
+        if (dist_setup(c)) return -1;
+        TfbChunks ch;
+        ch.n = c->nranks;
+        for (int r = 0; r <= c->nranks; r++) ch.j0[r] = s->j0s[r];
+        for (int r = 0; r < c->nranks; r++) ch.dsp[r] = s->a2a_dsp_slab[r];
+        const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
+        const long long ncell = (long long)nx * ny * nzl;
+        float *pen = (float*)s->pen[0], *sbuf = (float*)s->sbuf, *rbuf = (float*)s->rbuf;
+        for (int q = 0; q < nv; q++) {
+            k_a2a_pack<true, float><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, b[q], sbuf);
+            TFB_LAUNCHED();
+            if (tfb_alltoallv_bytes(c, sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, pen, s->a2a_cnt_pen, s->a2a_dsp_pen, 4)) return -1;
+            float* px[1] = {pen};
+            if (tc_thomas(c, 1, vars + q, px, (long long)nx * cyme)) return -1;
+            if (tfb_alltoallv_bytes(c, pen, s->a2a_cnt_pen, s->a2a_dsp_pen, rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, 4)) return -1;
+            k_a2a_pack<false, float><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, b[q], rbuf);
+            TFB_LAUNCHED();
+        }
+        (void)nz;
+    }
+    return tc_planes(c, nv, vars, b, a, true);
+}
+
+// z(rows of the velocity components) = FDM^-1 (r - sub) through the tensor-core path
+static int velocity_fdm_tc(tfb_ctx* c, const double* r, double* z, int skip, const double* sub) {
+    tfb_solver_state* s = c->solver;
+    const int dof = c->desc.dof, dim = c->desc.dim;
+    const long long ncell = c->n_local / dof;
+    if (tc_buffers(c)) return -1;
+    int vars[TFB_MAXVAR], nv = 0;
+    float *a[TFB_MAXVAR], *b[TFB_MAXVAR];
+    for (int v = 0; v < dim; v++) {
+        if (v == skip) continue;
+        a[nv] = s->tc32[0] + (size_t)nv * s->tc32_cap;
+        b[nv] = s->tc32[1] + (size_t)nv * s->tc32_cap;
+        vars[nv++] = v;
+    }
+    tfbtc::DeintArgs da{};
+    tfbtc::IntArgs ia{};
+    for (int q = 0; q < nv; q++) {
+        const FdmVar& f = s->var[vars[q]];
+        da.comp[q] = a[q]; da.var[q] = vars[q];
+        ia.comp[q] = a[q]; ia.var[q] = vars[q]; ia.mx[q] = f.m[0]; ia.my[q] = f.m[1]; ia.mz[q] = f.m[2];
+    }
+    da.nv = nv; da.dof = dof; da.ncell = ncell;
+    ia.nv = nv; ia.dof = dof; ia.nx = c->desc.nx; ia.ny = c->desc.ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
+    tfbtc::tfb_deint_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(da, r, sub);
+    TFB_LAUNCHED();
+    if (fdm_solve_tc(c, nv, vars, a, b)) return -1;
+    tfbtc::tfb_int_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(ia, r, sub, z);
+    TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -915,6 +1039,7 @@ __global__ void k_mask_copy(long long n, int dof, unsigned mask, const double* _
 template <class FT>
 static int velocity_fdm(tfb_ctx* c, const double* r, double* z, int skip = -1) {
     tfb_solver_state* s = c->solver;
+    if (s->precond_tc) return velocity_fdm_tc(c, r, z, skip, nullptr);
     const int dof = c->desc.dof, dim = c->desc.dim;
     const long long ncell = c->n_local / dof;
     FT *c0 = (FT*)s->comp[0], *c1 = (FT*)s->comp[1], *c2 = (FT*)s->comp[2];
@@ -1114,6 +1239,12 @@ static int apply_precond_t(tfb_ctx* c, tfb_mat* m, int prow, const double* r, do
                                                c->d_met[2], s->gamma, pin_local, r, z, ta);
         TFB_LAUNCHED();
         if (sub_spmv(c, s->subG, ta, tb)) return -1;                     // G dp
+        if (s->precond_tc && s->inner_its <= 0 && !joint && !smask) {
+            // tensor-core path: r - G dp is formed while the components are split off
+            if (velocity_fdm_tc(c, r, z, -1, tb)) return -1;
+            TFB_CUDA(cudaGetLastError());
+            return 0;
+        }
         k_axpy<<<vec_blocks(n), 256, 0, c->stream>>>(n, -1.0, tb, ru);
         TFB_LAUNCHED();
         if (velocity_solve<FT>(c, m, prow, ru, z)) return -1;
@@ -1189,9 +1320,57 @@ extern "C" int tfb_fdm_set(tfb_ctx* c, int var, int axis, int m, const double* Q
     }
     f.coef = coef;
     f.present = true;
+    f.th_dirty = true;
     double mx = 0.0;
     for (int i = 0; i < m; i++) mx = std::max(mx, fabs(lam[i]));
     f.maxden = std::max(f.maxden, 3.0 * mx);
+    // tensor-core copies of the x / y bases: Q^T (forward) and Q (backward), tf32 hi/lo split, swizzled K-chunks
+    const int nax = axis == 0 ? c->desc.nx : c->desc.ny;
+    if (axis < 2 && c->desc.dim == 3 && c->desc.nz > 1 && nax <= tfbtc::MROWS && m <= nax) {
+        const int kpad = (nax + TFB_TC_KC - 1) / TFB_TC_KC * TFB_TC_KC;
+        std::vector<double> qt((size_t)m * m);
+        for (int i = 0; i < m; i++)
+            for (int a = 0; a < m; a++) qt[(size_t)a * m + i] = Q[(size_t)i * m + a];
+        std::vector<float> fmt;
+        for (int dir = 0; dir < 2; dir++) {
+            tfbtc::tfb_tc_format_matrix<TFB_TC_KC>(dir == 0 ? qt.data() : Q, m, m, m, kpad, fmt);
+            cudaFree(f.tcA[axis][dir]);
+            f.tcA[axis][dir] = nullptr;
+            TFB_CUDA(cudaMalloc(&f.tcA[axis][dir], sizeof(float) * fmt.size()));
+            TFB_CUDA(cudaMemcpy(f.tcA[axis][dir], fmt.data(), sizeof(float) * fmt.size(), cudaMemcpyHostToDevice));
+        }
+        auto kern = tfbtc::tfb_fdm_plane_kernel<TFB_TC_KC, TFB_TC_STAGES>;
+        const int smem = (int)tfbtc::plane_kernel_smem<TFB_TC_KC, TFB_TC_STAGES>();
+        TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        int occ = 0;
+        TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, tfbtc::THREADS, smem));
+        g_tc_grid_per_sm = std::max(1, std::min(occ, 2));   // TMEM: 256 of 512 columns per CTA
+    }
+    return 0;
+}
+
+// The 1-D stencils behind the eigen-decompositions of tfb_fdm_set: K = tridiag(lower, diag, upper) and the diagonal
+// mass M of variable `var` along `axis` (hostprep._pencil_km), m entries each.  The tensor-core path solves the z
+// direction with them (Thomas sweeps per horizontal mode) instead of transforming along z.
+extern "C" int tfb_fdm_set_pencil(tfb_ctx* c, int var, int axis, int m, const double* lower, const double* diag,
+                                  const double* upper, const double* mass) {
+    TFB_CHECK(c && var >= 0 && var < TFB_MAXVAR && axis >= 0 && axis < 3 && m > 0 && lower && diag && upper && mass, "bad arguments");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    tfb_solver_state* s = solver_of(c);
+    FdmVar& f = s->var[var];
+    const int n = axis == 0 ? c->desc.nx : axis == 1 ? c->desc.ny : c->desc.nz;
+    TFB_CHECK(m <= n, "pencil longer than the grid");
+    if (f.pencil_n[axis] != n) {
+        cudaFree(f.pencil[axis]);
+        f.pencil[axis] = nullptr;
+        TFB_CUDA(cudaMalloc(&f.pencil[axis], sizeof(double) * 4 * n));
+        f.pencil_n[axis] = n;
+    }
+    std::vector<double> tab((size_t)4 * n, 0.0);
+    for (int i = 0; i < m; i++) { tab[i] = lower[i]; tab[n + i] = diag[i]; tab[2 * n + i] = upper[i]; tab[3 * n + i] = mass[i]; }
+    TFB_CUDA(cudaMemcpy(f.pencil[axis], tab.data(), sizeof(double) * 4 * n, cudaMemcpyHostToDevice));
+    f.th_dirty = true;
     return 0;
 }
 
@@ -1367,7 +1546,8 @@ static int fgmres_run(tfb_mat* m, const double* b, double* x, const tfb_solve_op
     std::vector<double> H((size_t)(mk + 1) * mk, 0.0), g(mk + 1), cs(mk), sn(mk), hcol(mk + 2), y(mk);
     auto Hx = [&](int i, int j) -> double& { return H[(size_t)j * (mk + 1) + i]; };
 
-    int total_its = 0, converged = 0, reorth = 0, cycles = 0;
+    int total_its = 0, converged = 0, reorth = 0, cycles = 0, stalled = 0;
+    const int stall_limit = o->stall_cycles > 0 ? o->stall_cycles : 3;
     const bool prof = o->verbose >= 1;
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); evs.push_back(e); } };
@@ -1401,8 +1581,9 @@ static int fgmres_run(tfb_mat* m, const double* b, double* x, const tfb_solve_op
         beta = sqrt(beta);
         relres = beta / bnorm;
         if (relres <= o->tol) { converged = 1; break; }
-        if (cycles > 0 && relres > 0.5 * prev_true) break;     // a whole cycle did not help: stagnation
-        prev_true = relres;
+        // stagnation: several restart cycles in a row without a 2x reduction of the true residual
+        if (cycles > 0 && relres > 0.5 * prev_true) { if (++stalled >= stall_limit) break; } else stalled = 0;
+        prev_true = std::min(prev_true, relres);
         cycles++;
         TFB_CUDA(cudaMemcpyAsync(s->d_scal + 4, &beta, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         k_store_scaled<BT><<<vec_blocks(n), 256, 0, c->stream>>>(n, s->d_scal, 4, w, V);
@@ -1556,7 +1737,8 @@ static int bicgstab_run(tfb_mat* m, const double* b, double* x, const tfb_solve_
     double bn2 = 0.0;
     if (dot(d_b, d_b, bn2)) return -1;
     const double bnorm = sqrt(bn2);
-    int its = 0, converged = 0;
+    int its = 0, converged = 0, stalled = 0;
+    const int stall_limit = o->stall_cycles > 0 ? o->stall_cycles : 3;
     double relres = 1.0;
     if (bnorm == 0.0) {
         memset(x, 0, sizeof(double) * n);
@@ -1576,8 +1758,8 @@ static int bicgstab_run(tfb_mat* m, const double* b, double* x, const tfb_solve_
         if (dot(r, r, rr)) return -1;
         relres = sqrt(rr) / bnorm;
         if (relres <= o->tol) { converged = 1; break; }
-        if (relres > 0.5 * prev_true && its > 0) break;
-        prev_true = relres;
+        if (relres > 0.5 * prev_true && its > 0) { if (++stalled >= stall_limit) break; } else stalled = 0;
+        prev_true = std::min(prev_true, relres);
         TFB_CUDA(cudaMemcpyAsync(rh, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
         TFB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * n, c->stream));
         TFB_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * n, c->stream));
@@ -1709,15 +1891,17 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
         if (info) { info->iters = 0; info->converged = 1; info->relres = 0.0; info->setup_ms = info->solve_ms = 0; }
         return 0;
     }
-    int its = 0, converged = 0, cycles = 0;
+    int its = 0, converged = 0, cycles = 0, stalled = 0;
+    // IDR is only ever the first attempt of 'auto' (FGMRES is the fallback), so it gives up after one stalled restart
+    // unless the caller asks for more
+    const int stall_limit = o->stall_cycles > 0 ? o->stall_cycles : 1;
     double relres = 1.0, prev_true = 1e300;
     std::vector<double> M((size_t)S * S), f(S), cf(S), d(S), al(S);
     auto Mx = [&](int i, int j) -> double& { return M[(size_t)i * S + j]; };
     // One application of the fixed preconditioner is ~45 short launches (30 of them cuBLAS calls whose host side costs
     // about as much as the 20 us kernel they start) between two host synchronisations of the recurrence: on one GPU,
     // with no inner iteration, it has no host dependence, so the second application with the same (in, out) pair is
-    // captured into a CUDA graph and replayed for the rest of the solve.  The first one runs eagerly (cuBLAS workspace,
-    // lazy module loads).  Slot 0: v -> vh, slot 1: r -> vh.  TFB_NO_GRAPH=1 keeps the eager path.
+    // captured into a CUDA graph and replayed for the rest of the solve.  The first one runs eagerly (lazy module loads).  Slot 0: v -> vh, slot 1: r -> vh.  TFB_NO_GRAPH=1 keeps the eager path.
     static int graphs_allowed = -1;
     if (graphs_allowed < 0) { const char* e = getenv("TFB_NO_GRAPH"); graphs_allowed = !(e && e[0] == '1'); }
     bool use_graph = graphs_allowed && c->nranks == 1 && s->inner_its <= 0 && !s->joint_on;
@@ -1770,8 +1954,9 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
         if (multi_dot<double>(c, r, 1, r, d_dot) || fetch(&rr, d_dot, 1)) return -1;
         relres = sqrt(rr) / bnorm;
         if (relres <= o->tol) { converged = 1; break; }
-        if (cycles > 0 && relres > 0.5 * prev_true) break;      // a whole restart did not help: stagnation
-        prev_true = relres;
+        // stagnation: several restarts in a row without a 2x reduction of the true residual
+        if (cycles > 0 && relres > 0.5 * prev_true) { if (++stalled >= stall_limit) break; } else stalled = 0;
+        prev_true = std::min(prev_true, relres);
         cycles++;
         TFB_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)2 * S * n, c->stream));   // G and U
         std::fill(M.begin(), M.end(), 0.0);
@@ -1878,27 +2063,46 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
     return relres <= o->tol * 1.0001 ? 0 : 1;
 }
 
+// solver state that follows from the options (shared by tfb_solve and the diagnostics)
+static int configure_precond(tfb_ctx* c, const tfb_solve_opts* o) {
+    tfb_solver_state* s = solver_of(c);
+    if (dist_setup(c)) return -1;
+    s->precond_single = (o->precond_flags & TFB_PREC_FP32) != 0;
+    s->inner_its = std::max(0, std::min(24, o->inner_its));   // d_scal slice holds 2k+3 <= 56 doubles
+    s->inner_total = 0;
+    s->joint_on = s->joint_ready && !(o->precond_flags & TFB_PREC_NO_JOINT);
+    s->schur_mass = (o->precond_flags & TFB_PREC_SCALED_MASS) != 0;
+    bool tc = (o->precond_flags & TFB_PREC_TENSOR) != 0;
+    for (int v = 0; tc && v < c->desc.dim; v++) tc = tc_ready(c, v);
+    s->precond_tc = tc;
+    if (const char* e = getenv("TFB_INNER_TOL")) s->inner_tol = atof(e);
+    return 0;
+}
+
 extern "C" int tfb_solve(tfb_mat* m, const double* b, double* x, const tfb_solve_opts* o, tfb_solve_info* info) {
     TFB_CHECK(m && b && x && o, "null argument");
     tfb_ctx* c = m->ctx;
     TFB_CUDA(cudaSetDevice(c->desc.device));
-    solver_of(c);
-    if (dist_setup(c)) return -1;
-    solver_of(m->ctx)->precond_single = (o->reserved[2] & 1) == 1;
-    solver_of(m->ctx)->inner_its = std::min(24, (o->reserved[2] >> 8) & 0xff);   // d_scal slice holds 2k+3 <= 56 doubles
-    solver_of(m->ctx)->inner_total = 0;
-    // reserved[2] bit 2: the fp32 FDM transforms may run on the tensor cores in TF32 (cuBLAS math mode); they are
-    // plain dense GEMMs and only ever feed the flexible preconditioner
-    if (blas_ready(m->ctx) && g_blas.SetMathMode)
-        g_blas.SetMathMode(g_blas.h, (o->reserved[2] & 5) == 5 ? 3 /* CUBLAS_TF32_TENSOR_OP_MATH */ : 0 /* CUBLAS_DEFAULT_MATH */);
-    // reserved[2] bit 1: 'Scalar Coupling': 'none' (block-triangular treatment of the scalars)
-    solver_of(m->ctx)->joint_on = solver_of(m->ctx)->joint_ready && !(o->reserved[2] & 2);
-    solver_of(m->ctx)->schur_mass = (o->reserved[2] & 8) != 0;   // bit 3: scaled-mass Schur complement instead of LSC
-    if (const char* e = getenv("TFB_INNER_TOL")) solver_of(m->ctx)->inner_tol = atof(e);
-    if (o->reserved[1] == 1) return bicgstab_run(m, b, x, o, info);
-    if (o->reserved[1] >= 2) return idr_run(m, b, x, o, info, o->reserved[1] >> 8 ? o->reserved[1] >> 8 : 8);
-    if (o->reserved[0] == 1) return fgmres_run<float>(m, b, x, o, info);
+    if (configure_precond(c, o)) return -1;
+    if (o->method == TFB_METHOD_BICGSTAB) return bicgstab_run(m, b, x, o, info);
+    if (o->method == TFB_METHOD_IDR) return idr_run(m, b, x, o, info, o->idr_s > 0 ? o->idr_s : 8);
+    if (o->basis_fp32 == 1) return fgmres_run<float>(m, b, x, o, info);
     return fgmres_run<double>(m, b, x, o, info);
+}
+
+extern "C" int tfb_precond_apply_opts(tfb_mat* m, const double* r, double* z, const tfb_solve_opts* o) {
+    TFB_CHECK(m && r && z && o, "null argument");
+    tfb_ctx* c = m->ctx;
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    if (ensure_buffers(c, 1)) return -1;     // the gamma estimate of the scaled-mass variant uses the dot-product slots
+    if (configure_precond(c, o)) return -1;
+    tfb_solver_state* s = c->solver;
+    TFB_CUDA(cudaMemcpyAsync(s->vec[4], r, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    if (sub_refresh(c, m, o->pressure_row)) return -1;
+    if (apply_precond(c, m, o->pressure_row, s->vec[4], s->vec[5])) return -1;
+    TFB_CUDA(cudaMemcpyAsync(z, s->vec[5], sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 // average device time of y = J x over `reps` launches (vectors and matrix resident; the operands

@@ -281,8 +281,9 @@ def joint_z_operators(cfg, prm, mets, nz):
     return numpy.ascontiguousarray(out)
 
 
-def fdm_operators(cfg, prm, mets, nx, ny, nz):
-    '''[(var, axis, m, Q, lam, coef)] for tfb_fdm_set.'''
+def fdm_operators(cfg, prm, mets, nx, ny, nz, pencils=None):
+    '''[(var, axis, m, Q, lam, coef)] for tfb_fdm_set.  If `pencils` is a list it receives
+    (var, axis, m, lower, diag, upper, mass) of the same 1-D stencils for tfb_fdm_set_pencil.'''
     folds = fold_coefficients(cfg, prm)
     n = (nx, ny, nz)
     ndir = 3 if (cfg.dim == 3 and nz > 1) else 2
@@ -298,9 +299,17 @@ def fdm_operators(cfg, prm, mets, nx, ny, nz):
             coef = prm.c_S
         for a in range(ndir):
             if v == cfg.p:
-                Q, lam = _pencil('cen', mets[a], n[a], 1.0, 1.0)
+                args = ('cen', mets[a], n[a], 1.0, 1.0)
             else:
                 kind = 'own' if (v < cfg.dim and a == v) else 'cen'
-                Q, lam = _pencil(kind, mets[a], n[a], folds.get((v, a, 0), 0.0), folds.get((v, a, 1), 0.0))
+                args = (kind, mets[a], n[a], folds.get((v, a, 0), 0.0), folds.get((v, a, 1), 0.0))
+            Q, lam = _pencil(*args)
             out.append((v, a, Q.shape[0], Q, lam, float(coef)))
+            if pencils is not None:
+                K, M = _pencil_km(*args)
+                m = K.shape[0]
+                lower, upper = numpy.zeros(m), numpy.zeros(m)
+                lower[1:] = numpy.diag(K, -1)
+                upper[:m - 1] = numpy.diag(K, 1)
+                pencils.append((v, a, m, lower, numpy.ascontiguousarray(numpy.diag(K)), upper, numpy.ascontiguousarray(M)))
     return out

@@ -269,8 +269,11 @@ class Interface:
             return
         if self.config.fold:
             raise NotImplementedError('solve() on semi-2D (dim=3, nz=1) grids')
-        for v, a, m, Q, lam, coef in hostprep.fdm_operators(self.config, self._prm, self._mets, self.nx, self.ny, self.nz):
+        pencils = []
+        for v, a, m, Q, lam, coef in hostprep.fdm_operators(self.config, self._prm, self._mets, self.nx, self.ny, self.nz, pencils):
             check(_lib.lib().tfb_fdm_set(self._ctx, v, a, m, ptr(Q), ptr(lam), ctypes.c_double(coef)))
+        for v, a, m, lower, diag, upper, mass in pencils:
+            check(_lib.lib().tfb_fdm_set_pencil(self._ctx, v, a, m, ptr(lower), ptr(diag), ptr(upper), ptr(mass)))
         if self.problem == recipes.AMOC:
             check(_lib.lib().tfb_fdm_pin(self._ctx, self.config.S, ctypes.c_int64(0), ctypes.c_double(-1.0)))
         # Rayleigh-Benard on a true 3-D grid: w and T are solved together along z (csrc/tfb_joint.h)
@@ -411,25 +414,26 @@ class Interface:
         o.verbose = int(bool(self.parameters.get('Verbose', False)))
         # 'Basis Precision': 'single' stores the Krylov basis in fp32 (compressed-basis GMRES, all
         # arithmetic fp64, cycles restart from the true residual); default fp64
-        o.reserved[0] = int(its.get('Basis Precision', 'double') == 'single')
+        o.basis_fp32 = int(its.get('Basis Precision', 'double') == 'single')
         # 'Method': 'FGMRES' | 'IDR' | 'BiCGStab'.  Default ('auto'): IDR(8) for large true 3-D grids with a fixed
         # preconditioner (the orthogonalisation against an un-restarted basis is 45 % of an FGMRES solve at 128^3),
         # FGMRES otherwise and as the fallback whenever IDR does not reach the tolerance
         method = str(its.get('Method', 'auto')).lower()
-        o.reserved[1] = int(method == 'bicgstab')
+        o.method = _lib.METHOD_BICGSTAB if method == 'bicgstab' else _lib.METHOD_FGMRES
+        o.stall_cycles = int(its.get('Stagnation Cycles', 0))
         # 'Scalar Coupling': 'joint' (default where available: 3-D Rayleigh-Benard) solves w and T together and
         # iterates on the (velocity, temperature) block; 'none' is the block-triangular preconditioner
         joint = getattr(self, '_joint', False) and str(its.get('Scalar Coupling', 'joint')).lower() != 'none'
         inner = int(its.get('Velocity Iterations', 8 if joint else 0))
-        # 'Preconditioner Precision': 'single' runs the FDM sub-solves in fp32, 'tf32' additionally lets their dense
-        # transforms use the tensor cores in TF32 (FGMRES is flexible: the outer iteration and the tolerance stay fp64)
-        pprec = str(its.get('Preconditioner Precision', 'double')).lower()
-        if pprec == 'tf32' and joint:
-            # measured at 128^3 Rayleigh-Benard: the outer iteration stalls at ~1e-4 (1000 iterations, not converged)
-            raise ValueError("'Preconditioner Precision': 'tf32' is not available with the coupled (w, T) solve; "
-                             "use 'single' or 'Scalar Coupling': 'none'")
-        o.reserved[2] = (1 if pprec in ('single', 'tf32') else 0) | (4 if pprec == 'tf32' else 0) \
-            | (0 if joint else 2) | (min(24, max(0, inner)) << 8)
+        # 'Preconditioner Precision': 'double' | 'single' (fp32 FDM sub-solves) | 'tf32x3' (x/y transforms of the FDM
+        # solves on the tensor cores with a 3xTF32 split -- fp32 accuracy -- and Thomas sweeps along z).  The
+        # preconditioner only steers the iteration: convergence is always decided on the true fp64 residual.
+        pprec = str(its.get('Preconditioner Precision', 'auto')).lower()
+        if pprec not in ('auto', 'double', 'single', 'tf32x3'):
+            raise ValueError("'Preconditioner Precision' must be 'double', 'single' or 'tf32x3'")
+        tensor_ok = self.dim == 3 and self.nz > 1 and self.nx <= 128 and self.ny <= 128
+        if pprec == 'tf32x3' and not tensor_ok:
+            raise ValueError("'Preconditioner Precision': 'tf32x3' needs a 3-D grid with nx, ny <= 128")
         # 'Schur Complement': 'LSC' (least-squares commutator, two Poisson solves and a product with the velocity block)
         # or 'Scaled Mass' (dp = gamma r_p / cell volume, gamma estimated per matrix from the velocity block's spectrum)
         # Default ('auto'): the scaled mass matrix wherever IDR is chosen automatically for a problem without scalars
@@ -441,23 +445,25 @@ class Interface:
         auto = method == 'auto'
         if auto:
             big3d = self.dim == 3 and self.nz > 1 and self.n >= self.AUTO_IDR_MIN_UNKNOWNS   # global size: same choice on every rank
-            method = 'idr' if (big3d and inner == 0 and 'Basis Precision' not in its and pprec == 'double') else 'fgmres'
+            method = 'idr' if (big3d and inner == 0 and 'Basis Precision' not in its and pprec in ('auto', 'double', 'tf32x3')) else 'fgmres'
         auto_schur = schur == 'auto'
         if auto_schur:
             schur = 'scaled mass' if (auto and method == 'idr' and self.dof == self.dim + 1) else 'lsc'
-        if schur == 'scaled mass':
-            o.reserved[2] |= 8
+        if pprec == 'auto':
+            # the tensor-core path where the automatic choice is IDR + scaled mass (large 3-D cavities), fp64 elsewhere
+            pprec = 'tf32x3' if (auto and method == 'idr' and schur == 'scaled mass' and tensor_ok) else 'double'
+        flags = (_lib.PREC_FP32 if pprec == 'single' else 0) | (_lib.PREC_TENSOR if pprec == 'tf32x3' else 0) \
+            | (0 if joint else _lib.PREC_NO_JOINT) | (_lib.PREC_SCALED_MASS if schur == 'scaled mass' else 0)
+        o.precond_flags = flags
+        o.inner_its = min(24, max(0, inner))
         if method.startswith('idr'):
             # IDR(s): short recurrences instead of a Krylov basis; needs a fixed preconditioner, so the variants with
             # inner iterations keep FGMRES
             if inner > 0:
                 raise ValueError("'Method': 'IDR' cannot be combined with inner iterations ('Velocity Iterations', "
                                  "coupled scalar solve); use FGMRES or 'Scalar Coupling': 'none'")
-            if pprec == 'tf32':
-                # measured at 128^3: TF32 transforms perturb the preconditioner beyond what the short recurrences tolerate
-                # (diverges); fp32 sub-solves ('single') are fine with IDR
-                raise ValueError("'Method': 'IDR' cannot be combined with 'Preconditioner Precision': 'tf32'; use 'single' or FGMRES")
-            o.reserved[1] = 2 | (max(1, min(16, int(its.get('IDR Dimension', 8)))) << 8)
+            o.method = _lib.METHOD_IDR
+            o.idr_s = max(1, min(16, int(its.get('IDR Dimension', 8))))
         info = _lib.TfbSolveInfo()
         y = self._result_vector()          # tfb_solve writes every entry (the solvers start from x = 0 on the device)
         rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
@@ -466,15 +472,20 @@ class Interface:
             # IDR stagnated or broke down: the un-restarted FGMRES is the robust path
             self._debug_print('IDR: relres %.3e after %d products, falling back to FGMRES' % (info.relres, info.iters))
             spent_its, spent_ms = info.iters, info.solve_ms
-            method, o.reserved[1] = 'fgmres', 0
+            method, o.method = 'fgmres', _lib.METHOD_FGMRES
             if auto_schur:
                 schur = 'lsc'
-                o.reserved[2] &= ~8
+                o.precond_flags &= ~_lib.PREC_SCALED_MASS
             rc = check(_lib.lib().tfb_solve(jac._h, ptr(b), ptr(y), ctypes.byref(o), ctypes.byref(info)))
         self.last_solve = {'iterations': info.iters + spent_its, 'relres': info.relres, 'converged': rc == 0,
                            'setup_ms': info.setup_ms, 'solve_ms': info.solve_ms + spent_ms,
                            'method': 'IDR' if method.startswith('idr') else ('BiCGStab' if method == 'bicgstab' else 'FGMRES'),
-                           'schur': 'Scaled Mass' if schur == 'scaled mass' else 'LSC'}
+                           'schur': 'Scaled Mass' if schur == 'scaled mass' else 'LSC', 'precond_precision': pprec}
+        if rc != 0:
+            # the reference's direct solve cannot fail silently; an unconverged Krylov solve must not either
+            import warnings
+            warnings.warn('B200 solve: %s stopped at relative residual %.3e after %d iterations (tolerance %.1e)'
+                          % (self.last_solve['method'], info.relres, self.last_solve['iterations'], o.tol), RuntimeWarning)
         self._debug_print('%s: %d iterations, relres %.3e' % (self.last_solve['method'], info.iters, info.relres))
         return y
 
