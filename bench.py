@@ -95,6 +95,8 @@ class ClockSampler:
 def cpu_port_cells_per_s(grid, planes, repeats=1):
     '''Jacobian+RHS with the oracle C port (all OpenMP threads) on a (grid x grid x planes) sample.'''
     from oracle.tf_oracle import Oracle, lib
+    # all host cores, set explicitly: launchers such as torch.distributed.run export OMP_NUM_THREADS=1
+    lib().tfo_set_num_threads(os.cpu_count() or 1)
     orc = Oracle(dict(PARAMS), grid, grid, planes)
     state = numpy.random.default_rng(0).uniform(-0.5, 0.5, orc.n)
     best = None
@@ -145,6 +147,9 @@ def parity_gate(device, flat):
     n = 12
     params = {k: v for k, v in PARAMS.items() if k != 'Iterative Solver'}
     it = Interface(dict(params), n, n, 1 if flat else n, device=device)
+    # the solver configuration 'auto' selects for the timed 128^3 Newton steps (IDR(8) + scaled-mass Schur complement +
+    # tensor-core FDM sub-solves + CUDA-graph replay), forced onto this small instance
+    it.AUTO_IDR_MIN_UNKNOWNS = 1000
     orc = Oracle(dict(params), it.nx, it.ny, it.nz)
     x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
     jac, f = it.jacobian_rhs(x)
@@ -159,9 +164,162 @@ def parity_gate(device, flat):
         dx = it.solve(jac, -f)
         want = direct_solve(orc.jacobian_csr(x), -fo, orc.dim, orc.dof)
         out['newton_update_max_rel_err_vs_spsolve'] = float(numpy.abs(dx - want).max() / numpy.abs(want).max())
+        out['newton_update_solver'] = '%s / %s / preconditioner %s, %d iterations, relres %.1e' % (
+            it.last_solve['method'], it.last_solve['schur'], it.last_solve['precond_precision'],
+            it.last_solve['iterations'], it.last_solve['relres'])
     except Exception as e:     # noqa: BLE001
         out['newton_update_error'] = str(e)
     return out
+
+
+def parity_gate_slabs(dist, rank, world, device):
+    '''The same gate for a z-slab run: every rank's owned CSR rows and RHS against the oracle (bit-identical) and the
+    distributed Newton update against the pinned SuperLU solve, on a ragged grid with >= 2 planes per rank.  Collective:
+    every rank calls it; the worst rank is reported.'''
+    import torch
+    from oracle.tf_oracle import Oracle, direct_solve
+    from transiflow_b200 import Interface, parallel
+    nx, ny, nz = 12, 10, 2 * world + 3
+    params = {k: v for k, v in PARAMS.items() if k != 'Iterative Solver'}
+    k0, k1 = parallel.slab_range(nz, world, rank)
+    it = Interface(dict(params), nx, ny, nz, device=device, slab=(k0, k1))
+    parallel.init_comm(it, dist, rank, world)
+    it.AUTO_IDR_MIN_UNKNOWNS = 1000
+    orc = Oracle(dict(params), nx, ny, nz)
+    r0, r1 = parallel.owned_rows(nx, ny, it.dof, k0, k1)
+    x = numpy.random.default_rng(0).uniform(-0.1, 0.1, orc.n)
+    jac, f = it.jacobian_rhs(x[r0:r1].copy())
+    row_ptr, col = it.pattern()
+    vals = jac.values()
+    keep = numpy.abs(vals) > 1e-14
+    csum = numpy.concatenate(([0], numpy.cumsum(keep, dtype=numpy.int64)))
+    coA, jcoA, begA = orc.jacobian(x)
+    e0, e1 = begA[r0], begA[r1]
+    exact = bool(numpy.array_equal(csum[row_ptr], begA[r0:r1 + 1] - e0) and numpy.array_equal(col[keep], jcoA[e0:e1])
+                 and numpy.array_equal(vals[keep], coA[e0:e1]) and numpy.array_equal(f, orc.rhs(x)[r0:r1]))
+    err, solver = float('inf'), ''
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            dx = it.solve(jac, -f)
+        want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
+        err = float(numpy.abs(dx - want[r0:r1]).max() / numpy.abs(want).max())
+        solver = '%s / %s / preconditioner %s, %d iterations' % (it.last_solve['method'], it.last_solve['schur'],
+                                                                 it.last_solve['precond_precision'], it.last_solve['iterations'])
+    except Exception as e:     # noqa: BLE001
+        solver = 'error: ' + str(e)
+    t = torch.tensor([0.0 if exact else 1.0, err if numpy.isfinite(err) else 1e300], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {'checked_on': '%dx%dx%d cavity on %d z-slabs vs CPU oracle (every rank, worst reported)' % (nx, ny, nz, world),
+            'owned_rows_and_rhs_bit_identical': bool(t[0] == 0.0),
+            'newton_update_max_rel_err_vs_spsolve': float(t[1]), 'newton_update_solver': solver}
+
+
+def solve_roofline(it, step, peak_gbs):
+    '''Algorithmic bytes of one operator product of the Krylov solve that was timed over the
+    measured time per product.  Components are listed so the figure can be recomputed.'''
+    n, nnz, dof, dim = it.n_local, it.nnz, it.dof, it.dim
+    ncell = n // dof
+    ms_per_product = step['solve_ms'] / max(1, step['iterations'])
+    comp = {'operator': 8 * nnz + 4 * (n + 1) + 16 * n}         # CSR values + row pointers + x read + y written
+    if step.get('method') == 'IDR':
+        s = 8
+        # vectors of 8n bytes moved per product by IDR(s) in the bi-orthogonal form, averaged over k = 0..s-1 and the
+        # omega step: v = r - G c (s-k+2), U_k (s-k+2), P^T G_k (s+1), bi-orthogonalisation of G_k, U_k (2(k+2)),
+        # r, x updates (6)
+        per_k = [(s - k + 2) + (s - k + 2) + (s + 1) + 2 * (k + 2) + 6 for k in range(s)]
+        comp['recurrence_vectors'] = 8 * n * (sum(per_k) + 12) // (s + 1)
+    else:
+        its = max(1, step['iterations'])
+        comp['orthogonalisation_vectors'] = 8 * n * (its + 6)       # mean basis size its/2, read twice, plus w, z
+    if step.get('precond') == 'tf32x3':
+        # r read, z written (fp64); fp32 planes of the `dim` velocity components: split off (w), x/y forward (r+w), Thomas
+        # (r+w + two factor arrays), x/y backward (r+w), merged (r); gradient product with the compact G (16 B per row)
+        comp['preconditioner'] = 16 * n + dim * ncell * 4 * 10 + 16 * dim * ncell
+    else:
+        comp['preconditioner'] = 16 * n + dim * ncell * 8 * 14       # six fp64 transforms (r+w) + scaling + (de)interleave
+    total = sum(comp.values())
+    achieved = total / (ms_per_product * 1e-3) / 1e9
+    return {'bound': 'hbm', 'unit': 'GB/s', 'achieved': achieved, 'peak': peak_gbs, 'frac': achieved / peak_gbs,
+            'ms_per_product': ms_per_product, 'products': step['iterations'], 'algorithmic_bytes_per_product': total,
+            'components': comp}
+
+
+def rb_strong_leg(args, dist, rank, world, local_rank, max_over_ranks):
+    '''BASELINE config 4: ONE Rayleigh-Benard grid^3 problem (dof 5, Ra = 1000) split over `world` z-slabs -- fused
+    assembly time, one Newton step from the perturbed conduction state, iterations.  Collective.'''
+    import ctypes
+    from transiflow_b200 import DeviceMatrix, Interface, _lib, parallel
+    from transiflow_b200._lib import check, ptr
+    L = _lib.lib()
+    grid = args.grid
+    if world > 1:
+        slab = parallel.slab_range(grid, world, rank)
+        it = Interface(dict(RB_PARAMS), grid, grid, grid, device=local_rank, slab=slab)
+        parallel.init_comm(it, dist, rank, world)
+    else:
+        it = Interface(dict(RB_PARAMS), grid, grid, grid, device=local_rank)
+    it._sync_params()
+    state = _lib.pinned_array(it.n_local)
+    state[:] = numpy.random.default_rng(rank).uniform(-0.5, 0.5, it.n_local)
+    mat = DeviceMatrix(it)
+    check(L.tfb_state_upload(it._ctx, ptr(state)))
+    for _ in range(5):
+        check(L.tfb_flush_l2(it._ctx))
+        check(L.tfb_assemble_resident(it._ctx, mat._h, 1, 1))
+    check(L.tfb_sync(it._ctx))
+    if dist:
+        dist.barrier()
+    ms_list = []
+    for _ in range(20):
+        check(L.tfb_flush_l2(it._ctx))
+        check(L.tfb_event_record(it._ctx, 6))
+        check(L.tfb_assemble_resident(it._ctx, mat._h, 1, 1))
+        check(L.tfb_event_record(it._ctx, 7))
+        ms = ctypes.c_float()
+        check(L.tfb_event_elapsed_ms(it._ctx, 6, 7, ctypes.byref(ms)))
+        ms_list.append(ms.value)
+    asm_ms = max_over_ranks(sum(ms_list) / len(ms_list))
+    del mat
+    # Newton: the first step from zero lands on the conduction state (linear); the timed steps start from that state
+    # plus a smooth roll-like perturbation
+    import warnings
+    x = it.vector()
+    steps = []
+    for k in range(3):
+        t0 = time.perf_counter()
+        check(L.tfb_event_record(it._ctx, 6))
+        jac, f = it.jacobian_rhs(x)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            dx = it.solve(jac, -f)
+        check(L.tfb_event_record(it._ctx, 7))
+        ms = ctypes.c_float()
+        check(L.tfb_event_elapsed_ms(it._ctx, 6, 7, ctypes.byref(ms)))
+        x = x + dx
+        if k == 0:
+            k0s, k1s = it.slab
+            c3 = numpy.indices((k1s - k0s, it.ny, it.nx)).astype(float)
+            roll = numpy.sin(numpy.pi * (c3[0] + k0s + 1) / it.nz) * numpy.cos(6 * numpy.pi * (c3[2] + 0.5) / it.nx)
+            xs = x.reshape(k1s - k0s, it.ny, it.nx, it.dof)
+            xs[..., 2] += 1e-2 * roll
+            if k1s == it.nz:
+                xs[-1, :, :, 2] = 0.0
+            xs[..., 4] += 1e-2 * roll
+        steps.append({'ms': max_over_ranks(ms.value), 'iterations': it.last_solve['iterations'], 'relres': it.last_solve['relres'],
+                      'solve_ms': max_over_ranks(it.last_solve['solve_ms']), 'converged': bool(it.last_solve['converged']),
+                      'method': it.last_solve['method'], 'precond': it.last_solve.get('precond_precision')})
+    timed = steps[1:]
+    alg = 8 * it.nnz + 16 * it.n_local
+    return {'workload': 'ONE 3D Rayleigh-Benard %d^3 problem (dof 5, Ra=1000) on %d z-slab(s)' % (grid, world), 'scaling': 'strong',
+            'assembly_ms': asm_ms, 'assembly_cells_per_s': grid ** 3 / (asm_ms * 1e-3),
+            'assembly_roofline_frac': alg / (asm_ms * 1e-3) / 1e9 / measured_peaks()[0],
+            'newton_ms_per_step': sum(h['ms'] for h in timed) / len(timed),
+            'newton_steps_per_s': 1e3 * len(timed) / sum(h['ms'] for h in timed),
+            'krylov_iterations': [h['iterations'] for h in timed], 'relres': [h['relres'] for h in timed],
+            'solve_ms': [round(h['solve_ms'], 1) for h in timed], 'all_converged': all(h['converged'] for h in steps),
+            'method': timed[-1]['method'], 'preconditioner_precision': timed[-1]['precond'], 'unknowns': it.n}
 
 
 def run_reference(args, rank, world):
@@ -204,6 +362,8 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--problem', default='ldc', choices=['ldc', 'rb'] + sorted(PROBLEMS_2D))
+    ap.add_argument('--rb-strong', type=int, default=1,
+                    help='1 (default): add the strong-scaling leg of one Rayleigh-Benard grid^3 problem on N z-slabs; 0: skip')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak (default): grid^3 cells per GPU; strong: one grid^3 problem split over the GPUs')
     args = ap.parse_args()
@@ -364,6 +524,8 @@ def main():
                          'fnorm': float(numpy.sqrt(max_over_ranks(float(f @ f)) if world > 1 else f @ f)),
                          'iterations': it.last_solve['iterations'], 'relres': it.last_solve['relres'],
                          'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
+                         'precond': it.last_solve.get('precond_precision'), 'method': it.last_solve.get('method'),
+                         'schur': it.last_solve.get('schur'),
                          'converged': bool(it.last_solve['converged'])})
         timed = hist[2:]
         nms = sum(h['ms'] for h in timed) / len(timed)
@@ -377,36 +539,44 @@ def main():
                              if args.problem == 'rb' else
                              ('IDR(8)' if it.last_solve.get('method') == 'IDR' else 'FGMRES')
                              + (' + block preconditioner (FDM velocity solves, scaled-mass Schur complement)'
-                                if it.last_solve.get('schur') == 'Scaled Mass' else ' + LSC block preconditioner (FDM sub-solves)'))
+                                if it.last_solve.get('schur') == 'Scaled Mass' else ' + LSC block preconditioner (FDM sub-solves)')
+                             + ('; FDM x/y transforms on tcgen05 (3xTF32), Thomas sweeps along z'
+                                if hist[-1].get('precond') == 'tf32x3' else ''))
                             + ', host vectors in/out'
                             + ('; z-slabs: NCCL halo exchange, all-reduce, all-to-all transposes' if world > 1 else '')}
-        # the same linear system with the opt-in mixed-precision storage (fp32 Krylov basis and fp32 FDM
-        # sub-solves; all reductions, the operator and the convergence test on the true residual stay fp64)
+        # per-product roofline of the solve: algorithmic bytes of one IDR(s) operator product over
+        # the measured time per product of the last timed solve
+        try:
+            newton['roofline'] = solve_roofline(it, timed[-1], measured_peaks()[0])
+        except Exception as e:     # noqa: BLE001
+            newton['roofline'] = {'error': str(e)}
+        # the same linear system with the fp64 SIMT preconditioner (the tensor-core path only steers the iteration: both
+        # reach the same 1e-10 true residual) -- shows what the tcgen05 transforms buy
         try:
             saved = it.parameters.get('Iterative Solver')
-            it.parameters['Iterative Solver'] = dict(saved or {}, **{'Basis Precision': 'single',
-                                                                     'Preconditioner Precision': 'single'})
+            it.parameters['Iterative Solver'] = dict(saved or {}, **{'Preconditioner Precision': 'double'})
             it.solve(jac, -f)
-            newton['mixed_precision_solve'] = {'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
-                                               'iterations': it.last_solve['iterations'],
-                                               'relres': it.last_solve['relres'],
-                                               'converged': bool(it.last_solve['converged']),
-                                               'default_newton_step_ms': max_over_ranks(hist[-1]['ms'])}
-            if args.problem != 'rb':
-                # (not for Rayleigh-Benard: TF32 transforms inside the inner GMRES of the coupled (u, T) block stall the
-                # outer iteration at ~1e-4 -- measured 128^3: 1000 iterations, not converged -- so the option is not offered there)
-                it.parameters['Iterative Solver'] = dict(saved or {}, **{'Preconditioner Precision': 'tf32'})
-                it.solve(jac, -f)
-                newton['tf32_preconditioner_solve'] = {'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
-                                                       'iterations': it.last_solve['iterations'],
-                                                       'relres': it.last_solve['relres'],
-                                                       'converged': bool(it.last_solve['converged'])}
+            newton['fp64_preconditioner_solve'] = {'solve_ms': max_over_ranks(it.last_solve['solve_ms']),
+                                                   'iterations': it.last_solve['iterations'],
+                                                   'relres': it.last_solve['relres'],
+                                                   'converged': bool(it.last_solve['converged']),
+                                                   'default_solve_ms': timed[-1]['solve_ms'],
+                                                   'default_preconditioner': timed[-1].get('precond')}
             if saved is None:
                 it.parameters.pop('Iterative Solver')
             else:
                 it.parameters['Iterative Solver'] = saved
         except Exception as e:     # noqa: BLE001
-            newton['mixed_precision_solve'] = {'error': str(e)}
+            newton['fp64_preconditioner_solve'] = {'error': str(e)}
+
+    # ---- strong scaling of ONE Rayleigh-Benard grid^3 problem on `world` z-slabs (BASELINE config 4) ----
+    rb_strong = None
+    if args.rb_strong and not two_d:
+        try:
+            rb_strong = rb_strong_leg(args, dist, rank, world, local_rank, max_over_ranks)
+        except Exception as e:     # noqa: BLE001
+            rb_strong = {'error': str(e)}
+    slab_gate = parity_gate_slabs(dist, rank, world, local_rank) if world > 1 else None
 
     if rank != 0:
         return
@@ -416,10 +586,16 @@ def main():
     alg_bytes = 8 * nnz + 16 * n_local       # CSR values written + state read + RHS written
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (step_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-    # capture of this kernel on this workload (profiles/r1_ncu_assemble_march_128.csv)
-    # dram read + write of one launch from the committed `ncu --set full` capture (profiles/), per workload
-    ncu_traffic = {('ldc', 128, 1): 105.420288e6 + 970.983680e6}.get((args.problem, grid, world))
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the timed kernel, from the committed `ncu --set full`
+    # capture of the CURRENT kernel on this workload: profiles/traffic.json, written by profiles/summarize_ncu.py
+    ncu_traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as tf:
+            entry = json.load(tf).get('%s_%d_%dgpu' % (args.problem, grid, world))
+        if entry:
+            ncu_traffic, traffic_src = entry['dram_bytes_per_launch'], entry['source']
+    except (OSError, ValueError, KeyError):
+        pass
     line = {
         'metric': 'jacobian_rhs_assembly_cells_per_s', 'value': value, 'unit': 'cells/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_ms,
@@ -430,7 +606,7 @@ def main():
                    'grid': [it.nx, it.ny, it.nz], 'unknowns': it.n, 'nnz_per_gpu': nnz,
                    'partition': 'z-slabs' if world > 1 else 'single GPU', 'l2': 'flushed between timed iterations (256 MiB write)'},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': ncu_traffic, 'peak_source': peak_src,
+                     'traffic': ncu_traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                      'kernel': ('tfb_assemble_kernel (2-D tile kernel)' if two_d else
                                 'tfb_assemble_march_kernel<Cfg_%s,J=1,F=1>' % ('rb3d' if args.problem == 'rb' else 'ldc3d')),
                      'algorithmic_bytes_per_launch': alg_bytes},
@@ -442,6 +618,10 @@ def main():
         'spmv': spmv,
         'parity': parity_gate(local_rank, bool(two_d)),
     }
+    if slab_gate is not None:
+        line['parity_slabs'] = slab_gate
+    if rb_strong is not None:
+        line['rb_strong'] = rb_strong
     if not args.no_cpu_baseline and world == 1 and not two_d:
         planes = max(2, min(grid, 32))
         v, cores, dt = cpu_port_cells_per_s(grid, planes, repeats=2)

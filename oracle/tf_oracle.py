@@ -62,6 +62,8 @@ def lib():
         _LIB.tfo_jacobian.restype = ctypes.c_int
         _LIB.tfo_mass_matrix.restype = ctypes.c_int
         _LIB.tfo_num_threads.restype = ctypes.c_int
+        _LIB.tfo_set_num_threads.argtypes = [ctypes.c_int]
+        _LIB.tfo_set_num_threads.restype = None
         _LIB.tfo_free.argtypes = [ctypes.c_void_p]
     return _LIB
 

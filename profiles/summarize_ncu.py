@@ -1,6 +1,11 @@
 #!/usr/bin/env python3
 '''Turns an `ncu --set full` report (gpurun_out/*.ncu-rep, scratch) into the small CSV summaries kept in
-profiles/:   python profiles/summarize_ncu.py REPORT.ncu-rep "comment line" "command line" > profiles/NAME.csv'''
+profiles/:   python profiles/summarize_ncu.py REPORT.ncu-rep "comment line" "command line" > profiles/NAME.csv
+
+With --traffic KEY NAME.csv as trailing arguments the DRAM bytes of the launch (read + write) are also recorded in
+profiles/traffic.json under KEY ('<problem>_<grid>_<N>gpu'), which is where bench.py takes `roofline.traffic` from.'''
+import json
+import os
 import csv
 import subprocess
 import sys
@@ -33,6 +38,23 @@ def main():
             stalls.append((float(v.replace(',', '')), h))
     for v, h in sorted(stalls, reverse=True)[:8]:
         print('%s,ratio,%.3f' % (h, v))
+    if '--traffic' in sys.argv:
+        key, source = sys.argv[sys.argv.index('--traffic') + 1], sys.argv[sys.argv.index('--traffic') + 2]
+        scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+        byts = {}
+        for h, u, v in zip(hdr, units, val):
+            if h in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                byts[h] = float(v.replace(',', '')) * scale[u]
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'traffic.json')
+        table = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                table = json.load(f)
+        table[key] = {'dram_bytes_per_launch': sum(byts.values()), 'dram_bytes_read': byts.get('dram__bytes_read.sum'),
+                      'dram_bytes_write': byts.get('dram__bytes_write.sum'), 'source': 'profiles/' + os.path.basename(source),
+                      'comment': comment}
+        with open(path, 'w') as f:
+            json.dump(table, f, indent=1, sort_keys=True)
 
 
 if __name__ == '__main__':

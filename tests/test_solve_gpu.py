@@ -62,7 +62,7 @@ def test_linear_solve_matches_reference(name):
     assert numpy.abs(y - g['y']).max() <= 1e-8 * scale, (numpy.abs(y - g['y']).max() / scale, it.last_solve)
 
 
-@pytest.mark.parametrize('name', ['ldc3d_8', 'ldc3d_12_str', 'ldc2d_24', 'dhc2d_16', 'rb3d_8', 'qg_16'])
+@pytest.mark.parametrize('name', ['ldc3d_8', 'ldc3d_12_str', 'ldc2d_24', 'dhc2d_16', 'rb3d_8', 'qg_16', 'amoc_16'])
 def test_newton_converges_to_reference_state(name):
     params, nx, ny, nz = NEWTON_CASES[name]
     g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
@@ -210,7 +210,9 @@ def test_implicit_euler_matches_reference_time_integration():
 
 
 @pytest.mark.parametrize('options', [{'Method': 'BiCGStab'}, {'Basis Precision': 'single', 'Restart': 40},
-                                     {'Preconditioner Precision': 'single'}, {'Preconditioner Precision': 'tf32'},
+                                     {'Preconditioner Precision': 'single'}, {'Preconditioner Precision': 'tf32x3'},
+                                     {'Schur Complement': 'Scaled Mass', 'Method': 'IDR', 'Preconditioner Precision': 'tf32x3'},
+                                     {'Schur Complement': 'Scaled Mass', 'Method': 'IDR', 'Preconditioner Precision': 'double'},
                                      {'Preconditioner Precision': 'single', 'Basis Precision': 'single'},
                                      {'Velocity Iterations': 3}, {'Method': 'IDR'}, {'Method': 'IDR', 'IDR Dimension': 4},
                                      {'Method': 'FGMRES'}, {'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'},
@@ -246,6 +248,7 @@ def test_automatic_method_uses_idr_on_large_grids():
     it.AUTO_IDR_MIN_UNKNOWNS = 1000
     y = it.solve(jac, g['b'])
     assert it.last_solve['method'] == 'IDR' and it.last_solve['schur'] == 'Scaled Mass' and it.last_solve['converged']
+    assert it.last_solve['precond_precision'] == 'tf32x3'       # tensor-core FDM sub-solves wherever IDR + scaled mass is automatic
     assert numpy.abs(y - g['y']).max() <= 1e-8 * numpy.abs(g['y']).max()
 
 

@@ -1,4 +1,4 @@
-'''Wall-clock split of Newton steps at 128^3 (diagnostic script, not a test): python tests/newton_probe.py [grid]'''
+'''Wall-clock split of Newton steps at 128^3 (diagnostic script, not a test): python tools/newton_probe.py [grid]'''
 import sys, time, numpy
 sys.path.insert(0, '.')
 import transiflow_b200 as tb

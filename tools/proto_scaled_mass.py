@@ -3,7 +3,7 @@ the scaled-mass Schur complement as a function of the scaling factor in gamma = 
 least-squares commutator -- the experiment behind the default 2.5 (csrc/tfb_solver.cu: schur_gamma_refresh).  The velocity
 sub-solve is the exact solve with the diffusion block (what the FDM solve computes).
 
-    python tests/proto_scaled_mass.py [N] [Re]
+    python tools/proto_scaled_mass.py [N] [Re]
 '''
 import os
 import sys

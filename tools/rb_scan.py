@@ -1,7 +1,7 @@
 '''Measurement helper (run on the GPU box): Rayleigh-Benard Newton-update solves at the conduction state for a
 list of grids and Rayleigh numbers; prints Krylov iterations, inner iterations and device time as JSON lines.
 
-    python tests/rb_scan.py 64x64x32:1000,3000 128x128x128:1000
+    python tools/rb_scan.py 64x64x32:1000,3000 128x128x128:1000
 '''
 import json
 import sys

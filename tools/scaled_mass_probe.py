@@ -1,5 +1,5 @@
 '''Accuracy / robustness of IDR with the scaled-mass Schur complement against the LSC default (diagnostic script):
-python tests/scaled_mass_probe.py'''
+python tools/scaled_mass_probe.py'''
 import sys, time, numpy
 sys.path.insert(0, '.')
 import transiflow_b200 as tb

@@ -1,5 +1,5 @@
 '''Solver-option scan on one Newton system of the 3-D cavity (diagnostic script, not a test):
-python tests/solve_scan.py [grid]'''
+python tools/solve_scan.py [grid]'''
 import sys, time, numpy
 sys.path.insert(0, '.')
 import transiflow_b200 as tb

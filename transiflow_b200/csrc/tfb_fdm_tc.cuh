@@ -487,6 +487,85 @@ __global__ void __launch_bounds__(256) tfb_int_kernel(const IntArgs a, const dou
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused head and tail of the scaled-mass block preconditioner (velocity-pressure problems):
+//   head:  dp = gamma r_p / |cell|  (pinned cell: -r_p),  comp[v] = (float)(r_v - (G dp)_v)
+//   tail:  z_v = FDM result (wall-normal boundary unknowns: -r_v),  z_p = dp
+// G is the gradient block of the matrix in a two-slot form: row (cell, v) couples to the pressure of the same cell
+// (slot 0) and of the next cell along axis v (slot 1) -- tfb_gell_build_kernel copies the values out of the compact
+// sub-matrix and counts entries that do not fit (then the caller keeps the general path).
+// ---------------------------------------------------------------------------------------------------------
+struct GEll {
+    float* val;            // [dim][2][ncell]
+    int* misfit;           // device counter
+};
+__global__ void __launch_bounds__(256) tfb_gell_build_kernel(long long ncell, int dof, int dim, int nx, int ny, long long cell0,
+                                                             const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                             const double* __restrict__ vals, GEll g) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    const long long stride[3] = {1, nx, (long long)nx * ny};
+    for (int v = 0; v < dim; v++) {
+        const long long row = cell * dof + v;
+        float s0 = 0.f, s1 = 0.f;
+        for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++) {
+            const long long pc = (long long)col[e] / dof - cell0;      // local cell of the pressure unknown
+            if (pc == cell) s0 += (float)vals[e];
+            else if (pc == cell + stride[v]) s1 += (float)vals[e];
+            else if (vals[e] != 0.0) atomicAdd(g.misfit, 1);
+        }
+        g.val[((long long)v * 2 + 0) * ncell + cell] = s0;
+        g.val[((long long)v * 2 + 1) * ncell + cell] = s1;
+    }
+}
+
+struct PreArgs {
+    float* comp[3];
+    float* dp;             // [ncell + ghost plane above]: the pressure update, also read by the tail
+    const float* gval;     // GEll::val
+    const double* hx; const double* hy; const double* hz;
+    double gamma;
+    long long ncell, pin_local;   // pin_local: local cell of the pinned pressure or -1
+    int dof, dim, nx, ny, k0;
+};
+// pass 1: dp (one thread per cell, plus the plane above the slab when it exists in `r_above`)
+__global__ void __launch_bounds__(256) tfb_tc_dp_kernel(const PreArgs a, const double* __restrict__ r) {
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < a.ncell; cell += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(cell % a.nx), j = (int)((cell / a.nx) % a.ny), k = a.k0 + (int)(cell / ((long long)a.nx * a.ny));
+        const double rp = r[cell * a.dof + a.dim];
+        a.dp[cell] = (float)(cell == a.pin_local ? -rp : a.gamma * rp / ((a.hx[i] * a.hy[j]) * a.hz[k]));
+    }
+}
+// pass 2: comp[v] = r_v - g0 dp(cell) - g1 dp(next cell along v)
+__global__ void __launch_bounds__(256) tfb_tc_pre_kernel(const PreArgs a, const double* __restrict__ r) {
+    const long long stride[3] = {1, a.nx, (long long)a.nx * a.ny};
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < a.ncell; cell += (long long)gridDim.x * blockDim.x) {
+        const float d0 = a.dp[cell];
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            if (v >= a.dim) break;
+            const float g0 = a.gval[((long long)v * 2 + 0) * a.ncell + cell], g1 = a.gval[((long long)v * 2 + 1) * a.ncell + cell];
+            double acc = r[cell * a.dof + v] - (double)g0 * (double)d0;
+            if (g1 != 0.f) acc -= (double)g1 * (double)a.dp[cell + stride[v]];
+            a.comp[v][cell] = (float)acc;
+        }
+    }
+}
+// tail: all rows of z
+__global__ void __launch_bounds__(256) tfb_tc_post_kernel(const IntArgs a, const float* __restrict__ dp, int pvar,
+                                                          const double* __restrict__ r, double* __restrict__ z) {
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < a.ncell; cell += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(cell % a.nx), j = (int)((cell / a.nx) % a.ny), k = a.k0 + (int)(cell / ((long long)a.nx * a.ny));
+#pragma unroll 4
+        for (int v = 0; v < a.nv; v++) {
+            const long long row = cell * a.dof + a.var[v];
+            const bool wall = i >= a.mx[v] || j >= a.my[v] || k >= a.mz[v];
+            z[row] = wall ? -r[row] : (double)a.comp[v][cell];
+        }
+        z[cell * a.dof + pvar] = (double)dp[cell];
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace tfbtc

@@ -108,6 +108,13 @@ struct tfb_solver_state {
     bool precond_tc = false;      // x/y transforms on the tensor cores (3xTF32), Thomas sweeps along z
     float* tc32[2] = {nullptr, nullptr};   // fp32 SoA work arrays, TFB_MAXVAR x ncell (pencil-sized with z-slabs) each
     long long tc32_cap = 0;
+    // fused head / tail of the scaled-mass preconditioner: two-slot copy of the gradient block, pressure update
+    float* gell = nullptr;        // [dim][2][ncell]
+    float* dp32 = nullptr;        // ncell + one plane
+    int* gell_misfit = nullptr;
+    bool gell_ok = false;
+    const tfb_mat* gell_owner = nullptr;
+    uint64_t gell_version = ~0ull;
     // velocity sub-solve: inner GMRES on the convection-diffusion block, preconditioned by the FDM solve
     int inner_its = 0;            // 0: one FDM (diffusion-only) solve
     double inner_tol = 1e-2;
@@ -130,6 +137,7 @@ void tfb_solver_free(tfb_solver_state* s) {
         cudaFree(v.th_inv); cudaFree(v.th_cp);
     }
     for (auto& p : s->tc32) cudaFree(p);
+    cudaFree(s->gell); cudaFree(s->dp32); cudaFree(s->gell_misfit);
     for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
     cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab);
     cudaFree(s->d_mass);
@@ -404,6 +412,7 @@ static int sub_build(tfb_ctx* c, SubCsr& S, int prow, unsigned rowmask, unsigned
 }
 static int joint_refresh(tfb_ctx* c, tfb_mat* m);
 static int schur_gamma_refresh(tfb_ctx* c, tfb_mat* m, int prow);
+static int gell_refresh(tfb_ctx* c, tfb_mat* m);
 static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
     tfb_solver_state* s = c->solver;
     const int dof = c->desc.dof, dim = c->desc.dim;
@@ -424,6 +433,7 @@ static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
         q->owner = m; q->version = m->version;
     }
     if (s->joint_ready && joint_refresh(c, m)) return -1;
+    if (s->schur_mass && s->precond_tc && c->nranks == 1 && gell_refresh(c, m)) return -1;
     if (s->schur_mass && schur_gamma_refresh(c, m, prow)) return -1;
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -827,6 +837,67 @@ static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* a, fl
     return tc_planes(c, nv, vars, b, a, true);
 }
 
+// two-slot copy of the gradient block G (values only) for the fused head of the scaled-mass preconditioner
+static int gell_refresh(tfb_ctx* c, tfb_mat* m) {
+    tfb_solver_state* s = c->solver;
+    if (s->gell_owner == m && s->gell_version == m->version) return 0;
+    const int dof = c->desc.dof, dim = c->desc.dim;
+    const long long ncell = c->n_local / dof, plane = (long long)c->desc.nx * c->desc.ny;
+    if (!s->gell) {
+        TFB_CUDA(cudaMalloc(&s->gell, sizeof(float) * (size_t)dim * 2 * ncell));
+        TFB_CUDA(cudaMalloc(&s->dp32, sizeof(float) * (size_t)(ncell + plane)));
+        TFB_CUDA(cudaMemset(s->dp32, 0, sizeof(float) * (size_t)(ncell + plane)));
+        TFB_CUDA(cudaMalloc(&s->gell_misfit, sizeof(int)));
+    }
+    TFB_CUDA(cudaMemsetAsync(s->gell_misfit, 0, sizeof(int), c->stream));
+    tfbtc::GEll g{s->gell, s->gell_misfit};
+    tfbtc::tfb_gell_build_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, c->stream>>>(
+        ncell, dof, dim, c->desc.nx, c->desc.ny, c->row0 / dof, s->subG.row_ptr, s->subG.col, s->subG.vals, g);
+    TFB_LAUNCHED();
+    int misfit = 0;
+    TFB_CUDA(cudaMemcpyAsync(&misfit, s->gell_misfit, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    s->gell_ok = misfit == 0;
+    s->gell_owner = m; s->gell_version = m->version;
+    return 0;
+}
+
+// scaled-mass block preconditioner of a velocity-pressure problem in five launches (head, x/y forward, Thomas,
+// x/y backward, tail):  z_p = dp = gamma r_p / |cell|,  z_u = FDM^-1 (r_u - G dp)
+static int precond_fused_tc(tfb_ctx* c, int prow, const double* r, double* z) {
+    tfb_solver_state* s = c->solver;
+    const int dof = c->desc.dof, dim = c->desc.dim;
+    const long long ncell = c->n_local / dof;
+    if (tc_buffers(c)) return -1;
+    int vars[3];
+    float *a[3], *b[3];
+    tfbtc::PreArgs pa{};
+    tfbtc::IntArgs ia{};
+    for (int v = 0; v < dim; v++) {
+        const FdmVar& f = s->var[v];
+        vars[v] = v;
+        a[v] = s->tc32[0] + (size_t)v * s->tc32_cap;
+        b[v] = s->tc32[1] + (size_t)v * s->tc32_cap;
+        pa.comp[v] = a[v];
+        ia.comp[v] = a[v]; ia.var[v] = v; ia.mx[v] = f.m[0]; ia.my[v] = f.m[1]; ia.mz[v] = f.m[2];
+    }
+    const long long pin_cell = prow >= 0 ? prow / dof : -1, cell0 = c->row0 / dof;
+    pa.dp = s->dp32; pa.gval = s->gell; pa.hx = c->d_met[0]; pa.hy = c->d_met[1]; pa.hz = c->d_met[2];
+    pa.gamma = s->gamma; pa.ncell = ncell;
+    pa.pin_local = (pin_cell >= cell0 && pin_cell < cell0 + ncell) ? pin_cell - cell0 : -1;
+    pa.dof = dof; pa.dim = dim; pa.nx = c->desc.nx; pa.ny = c->desc.ny; pa.k0 = c->desc.k0;
+    ia.nv = dim; ia.dof = dof; ia.nx = c->desc.nx; ia.ny = c->desc.ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
+    const unsigned nb = vec_blocks(ncell);
+    tfbtc::tfb_tc_dp_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
+    tfbtc::tfb_tc_pre_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
+    TFB_LAUNCHED(); TFB_LAUNCHED();
+    if (fdm_solve_tc(c, dim, vars, a, b)) return -1;
+    tfbtc::tfb_tc_post_kernel<<<nb, 256, 0, c->stream>>>(ia, s->dp32, dim, r, z);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // z(rows of the velocity components) = FDM^-1 (r - sub) through the tensor-core path
 static int velocity_fdm_tc(tfb_ctx* c, const double* r, double* z, int skip, const double* sub) {
     tfb_solver_state* s = c->solver;
@@ -1213,6 +1284,8 @@ static int apply_precond_t(tfb_ctx* c, tfb_mat* m, int prow, const double* r, do
     FT *c0 = (FT*)s->comp[0], *c1 = (FT*)s->comp[1], *c2 = (FT*)s->comp[2];
     double *ta = s->vec[0], *tb = s->vec[1], *tc = s->vec[2], *ru = s->vec[3];
     const unsigned vb = vec_blocks(ncell);
+    if (s->schur_mass && s->precond_tc && s->gell_ok && s->inner_its <= 0 && !s->joint_on && !smask && c->nranks == 1)
+        return precond_fused_tc(c, prow, r, z);
     TFB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * n, c->stream));
     // ---- scalars: s = At^-1 r_s ; ru = r - B s (velocity rows) ----
     TFB_CUDA(cudaMemcpyAsync(ru, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
@@ -1825,16 +1898,57 @@ static int bicgstab_run(tfb_mat* m, const double* b, double* x, const tfb_solve_
 }
 
 
-// deterministic shadow vectors for IDR(s): entry (vector j, GLOBAL row g) depends only on (j, g), so a z-slab run uses
-// the same shadow space as a single-GPU run
-__global__ void k_shadow_fill(long long n, long long row0, int nv, double* __restrict__ P) {
+// Shadow vectors of IDR(s) are never stored: entry (vector j, GLOBAL row g) is byte j%8 of a 64-bit hash of (g, j/8),
+// mapped to [-127.5, 127.5], so a z-slab run uses the same shadow space as a single-GPU run and the s dot products
+// P^T w cost one pass over w instead of s + 1 vector reads (and s vectors of HBM).
+__device__ __forceinline__ unsigned long long tfb_shadow_hash(unsigned long long grow, unsigned group) {
+    unsigned long long h = grow * 0x9E3779B97F4A7C15ull + (unsigned long long)(group + 1) * 0xD1B54A32D192ED03ull;
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    return h;
+}
+template <int NS>   // NS = 8 or 16 accumulators
+__global__ void __launch_bounds__(256) k_shadow_dots(long long n, long long row0, int nv, const double* __restrict__ w,
+                                                     double* __restrict__ out) {
+    double acc[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) acc[j] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        for (int j = 0; j < nv; j++) {
-            unsigned long long h = (unsigned long long)(row0 + i) * 0x9E3779B97F4A7C15ull + (unsigned long long)(j + 1) * 0xD1B54A32D192ED03ull;
-            h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
-            P[(long long)j * n + i] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        const double wi = w[i];
+#pragma unroll
+        for (int g = 0; g < NS / 8; g++) {
+            const unsigned long long h = tfb_shadow_hash((unsigned long long)(row0 + i), (unsigned)g);
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const double pj = (double)(int)((h >> (8 * b)) & 0xffull) - 127.5;
+                acc[g * 8 + b] += pj * wi;
+            }
         }
     }
+    __shared__ double red[8][NS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        double a = acc[j];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) red[warp][j] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double t = 0.0;
+        for (int wv = 0; wv < 8; wv++) t += red[wv][threadIdx.x];
+        atomicAdd(&out[threadIdx.x], t);
+    }
+}
+// out[0..S) = P^T w  (all-reduced over the slabs)
+static int shadow_dots(tfb_ctx* c, int S, const double* w, double* d_out) {
+    const long long n = c->n_local;
+    TFB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * S, c->stream));
+    const unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 8);
+    if (S <= 8) k_shadow_dots<8><<<nb, 256, 0, c->stream>>>(n, c->row0, S, w, d_out);
+    else k_shadow_dots<16><<<nb, 256, 0, c->stream>>>(n, c->row0, S, w, d_out);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return tfb_allreduce_sum(c, d_out, S);
 }
 
 // Right-preconditioned IDR(s) in the bi-orthogonal form (van Gijzen & Sonneveld, ACM TOMS 38, 2011).  Short
@@ -1848,7 +1962,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
     tfb_ctx* c = m->ctx;
     const long long n = c->n_local;
     const int S = std::max(1, std::min(sdim, 16));
-    if (ensure_buffers(c, 2 * S + 2, false)) return -1;
+    if (ensure_buffers(c, 2 * S + 3, false)) return -1;
     tfb_solver_state* s = c->solver;
     const int prow = o->pressure_row;
     cudaEvent_t e0, e1;
@@ -1864,7 +1978,6 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
     double* r = U + (size_t)S * n;            // r and t adjacent: one fused pass gives (r.t, t.t)
     double* t = r + n;
     double* v = t + n;
-    double* P = s->d_Z;                       // S shadow vectors
     double* d_dot = s->d_h;                   // [0,S) dots, [S,2S) coefficients, [2S] norm, [2S+1, 2S+3) pair
     double* d_coef = s->d_h + S;
     double* d_nrm = s->d_h + 2 * S;
@@ -1872,8 +1985,6 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
     const unsigned nb = vec_blocks(n);
     TFB_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     TFB_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * n, c->stream));
-    k_shadow_fill<<<nb, 256, 0, c->stream>>>(n, c->row0, S, P);
-    TFB_LAUNCHED();
     auto fetch = [&](double* host, const double* dev, int cnt) -> int {
         TFB_CUDA(cudaMemcpyAsync(host, dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost, c->stream));
         TFB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1964,7 +2075,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
         double om = 1.0;
         bool done = false, breakdown = false;
         while (its < o->maxit && !done && !breakdown) {
-            if (multi_dot<double>(c, P, S, r, d_dot) || fetch(f.data(), d_dot, S)) return -1;       // f = P^T r
+            if (shadow_dots(c, S, r, d_dot) || fetch(f.data(), d_dot, S)) return -1;                // f = P^T r
             for (int k = 0; k < S && its < o->maxit; k++) {
                 // c = M[k:,k:]^-1 f[k:]  (lower triangular)
                 for (int i = k; i < S; i++) {
@@ -1985,7 +2096,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
                 if (spmv(c, m, Uk, Gk, prow)) return -1;                                            // G_k = A U_k
                 its++;
                 // bi-orthogonalise against p_0..p_{k-1}: all dots in one pass, recursion on the host
-                if (multi_dot<double>(c, P, S, Gk, d_dot) || fetch(d.data(), d_dot, S)) return -1;
+                if (shadow_dots(c, S, Gk, d_dot) || fetch(d.data(), d_dot, S)) return -1;
                 for (int i = 0; i < k; i++) {
                     double acc = d[i];
                     for (int j = 0; j < i; j++) acc -= al[j] * Mx(i, j);

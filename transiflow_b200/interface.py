@@ -20,6 +20,44 @@ from . import _lib, hostprep, recipes
 from ._lib import as_f64, check, ptr
 
 
+class ParameterEncoder(json.JSONEncoder):
+    '''JSON form of a parameter set in the reference's file convention (BaseInterface.py:10-29): numpy scalars as
+    Python numbers, arrays as lists, complex values as ``{'__complex__': true, 'real': .., 'imag': ..}``.'''
+
+    def default(self, obj):
+        if isinstance(obj, numpy.integer):
+            return int(obj)
+        if isinstance(obj, numpy.floating):
+            return float(obj)
+        if isinstance(obj, (complex, numpy.complexfloating)):
+            return {'__complex__': True, 'real': float(obj.real), 'imag': float(obj.imag)}
+        if isinstance(obj, numpy.ndarray):
+            return obj.tolist()
+        return super().default(obj)
+
+
+def parameter_decoder(obj):
+    '''object_hook that restores the complex values ParameterEncoder wrote.'''
+    if '__complex__' in obj:
+        return complex(obj['real'], obj['imag'])
+    return obj
+
+
+class _DiscretizationInfo:
+    '''The attributes of ``interface.discretization`` that reference utilities read (utils.create_padded_state_mtx,
+    utils.py:105-107; BaseInterface.py:58-63): grid, coordinate vectors and the periodicity flags of
+    Discretization.py:121-128.  The discretization itself lives in the CUDA kernels.'''
+
+    def __init__(self, interface):
+        self.nx, self.ny, self.nz = interface.nx, interface.ny, interface.nz
+        self.dim, self.dof = interface.dim, interface.dof
+        self.x, self.y, self.z = interface.x, interface.y, interface.z
+        self.x_periodic = False
+        self.y_periodic = False
+        self.z_periodic = interface.nz == 1
+        self.parameters = interface.parameters
+
+
 class DeviceMatrix:
     '''Jacobian on the device: CSR values on the Interface's fixed structural pattern.
 
@@ -37,6 +75,13 @@ class DeviceMatrix:
         self.shape = (interface.n, interface.n)
         self.dtype = numpy.dtype(numpy.float64)
         self._host = None
+        self._complex_shift = None       # (sigma, mass diagonal) of a complex shifted matrix J - sigma M (eigs)
+
+    @property
+    def data(self):
+        '''Values of the compressed matrix -- what ``scipy.sparse`` matrices expose and the reference's JaDa glue
+        inspects for its dtype (``mat.data.dtype``, JaDa.py:27).'''
+        return self.tocsr().data
 
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
@@ -49,6 +94,7 @@ class DeviceMatrix:
         ``J - M / (theta * dt)`` of TimeIntegration.py:58 or a real shifted matrix
         ``beta * J - alpha * M`` of the eigen-solver glue) so that ``solve`` can run on the device.'''
         from scipy import sparse
+        interface._require_whole_grid('DeviceMatrix.from_scipy')
         A = sparse.csr_matrix(A)
         if A.shape != (interface.n, interface.n) or numpy.iscomplexobj(A.data):
             raise NotImplementedError('only real matrices of the Interface size can be uploaded')
@@ -191,6 +237,7 @@ class Interface:
         self.border_scaling = 1e-3                                         # SciPy.py:33
         self.device = device
         self._subspaces = None
+        self.discretization = _DiscretizationInfo(self)
 
         L = _lib.lib()
         if L.tfb_device_count() <= 0:
@@ -223,6 +270,13 @@ class Interface:
         if ctx and _lib._LIB is not None:
             _lib._LIB.tfb_destroy(ctx)
 
+    def _require_whole_grid(self, what):
+        '''The numpy layer above the C ABI is not distributed: on a z-slab only assembly, `jac @ x` free solves and
+        the Krylov solve are.'''
+        if self.slab != (0, self.nz):
+            raise NotImplementedError('%s is not available on a z-slab Interface (slab=%r of %d planes)'
+                                      % (what, self.slab, self.nz))
+
     def _result_vector(self):
         return self._pool.empty() if self._pool is not None else numpy.empty(self.n_local)
 
@@ -231,7 +285,15 @@ class Interface:
         if self.parameters.get('Verbose', False):
             print('Debug:', *args, flush=True)
 
+    def _debug_print_residual(self, string, jac, x, rhs):
+        # BaseInterface.py:36-43
+        if self.parameters.get('Verbose', False):
+            r = jac @ x - rhs
+            self._debug_print(string, numpy.sqrt(abs(numpy.vdot(r, r))))
+
     def set_parameter(self, name, value):
+        if name in self.parameters and self.get_parameter(name) == value:      # Discretization.py:158-161
+            return
         self.parameters[name] = value
 
     def get_parameter(self, name, default=0):
@@ -339,6 +401,7 @@ class Interface:
         '''M as scipy csc (diagonal; pressure rows empty); replaces Discretization.mass_matrix
         (:417-437) + SciPy.Interface.mass_matrix (SciPy.py:47-49).'''
         from scipy import sparse
+        self._require_whole_grid('mass_matrix')
         diag = numpy.empty(self.n)
         check(_lib.lib().tfb_mass_diag(self._ctx, ptr(diag)))
         keep = numpy.abs(diag) > 1e-14                      # Discretization.py:541
@@ -491,6 +554,7 @@ class Interface:
 
     def _bordered_solve(self, jac, rhs, rhs2, V, W, C):
         # [J V; W^T C] [y1; y2] = [rhs; rhs2]  ->  block elimination with two solves with J
+        self._require_whole_grid('the bordered solve')      # W @ a would need an all-reduce over the slabs
         if W is None:
             W = V
         if C is None:
@@ -509,6 +573,7 @@ class Interface:
         operator ``(J - sigma M)^-1 M`` is one device Krylov solve per step (transiflow_b200/eigs.py).
         Real targets only.'''
         from .eigs import shift_invert_arnoldi
+        self._require_whole_grid('eigs')
         prm = self.parameters.get('Eigenvalue Solver', {})
         target = prm.get('Target', 0.0)
         if numpy.iscomplexobj(target) and complex(target).imag != 0.0:
@@ -540,19 +605,42 @@ class Interface:
             return lam, vec
         return lam
 
-    # ---- save / load (BaseInterface.py:106-215) ----
+    # ---- save / load: the file conventions of BaseInterface.py:118-215 ----
+    def save_json(self, name, obj):
+        with open(name, 'w') as f:
+            json.dump(obj, f, cls=ParameterEncoder)
+
+    def load_json(self, name):
+        with open(name, 'r') as f:
+            return json.load(f, object_hook=parameter_decoder)
+
+    def save_parameters(self, name):
+        '''Parameter set -> ``name + '.params'``.'''
+        params_name = name + '.params'
+        self.save_json(params_name, self.parameters)
+        print('Wrote parameters to', params_name, flush=True)
+
+    def load_parameters(self, name):
+        '''``name + '.params'`` -> the (shared) parameter dict, reporting what changed.'''
+        params_name = name + '.params'
+        before = self.parameters.copy()
+        self.parameters.update(self.load_json(params_name))
+        print('Read parameters from', params_name, flush=True)
+        for key, value in self.parameters.items():
+            if value != before.get(key):
+                print("Updated '{}' from {} to {}".format(key, before.get(key), value), flush=True)
+
     def save_state(self, name, x):
+        self.save_parameters(name)
         if not name.endswith('.npy'):
             name += '.npy'
         numpy.save(name, x)
-        with open(os.path.splitext(name)[0] + '.params', 'w') as f:
-            json.dump(self.parameters, f, default=float)
+        print('Wrote state to', name, flush=True)
 
     def load_state(self, name):
+        self.load_parameters(name)
         if not name.endswith('.npy'):
             name += '.npy'
-        pname = os.path.splitext(name)[0] + '.params'
-        if os.path.exists(pname):
-            with open(pname) as f:
-                self.parameters.update(json.load(f))
-        return numpy.load(name)
+        x = numpy.load(name)
+        print('Read state from', name, flush=True)
+        return x
