@@ -68,7 +68,9 @@ def test_newton_converges_to_reference_state(name):
     g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
     it = _iface(params, nx, ny, nz)
     x, k = newton(it, it.vector())
-    assert numpy.linalg.norm(it.rhs(x)) < 1e-9
+    # AMOC: the reference's own Newton run stops at its iteration limit with |F| = 1.8e-8 (golden `fnorm`); the bar is the
+    # residual the SciPy backend reached, and the same state
+    assert numpy.linalg.norm(it.rhs(x)) < max(1e-9, 1.001 * float(g['fnorm']))
     scale = max(numpy.abs(g['x']).max(), 1e-300)
     assert numpy.abs(x - g['x']).max() <= 1e-8 * scale, numpy.abs(x - g['x']).max() / scale
 
