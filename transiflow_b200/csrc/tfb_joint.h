@@ -36,8 +36,10 @@ enum {
 
 // w, T: right-hand sides on entry, solution on exit (plane k at [k * stride]); al, be: scratch for
 // the two upper bands of the factor, N entries each (entry i at [i * stride]).
+// VT: storage type of the right-hand sides / solutions (double, or float on the tensor-core path); arithmetic is fp64.
+template <class VT>
 TFB_HD void tfb_joint_line(int nz, const double* __restrict__ zc, double mu, double cv, double cT, long long stride,
-                           double* __restrict__ w, double* __restrict__ T, double* __restrict__ al, double* __restrict__ be) {
+                           VT* __restrict__ w, VT* __restrict__ T, double* __restrict__ al, double* __restrict__ be) {
     const double* KW_LO = zc + TFB_JZ_KW_LO * nz; const double* KW_D = zc + TFB_JZ_KW_D * nz;
     const double* KW_UP = zc + TFB_JZ_KW_UP * nz; const double* MW = zc + TFB_JZ_MW * nz;
     const double* KT_LO = zc + TFB_JZ_KT_LO * nz; const double* KT_D = zc + TFB_JZ_KT_D * nz;
@@ -54,13 +56,13 @@ TFB_HD void tfb_joint_line(int nz, const double* __restrict__ zc, double mu, dou
             double d = cT * (mu * MT[k] + KT_D[k]);
             double c1 = k < nz - 1 ? C0[k] : 0.0;
             const double c2 = k < nz - 1 ? cT * KT_UP[k] : 0.0;
-            double r = T[k * stride];
+            double r = (double)T[k * stride];
             s1 -= s2 * a2p; d -= s2 * b2p; r -= s2 * g2p;
             d -= s1 * a1p; c1 -= s1 * b1p; r -= s1 * g1p;
             const double inv = 1.0 / d;
             a2p = a1p; b2p = b1p; g2p = g1p;
             a1p = c1 * inv; b1p = c2 * inv; g1p = r * inv;
-            al[(2LL * k) * stride] = a1p; be[(2LL * k) * stride] = b1p; T[k * stride] = g1p;
+            al[(2LL * k) * stride] = a1p; be[(2LL * k) * stride] = b1p; T[k * stride] = (VT)g1p;
         }
         if (k < nz - 1) {   // row 2k+1 : vertical momentum at the face above plane k
             const double s2 = k > 0 ? cv * KW_LO[k] : 0.0;
@@ -68,25 +70,25 @@ TFB_HD void tfb_joint_line(int nz, const double* __restrict__ zc, double mu, dou
             double d = cv * (mu * MW[k] + KW_D[k]);
             double c1 = BP[k];
             const double c2 = k < nz - 2 ? cv * KW_UP[k] : 0.0;
-            double r = w[k * stride];
+            double r = (double)w[k * stride];
             s1 -= s2 * a2p; d -= s2 * b2p; r -= s2 * g2p;
             d -= s1 * a1p; c1 -= s1 * b1p; r -= s1 * g1p;
             const double inv = 1.0 / d;
             a2p = a1p; b2p = b1p; g2p = g1p;
             a1p = c1 * inv; b1p = c2 * inv; g1p = r * inv;
-            al[(2LL * k + 1) * stride] = a1p; be[(2LL * k + 1) * stride] = b1p; w[k * stride] = g1p;
+            al[(2LL * k + 1) * stride] = a1p; be[(2LL * k + 1) * stride] = b1p; w[k * stride] = (VT)g1p;
         }
     }
     // back substitution  y_i = g_i - a_i y_{i+1} - b_i y_{i+2}
     double y1 = 0.0, y2 = 0.0;                // y_{i+1}, y_{i+2}
     for (int k = nz - 1; k >= 0; k--) {
         if (k < nz - 1) {
-            const double y = w[k * stride] - al[(2LL * k + 1) * stride] * y1 - be[(2LL * k + 1) * stride] * y2;
-            w[k * stride] = y;
+            const double y = (double)w[k * stride] - al[(2LL * k + 1) * stride] * y1 - be[(2LL * k + 1) * stride] * y2;
+            w[k * stride] = (VT)y;
             y2 = y1; y1 = y;
         }
-        const double y = T[k * stride] - al[(2LL * k) * stride] * y1 - be[(2LL * k) * stride] * y2;
-        T[k * stride] = y;
+        const double y = (double)T[k * stride] - al[(2LL * k) * stride] * y1 - be[(2LL * k) * stride] * y2;
+        T[k * stride] = (VT)y;
         y2 = y1; y1 = y;
     }
 }

@@ -632,6 +632,8 @@ static int dist_setup(tfb_ctx* c) {
     return 0;
 }
 
+static bool tc_ready(const tfb_ctx* c, int v);
+static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* in, float* const* mid, float* const* out);
 // out = Op_v^-1 in  (SoA arrays of the local slab; `in` is preserved, tmp is scratch)
 template <class FT> static inline FT* const* fdm_q(const FdmVar& f);
 template <> inline double* const* fdm_q<double>(const FdmVar& f) { return f.Q; }
@@ -648,6 +650,21 @@ static int fdm_solve(tfb_ctx* c, int v, FT* in, FT* tmp, FT* out) {
     const bool three = c->desc.dim == 3 && nz > 1;
     const int mx = f.m[0], my = f.m[1], mz = three ? f.m[2] : nz;
     const double thresh = 1e-12 * fabs(f.coef) * f.maxden;
+    if constexpr (sizeof(FT) == 4) {
+        if (s->precond_tc && tc_ready(c, v)) {
+            // tensor-core path: x/y transforms per plane (3xTF32), Thomas sweeps along z
+            float* iv[1] = {in};
+            float* mv[1] = {tmp};
+            float* ov[1] = {out};
+            if (fdm_solve_tc(c, 1, &v, iv, mv, ov)) return -1;
+            if (mx < nx || my < ny || mz < nz) {
+                k_fdm_walls<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, k0, mx, my, mz, in, out);
+                TFB_LAUNCHED();
+            }
+            TFB_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     // forward: x, y on the local planes
     if (axis_gemm(c, false, in, tmp, Q[0], mx, ny * nzl, mx, mx, nx, 1, 0, 1)) return -1;
     if (axis_gemm(c, false, tmp, out, Q[1], my, nx, my, my, 1, nx, (long long)nx * ny, nzl)) return -1;
@@ -800,9 +817,8 @@ static int tc_thomas(tfb_ctx* c, int nv, const int* vars, float* const* x, long 
     return 0;
 }
 
-// a[q] <- Op_{vars[q]}^-1 a[q] for nv SoA fp32 arrays of the local slab; b[q] is scratch.  The x/y basis of
-// array q is that of variable bvar[q] (normally vars[q]).
-static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* a, float* const* b) {
+// out[q] = Op_{vars[q]}^-1 in[q] for nv SoA fp32 arrays of the local slab; mid[q] is scratch (in == out is fine).
+static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* a, float* const* b, float* const* out) {
     tfb_solver_state* s = c->solver;
     const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl;
     for (int q = 0; q < nv; q++) {
@@ -834,8 +850,9 @@ static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* a, fl
         }
         (void)nz;
     }
-    return tc_planes(c, nv, vars, b, a, true);
+    return tc_planes(c, nv, vars, b, out, true);
 }
+
 
 // two-slot copy of the gradient block G (values only) for the fused head of the scaled-mass preconditioner
 static int gell_refresh(tfb_ctx* c, tfb_mat* m) {
@@ -891,7 +908,7 @@ static int precond_fused_tc(tfb_ctx* c, int prow, const double* r, double* z) {
     tfbtc::tfb_tc_dp_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
     tfbtc::tfb_tc_pre_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
     TFB_LAUNCHED(); TFB_LAUNCHED();
-    if (fdm_solve_tc(c, dim, vars, a, b)) return -1;
+    if (fdm_solve_tc(c, dim, vars, a, b, a)) return -1;
     tfbtc::tfb_tc_post_kernel<<<nb, 256, 0, c->stream>>>(ia, s->dp32, dim, r, z);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
@@ -923,7 +940,7 @@ static int velocity_fdm_tc(tfb_ctx* c, const double* r, double* z, int skip, con
     ia.nv = nv; ia.dof = dof; ia.nx = c->desc.nx; ia.ny = c->desc.ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
     tfbtc::tfb_deint_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(da, r, sub);
     TFB_LAUNCHED();
-    if (fdm_solve_tc(c, nv, vars, a, b)) return -1;
+    if (fdm_solve_tc(c, nv, vars, a, b, a)) return -1;
     tfbtc::tfb_int_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(ia, r, sub, z);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
@@ -998,9 +1015,10 @@ __global__ void k_joint_couplings(long long nrows, long long row0, int dof, int 
 }
 
 // one thread per horizontal mode (a, b): banded solve along z
+template <class VT>
 __global__ void __launch_bounds__(128)
 k_joint_lines(int ex, int ey, int jofs, int nz, const double* __restrict__ zc, const double* __restrict__ lx,
-              const double* __restrict__ ly, double cv, double cT, double* __restrict__ w, double* __restrict__ T,
+              const double* __restrict__ ly, double cv, double cT, VT* __restrict__ w, VT* __restrict__ T,
               double* __restrict__ al, double* __restrict__ be) {
     extern __shared__ double s_zc[];
     for (int q = threadIdx.x; q < TFB_JZ_ROWS * nz; q += blockDim.x) s_zc[q] = zc[q];
@@ -1034,8 +1052,10 @@ static int joint_refresh(tfb_ctx* c, tfb_mat* m) {
 
 // (z_w, z_T) = Fwt^-1 (r_w, r_T) on interleaved vectors: the x/y transforms of the vertical velocity's
 // fast-diagonalisation basis, one banded solve per horizontal mode, transforms back.
+static int joint_solve_tc(tfb_ctx* c, const double* r, double* z);
 static int joint_solve(tfb_ctx* c, const double* r, double* z) {
     tfb_solver_state* s = c->solver;
+    if (s->precond_tc && c->nranks == 1) return joint_solve_tc(c, r, z);
     const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl, dof = c->desc.dof;
     const int wv = s->joint_w, sv = s->joint_s;
     // horizontal basis: the vertical velocity's (exact for the viscous block; the scalar block then sees w's
@@ -1062,7 +1082,7 @@ static int joint_solve(tfb_ctx* c, const double* r, double* z) {
     if (axis_gemm<double>(c, false, b, a, f.Q[1], ny, nx, ny, ny, 1, nx, plane, nzl * 2)) return -1;
     const size_t jsmem = sizeof(double) * TFB_JZ_ROWS * nz;
     if (!dist) {
-        k_joint_lines<<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(
+        k_joint_lines<double><<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(
             nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, a, a + ncell, s->jab, s->jab + 2 * ncell);
         TFB_LAUNCHED();
     } else {
@@ -1077,7 +1097,7 @@ static int joint_solve(tfb_ctx* c, const double* r, double* z) {
             TFB_LAUNCHED();
             if (tfb_alltoallv_bytes(c, s->sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, s->pen[h], s->a2a_cnt_pen, s->a2a_dsp_pen, (int)sizeof(double))) return -1;
         }
-        k_joint_lines<<<(unsigned)((lines + 127) / 128), 128, jsmem, c->stream>>>(
+        k_joint_lines<double><<<(unsigned)((lines + 127) / 128), 128, jsmem, c->stream>>>(
             nx, cyme, s->j0s[c->rank], nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, s->pen[0], s->pen[1],
             s->jab, s->jab + 2 * npen);
         TFB_LAUNCHED();
@@ -1097,6 +1117,40 @@ static int joint_solve(tfb_ctx* c, const double* r, double* z) {
         k_negate_var<<<vec_blocks(plane), 256, 0, c->stream>>>(plane, dof, wv, r + top, z + top);
         TFB_LAUNCHED();
     }
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Coupled (w, T) solve on the tensor-core path: x/y transforms of both arrays in the vertical velocity's basis
+// (3xTF32 plane kernel), the pentadiagonal line solve per horizontal mode on fp32 arrays (fp64 arithmetic), back.
+static int joint_solve_tc(tfb_ctx* c, const double* r, double* z) {
+    tfb_solver_state* s = c->solver;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, nzl = c->nzl, dof = c->desc.dof;
+    const int wv = s->joint_w, sv = s->joint_s;
+    const FdmVar& f = s->var[wv];
+    TFB_CHECK(tc_ready(c, wv) && s->var[sv].present && f.m[0] == nx && f.m[1] == ny, "tensor-core basis of the vertical velocity missing");
+    const long long plane = (long long)nx * ny, ncell = plane * nzl;
+    if (tc_buffers(c)) return -1;
+    if (!s->jab) TFB_CUDA(cudaMalloc(&s->jab, sizeof(double) * 4 * ncell));
+    float* a[2] = {s->tc32[0], s->tc32[0] + s->tc32_cap};
+    float* b[2] = {s->tc32[1], s->tc32[1] + s->tc32_cap};
+    const int basis[2] = {wv, wv};
+    tfbtc::DeintArgs da{};
+    da.comp[0] = a[0]; da.comp[1] = a[1]; da.var[0] = wv; da.var[1] = sv; da.nv = 2; da.dof = dof; da.ncell = ncell;
+    tfbtc::tfb_deint_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(da, r, nullptr);
+    TFB_LAUNCHED();
+    if (tc_planes(c, 2, basis, a, b, false)) return -1;
+    const size_t jsmem = sizeof(double) * TFB_JZ_ROWS * nz;
+    k_joint_lines<float><<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(
+        nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, b[0], b[1], s->jab, s->jab + 2 * ncell);
+    TFB_LAUNCHED();
+    if (tc_planes(c, 2, basis, b, a, true)) return -1;
+    tfbtc::IntArgs ia{};
+    ia.comp[0] = a[0]; ia.comp[1] = a[1]; ia.var[0] = wv; ia.var[1] = sv;
+    ia.mx[0] = ia.mx[1] = nx; ia.my[0] = ia.my[1] = ny; ia.mz[0] = nz - 1; ia.mz[1] = nz;   // top-wall rows of w: -r
+    ia.nv = 2; ia.dof = dof; ia.nx = nx; ia.ny = ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
+    tfbtc::tfb_int_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(ia, r, nullptr, z);
+    TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
 }
@@ -2186,6 +2240,7 @@ static int configure_precond(tfb_ctx* c, const tfb_solve_opts* o) {
     bool tc = (o->precond_flags & TFB_PREC_TENSOR) != 0;
     for (int v = 0; tc && v < c->desc.dim; v++) tc = tc_ready(c, v);
     s->precond_tc = tc;
+    if (tc) s->precond_single = true;     // every FDM sub-solve works on fp32 arrays and takes the tensor-core path
     if (const char* e = getenv("TFB_INNER_TOL")) s->inner_tol = atof(e);
     return 0;
 }

@@ -506,15 +506,15 @@ class Interface:
         if schur not in ('auto', 'lsc', 'scaled mass'):
             raise ValueError("'Schur Complement' must be 'LSC' or 'Scaled Mass'")
         auto = method == 'auto'
+        big3d = self.dim == 3 and self.nz > 1 and self.n >= self.AUTO_IDR_MIN_UNKNOWNS   # global size: same choice on every rank
         if auto:
-            big3d = self.dim == 3 and self.nz > 1 and self.n >= self.AUTO_IDR_MIN_UNKNOWNS   # global size: same choice on every rank
             method = 'idr' if (big3d and inner == 0 and 'Basis Precision' not in its and pprec in ('auto', 'double', 'tf32x3')) else 'fgmres'
         auto_schur = schur == 'auto'
         if auto_schur:
             schur = 'scaled mass' if (auto and method == 'idr' and self.dof == self.dim + 1) else 'lsc'
         if pprec == 'auto':
-            # the tensor-core path where the automatic choice is IDR + scaled mass (large 3-D cavities), fp64 elsewhere
-            pprec = 'tf32x3' if (auto and method == 'idr' and schur == 'scaled mass' and tensor_ok) else 'double'
+            # large 3-D grids: every FDM sub-solve on the tensor-core path (fp32 storage); small grids keep fp64
+            pprec = 'tf32x3' if (big3d and tensor_ok) else 'double'
         flags = (_lib.PREC_FP32 if pprec == 'single' else 0) | (_lib.PREC_TENSOR if pprec == 'tf32x3' else 0) \
             | (0 if joint else _lib.PREC_NO_JOINT) | (_lib.PREC_SCALED_MASS if schur == 'scaled mass' else 0)
         o.precond_flags = flags
