@@ -1,5 +1,5 @@
 '''Rayleigh-Benard 128^3: solver options on the second Newton system after the perturbed conduction state (diagnostic
-script, same set-up as bench.py --problem rb): python tests/rb_options_probe.py [grid]'''
+script, same set-up as bench.py --problem rb): python tools/rb_options_probe.py [grid]'''
 import sys, numpy
 sys.path.insert(0, '.')
 import transiflow_b200 as tb
@@ -20,8 +20,15 @@ jac, f = it.jacobian_rhs(x)
 x = x + it.solve(jac, -f)
 jac, f = it.jacobian_rhs(x)
 ref = None
-for opts in ({}, {'Velocity Iterations': 4}, {'Velocity Iterations': 2}, {'Velocity Iterations': 0},
-             {'Velocity Iterations': 0, 'Method': 'IDR'}, {'Velocity Iterations': 12}):
+import warnings
+warnings.simplefilter('ignore')
+for opts in ({}, {'Velocity Iterations': 4}, {'Velocity Iterations': 0},
+             {'Velocity Iterations': 0, 'Method': 'IDR'},
+             {'Velocity Iterations': 0, 'Method': 'IDR', 'Schur Complement': 'Scaled Mass'},
+             {'Velocity Iterations': 0, 'Schur Complement': 'Scaled Mass', 'Method': 'FGMRES'},
+             {'Velocity Iterations': 4, 'Schur Complement': 'Scaled Mass'},
+             {'Schur Complement': 'Scaled Mass'},
+             {'Preconditioner Precision': 'double'}):
     it.parameters['Iterative Solver'] = dict(opts)
     dx = it.solve(jac, -f)
     if ref is None:

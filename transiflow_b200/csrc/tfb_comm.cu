@@ -17,6 +17,7 @@ static struct {
     int (*Send)(const void*, size_t, int, int, ncclComm_t_, cudaStream_t);
     int (*Recv)(void*, size_t, int, int, ncclComm_t_, cudaStream_t);
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t);
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t);
     int (*GroupStart)(void);
     int (*GroupEnd)(void);
     const char* (*GetErrorString)(int);
@@ -31,7 +32,7 @@ static int load_nccl() {
     }
     if (!nccl.handle) return tfb_fail(__FILE__, __LINE__, "dlopen(libnccl.so.2)", dlerror());
 #define SYM(f) *(void**)(&nccl.f) = dlsym(nccl.handle, "nccl" #f); if (!nccl.f) return tfb_fail(__FILE__, __LINE__, "dlsym", "nccl" #f);
-    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(AllGather) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
     return 0;
 }
@@ -137,6 +138,32 @@ int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count) {
     if (c->nranks <= 1) return 0;
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
     TFB_NCCL(nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t_)c->nccl_comm, c->stream));
+    TFB_LAUNCHED();
+    return 0;
+}
+
+// recv[r * count .. (r+1) * count) = send of rank r  (fp32 elements)
+int tfb_allgather_f32(tfb_ctx* c, const float* send, float* recv, size_t count) {
+    if (c->nranks <= 1) {
+        TFB_CUDA(cudaMemcpyAsync(recv, send, sizeof(float) * count, cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    TFB_NCCL(nccl.AllGather(send, recv, count, NCCL_FLOAT32, (ncclComm_t_)c->nccl_comm, c->stream));
+    TFB_LAUNCHED();
+    return 0;
+}
+
+// one-directional halo of an fp32 plane: every rank sends `count` floats at `first_plane` to the rank below and receives
+// the first plane of the rank above into `ghost_above`
+int tfb_halo_up_f32(tfb_ctx* c, const float* first_plane, float* ghost_above, size_t count) {
+    if (c->nranks <= 1) return 0;
+    TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    TFB_NCCL(nccl.GroupStart());
+    if (c->rank > 0) TFB_NCCL(nccl.Send(first_plane, count, NCCL_FLOAT32, c->rank - 1, comm, c->stream));
+    if (c->rank < c->nranks - 1) TFB_NCCL(nccl.Recv(ghost_above, count, NCCL_FLOAT32, c->rank + 1, comm, c->stream));
+    TFB_NCCL(nccl.GroupEnd());
     TFB_LAUNCHED();
     return 0;
 }

@@ -366,8 +366,11 @@ struct ThomasVar {
     float* inv;            // [mz][modes]
     float* cp;             // [mz][modes]
     double coef, shift;
-    int mz;                // active unknowns along z (nz - 1 for the vertical velocity)
+    int k0;                // first global plane of the block that is factored (z-slabs: the local block only)
+    int mz;                // unknowns of the block along z
     int mx, my;            // active modes along x, y (others are written as zero)
+    int pin_last;          // 1: a mode with lx + ly = 0 (constant mode of an all-Neumann operator) gets its last unknown pinned
+    double mu_eps;
 };
 
 __global__ void tfb_thomas_setup_kernel(ThomasVar v, int ex, int ey, int jofs, int nz, double thresh) {
@@ -377,15 +380,18 @@ __global__ void tfb_thomas_setup_kernel(ThomasVar v, int ex, int ey, int jofs, i
     const int i = (int)(m % ex), j = jofs + (int)(m / ex);
     const bool active = i < v.mx && j < v.my;
     const double mu = active ? v.lx[i] + v.ly[j] : 0.0;
+    const bool pin = v.pin_last && fabs(mu) <= v.mu_eps;
     double cprev = 0.0;
-    for (int k = 0; k < v.mz; k++) {
-        const double lo = v.coef * v.zk[k], dg = v.coef * (mu * v.zk[3 * nz + k] + v.zk[nz + k]) + v.shift * v.zk[3 * nz + k];
+    for (int kl = 0; kl < v.mz; kl++) {
+        const int k = v.k0 + kl;
+        const double lo = kl > 0 ? v.coef * v.zk[k] : 0.0;
+        const double dg = v.coef * (mu * v.zk[3 * nz + k] + v.zk[nz + k]) + v.shift * v.zk[3 * nz + k];
         const double up = v.coef * v.zk[2 * nz + k];
         const double den = dg - lo * cprev;
         double inv = 0.0, cp = 0.0;
-        if (active && fabs(den) > thresh) { inv = 1.0 / den; cp = (k + 1 < v.mz) ? up * inv : 0.0; }
-        v.inv[(long long)k * modes + m] = (float)inv;
-        v.cp[(long long)k * modes + m] = (float)cp;
+        if (active && fabs(den) > thresh && !(pin && kl == v.mz - 1)) { inv = 1.0 / den; cp = (kl + 1 < v.mz) ? up * inv : 0.0; }
+        v.inv[(long long)kl * modes + m] = (float)inv;
+        v.cp[(long long)kl * modes + m] = (float)cp;
         cprev = cp;
     }
 }
@@ -397,8 +403,9 @@ struct ThomasArgs {
     const double* zk[MAXQ];    // for the sub-diagonal
     double coef[MAXQ];
     int mz[MAXQ];
-    int narr, nz;
+    int narr, nz, k0;          // k0: global plane of local plane 0 (z-slabs solve their own block)
     long long modes;
+    float* iface;              // optional [narr][2][modes]: first and last unknown of every local solution
 };
 
 // one thread per (array, mode); the loads of a block of TB planes are issued before the dependent chain runs
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(128) tfb_thomas_kernel(const ThomasArgs a) {
     float* __restrict__ x = a.x[q] + m;
     const float* __restrict__ inv = a.inv[q] + m;
     const float* __restrict__ cp = a.cp[q] + m;
-    const double* __restrict__ lo = a.zk[q];
+    const double* __restrict__ lo = a.zk[q] + a.k0;
     const double coef = a.coef[q];
     const int mz = a.mz[q];
     const long long st = a.modes;
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(128) tfb_thomas_kernel(const ThomasArgs a) {
             const bool ok = k < mz;
             xv[t] = ok ? x[(long long)k * st] : 0.f;
             iv[t] = ok ? inv[(long long)k * st] : 0.f;
-            lv[t] = ok ? (float)(coef * lo[k]) : 0.f;
+            lv[t] = (ok && k > 0) ? (float)(coef * lo[k]) : 0.f;
         }
 #pragma unroll
         for (int t = 0; t < TB; t++) {
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(128) tfb_thomas_kernel(const ThomasArgs a) {
             if (k0 + t < mz) x[(long long)(k0 + t) * st] = rp;
         }
     }
-    float xn = 0.f;
+    float xn = 0.f, xlast = 0.f;
     for (int k1 = mz; k1 > 0; k1 -= TB) {
         float xv[TB], cv[TB];
 #pragma unroll
@@ -443,11 +450,151 @@ __global__ void __launch_bounds__(128) tfb_thomas_kernel(const ThomasArgs a) {
         }
 #pragma unroll
         for (int t = 0; t < TB; t++) {
-            xn = xv[t] - cv[t] * xn;
-            if (k1 - 1 - t >= 0) x[(long long)(k1 - 1 - t) * st] = xn;
+            if (k1 - 1 - t >= 0) {
+                xn = xv[t] - cv[t] * xn;
+                x[(long long)(k1 - 1 - t) * st] = xn;
+                if (k1 - 1 - t == mz - 1) xlast = xn;
+            }
         }
     }
+    if (a.iface) {
+        a.iface[((long long)q * 2 + 0) * st + m] = xn;       // first unknown (computed last)
+        a.iface[((long long)q * 2 + 1) * st + m] = xlast;
+    }
     // planes mz .. nz-1 (wall unknowns) are not touched here
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// z-slabs: the tridiagonal systems run through every slab.  Each rank factors and solves ITS block T_g (above), so
+//     x_g = y_g - l_{g-1} * v'_g - f_{g+1} * w'_g,      y_g = T_g^-1 r_g,
+// with the "spikes" v'_g = lo_g T_g^-1 e_first, w'_g = up_g T_g^-1 e_last (lo_g, up_g: the couplings to the neighbour
+// slabs) and l_{g-1}, f_{g+1} the last / first unknowns of the neighbours' SOLUTIONS.  Those follow from a reduced
+// system in the 2G interface unknowns (f_g, l_g) per mode,
+//     f_g + A_g l_{g-1} + B_g f_{g+1} = yf_g,   l_g + C_g l_{g-1} + D_g f_{g+1} = yl_g,
+//     A = v'_first, B = w'_first, C = v'_last, D = w'_last,
+// whose matrix depends only on the operator: tfb_spike_weights_kernel inverts it once per parameter set and keeps the
+// two rows every rank needs, so a solve is: local sweeps, ONE all-gather of (yf, yl) per array (2 floats per mode and
+// rank), two short dot products and one correction pass -- instead of two all-to-all transposes of the whole array.
+// ---------------------------------------------------------------------------------------------------------
+struct SpikeVar {
+    const float* inv; const float* cp; const double* zk;
+    float* v; float* w;        // [mz][modes]: the scaled spikes
+    float* coef4;              // [4][modes]: A, B, C, D of this rank (all-gathered afterwards)
+    double coef;
+    int k0, mz, nz_active;     // block offset, local unknowns, global unknowns of this variable along z
+    long long modes;
+};
+__global__ void __launch_bounds__(128) tfb_spike_setup_kernel(SpikeVar s) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= s.modes || s.mz <= 0) return;
+    const long long st = s.modes;
+    const float* inv = s.inv + m;
+    const float* cp = s.cp + m;
+    // v = T^-1 e_first: forward sweep of e_first, backward sweep; w = T^-1 e_last: only the last forward entry is non-zero
+    float* v = s.v + m;
+    float* w = s.w + m;
+    double rp = 0.0;
+    for (int k = 0; k < s.mz; k++) {
+        const double lok = k > 0 ? s.coef * s.zk[s.k0 + k] : 0.0;
+        rp = ((k == 0 ? 1.0 : 0.0) - lok * rp) * (double)inv[(long long)k * st];
+        v[(long long)k * st] = (float)rp;
+    }
+    double xv = 0.0, xw = 0.0;
+    for (int k = s.mz - 1; k >= 0; k--) {
+        xv = (double)v[(long long)k * st] - (double)cp[(long long)k * st] * xv;
+        xw = (k == s.mz - 1 ? (double)inv[(long long)k * st] : 0.0) - (double)cp[(long long)k * st] * xw;
+        v[(long long)k * st] = (float)xv;
+        w[(long long)k * st] = (float)xw;
+    }
+}
+// scale the spikes by the couplings to the neighbour slabs and publish this rank's four coefficients
+__global__ void __launch_bounds__(128) tfb_spike_scale_kernel(SpikeVar s, double lo_g, double up_g) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= s.modes) return;
+    const long long st = s.modes;
+    for (int k = 0; k < s.mz; k++) {
+        s.v[(long long)k * st + m] = (float)(lo_g * (double)s.v[(long long)k * st + m]);
+        s.w[(long long)k * st + m] = (float)(up_g * (double)s.w[(long long)k * st + m]);
+    }
+    const bool any = s.mz > 0;
+    s.coef4[0 * st + m] = any ? s.v[m] : 0.f;                                     // A: v'_first
+    s.coef4[1 * st + m] = any ? s.w[m] : 0.f;                                     // B: w'_first
+    s.coef4[2 * st + m] = any ? s.v[(long long)(s.mz - 1) * st + m] : 0.f;        // C: v'_last
+    s.coef4[3 * st + m] = any ? s.w[(long long)(s.mz - 1) * st + m] : 0.f;        // D: w'_last
+}
+// rows of the inverse of the reduced system that rank `me` needs: weights[0] -> l_{me-1}, weights[1] -> f_{me+1}; each is a
+// vector over the 2G gathered values ordered (yf_0, yl_0, yf_1, yl_1, ...).  coef_all: [G][4][modes].
+#define TFB_SPIKE_MAXG 16
+__global__ void __launch_bounds__(64) tfb_spike_weights_kernel(int G, int me, long long modes, const float* __restrict__ coef_all,
+                                                               float* __restrict__ weights) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= modes) return;
+    const int n = 2 * G;
+    double M[2 * TFB_SPIKE_MAXG][2 * TFB_SPIKE_MAXG];
+    double R[2 * TFB_SPIKE_MAXG][2];      // right-hand sides of M^T w = e_p, e_q
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < n; c++) M[r][c] = r == c ? 1.0 : 0.0;
+    for (int g = 0; g < G; g++) {
+        const double A = coef_all[((long long)g * 4 + 0) * modes + m], B = coef_all[((long long)g * 4 + 1) * modes + m];
+        const double C = coef_all[((long long)g * 4 + 2) * modes + m], D = coef_all[((long long)g * 4 + 3) * modes + m];
+        // M^T is what is factored: entry (row r, col c) of M goes to M[c][r]
+        if (g > 0) { M[2 * g - 1][2 * g] = A; M[2 * g - 1][2 * g + 1] = C; }
+        if (g < G - 1) { M[2 * g + 2][2 * g] = B; M[2 * g + 2][2 * g + 1] = D; }
+    }
+    const int p = 2 * (me - 1) + 1, q = 2 * (me + 1);
+    for (int r = 0; r < n; r++) { R[r][0] = (me > 0 && r == p) ? 1.0 : 0.0; R[r][1] = (me < G - 1 && r == q) ? 1.0 : 0.0; }
+    // Gaussian elimination without pivoting (the system is diagonally dominant: |spike tips| < 1); band of width 3
+    for (int k = 0; k < n; k++) {
+        const double piv = M[k][k];
+        const double ip = fabs(piv) > 1e-12 ? 1.0 / piv : 0.0;
+        const int rmax = k + 3 < n ? k + 3 : n - 1;
+        for (int r = k + 1; r <= rmax; r++) {
+            const double fct = M[r][k] * ip;
+            if (fct == 0.0) continue;
+            for (int c = k; c <= (k + 3 < n ? k + 3 : n - 1); c++) M[r][c] -= fct * M[k][c];
+            R[r][0] -= fct * R[k][0]; R[r][1] -= fct * R[k][1];
+        }
+    }
+    for (int k = n - 1; k >= 0; k--) {
+        const double piv = M[k][k];
+        const double ip = fabs(piv) > 1e-12 ? 1.0 / piv : 0.0;
+        double a0 = R[k][0], a1 = R[k][1];
+        for (int c = k + 1; c <= (k + 3 < n ? k + 3 : n - 1); c++) { a0 -= M[k][c] * R[c][0]; a1 -= M[k][c] * R[c][1]; }
+        R[k][0] = a0 * ip; R[k][1] = a1 * ip;
+    }
+    for (int r = 0; r < n; r++) {
+        weights[((long long)0 * n + r) * modes + m] = (float)R[r][0];
+        weights[((long long)1 * n + r) * modes + m] = (float)R[r][1];
+    }
+}
+// x = y - l_{g-1} v' - f_{g+1} w' with (l_{g-1}, f_{g+1}) = weights . gathered interface values
+struct SpikeFixArgs {
+    float* x[MAXQ];
+    const float* v[MAXQ]; const float* w[MAXQ];
+    const float* weights[MAXQ];   // [2][2G][modes]
+    int mz[MAXQ];
+    const float* gathered;        // [G][narr][2][modes]
+    int narr, G;
+    long long modes;
+};
+__global__ void __launch_bounds__(128) tfb_spike_fix_kernel(const SpikeFixArgs a) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (m >= a.modes) return;
+    const long long st = a.modes;
+    const int n = 2 * a.G;
+    double lp = 0.0, fn = 0.0;
+    for (int g = 0; g < a.G; g++) {
+        const float* y = a.gathered + ((long long)(g * a.narr + q) * 2) * st + m;
+        const double yf = y[0], yl = y[st];
+        lp += (double)a.weights[q][((long long)0 * n + 2 * g) * st + m] * yf + (double)a.weights[q][((long long)0 * n + 2 * g + 1) * st + m] * yl;
+        fn += (double)a.weights[q][((long long)1 * n + 2 * g) * st + m] * yf + (double)a.weights[q][((long long)1 * n + 2 * g + 1) * st + m] * yl;
+    }
+    const float lpf = (float)lp, fnf = (float)fn;
+    float* x = a.x[q] + m;
+    const float* v = a.v[q] + m;
+    const float* w = a.w[q] + m;
+    for (int k = 0; k < a.mz[q]; k++) x[(long long)k * st] -= lpf * v[(long long)k * st] + fnf * w[(long long)k * st];
 }
 
 // interleaved fp64 vector -> fp32 SoA arrays of `nv` variables:  comp[v][cell] = r[cell*dof + var[v]] - sub[...]

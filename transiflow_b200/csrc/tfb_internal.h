@@ -84,4 +84,6 @@ int tfb_halo_exchange(tfb_ctx* ctx, double* d_vec_with_ghosts);
 int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
 int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
                   double* recv, const long long* rcount, const long long* rdispl);
+int tfb_halo_up_f32(tfb_ctx* c, const float* first_plane, float* ghost_above, size_t count);
+int tfb_allgather_f32(tfb_ctx* c, const float* send, float* recv, size_t count);
 void tfb_solver_free(tfb_solver_state* s);

@@ -57,6 +57,14 @@ struct FdmVar {
     long long th_cap = 0;         // floats allocated per array
     bool th_dirty = true;
     double shift = 0.0;           // operator + shift * mass (time stepping, shifted eigenproblems)
+    std::vector<double> pencil_h[3];   // host copies of the pencil tables
+    // z-slabs: scaled spikes of the local block, this rank's / everybody's reduced-system coefficients, inverse rows
+    float* sp_v = nullptr;
+    float* sp_w = nullptr;
+    float* sp_coef = nullptr;     // [4][modes]
+    float* sp_coef_all = nullptr; // [G][4][modes]
+    float* sp_weights = nullptr;  // [2][2G][modes]
+    int mz_local = 0;
 };
 
 // Compact copy of the entries of J with (row variable, column variable) in given masks: the
@@ -93,7 +101,10 @@ struct tfb_solver_state {
     uint64_t gam_version = ~0ull;
     double* d_mass = nullptr;     // velocity mass diagonal (LSC scaling), n_local
     double* comp[3] = {};         // SoA work arrays, ncell each
-    double* vec[8] = {};          // interleaved work vectors, n_local each
+    double* vec[8] = {};          // interleaved work vectors, n_local each, one plane of slack before and after
+    double* vec_base[8] = {};
+    long long dv_stride = 0;      // > 0: d_V holds dv_count vectors of this stride, each preceded by a plane of slack (idr_run)
+    int dv_count = 0;
     double* d_scal = nullptr;     // small device scalars
     // z-slab runs: ghosted copy of a vector, pencil-layout work arrays, all-to-all staging
     double* xg = nullptr;
@@ -106,6 +117,8 @@ struct tfb_solver_state {
     bool dist_ready = false;
     bool precond_single = false;  // apply the FDM sub-solves in fp32 (FGMRES keeps the outer iteration exact)
     bool precond_tc = false;      // x/y transforms on the tensor cores (3xTF32), Thomas sweeps along z
+    float* sp_send = nullptr;     // z-slabs: interface values of the local Thomas solutions, [TFB_MAXVAR][2][modes]
+    float* sp_recv = nullptr;     // [G] x that
     float* tc32[2] = {nullptr, nullptr};   // fp32 SoA work arrays, TFB_MAXVAR x ncell (pencil-sized with z-slabs) each
     long long tc32_cap = 0;
     // fused head / tail of the scaled-mass preconditioner: two-slot copy of the gradient block, pressure update
@@ -135,14 +148,16 @@ void tfb_solver_free(tfb_solver_state* s) {
         for (int a = 0; a < 3; a++) { cudaFree(v.Q[a]); cudaFree(v.lam[a]); cudaFree(v.Qf[a]); cudaFree(v.lamf[a]); cudaFree(v.pencil[a]); }
         for (int a = 0; a < 2; a++) { cudaFree(v.tcA[a][0]); cudaFree(v.tcA[a][1]); }
         cudaFree(v.th_inv); cudaFree(v.th_cp);
+        cudaFree(v.sp_v); cudaFree(v.sp_w); cudaFree(v.sp_coef); cudaFree(v.sp_coef_all); cudaFree(v.sp_weights);
     }
+    cudaFree(s->sp_send); cudaFree(s->sp_recv);
     for (auto& p : s->tc32) cudaFree(p);
     cudaFree(s->gell); cudaFree(s->dp32); cudaFree(s->gell_misfit);
     for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
     cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab);
     cudaFree(s->d_mass);
     for (auto p : s->comp) cudaFree(p);
-    for (auto p : s->vec) cudaFree(p);
+    for (auto p : s->vec_base) cudaFree(p);
     cudaFree(s->xg); cudaFree(s->pen[0]); cudaFree(s->pen[1]); cudaFree(s->sbuf); cudaFree(s->rbuf);
     cudaFree(s->d_scal); cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h); cudaFree(s->d_Vi); cudaFree(s->d_Zi);
     delete s;
@@ -200,10 +215,26 @@ static inline int local_prow(const tfb_ctx* c, int prow) {
 // planes, the halos are exchanged (NCCL) and the kernels index a pointer shifted by the first
 // owned row, so that global columns address the ghosted copy.
 static int dist_setup(tfb_ctx* c);
+// Work vectors are allocated with one plane of slack on either side (ensure_buffers, idr_run), so on z-slabs the halo
+// planes of x are received next to it and no ghosted copy of the vector is made.
+static bool ghost_capable(const tfb_ctx* c, const double* x) {
+    const tfb_solver_state* s = c->solver;
+    for (const double* v : s->vec) if (x == v) return true;
+    if (s->dv_stride > 0 && s->d_V) {
+        const double* first = s->d_V + c->plane_rows;
+        if (x >= first && x < first + (size_t)s->dv_stride * s->dv_count && (size_t)(x - first) % (size_t)s->dv_stride == 0) return true;
+    }
+    return false;
+}
 static int ghosted(tfb_ctx* c, const double* x, const double** xs) {
     if (c->nranks == 1) { *xs = x; return 0; }
     if (dist_setup(c)) return -1;
     tfb_solver_state* s = c->solver;
+    if (ghost_capable(c, x)) {
+        if (tfb_halo_exchange(c, const_cast<double*>(x) - c->plane_rows)) return -1;
+        *xs = x - c->row0;
+        return 0;
+    }
     TFB_CUDA(cudaMemcpyAsync(s->xg + c->plane_rows, x, sizeof(double) * c->n_local, cudaMemcpyDeviceToDevice, c->stream));
     if (tfb_halo_exchange(c, s->xg)) return -1;
     *xs = s->xg + c->plane_rows - c->row0;
@@ -220,7 +251,8 @@ static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, un
         static int use_structured = -1;
         if (use_structured < 0) { const char* e = getenv("TFB_SPMV_CSR"); use_structured = !(e && e[0] == '1'); }
         if (use_structured) {
-            const int kv0 = c->nranks == 1 ? 0 : c->desc.k0 - 1, kv1 = c->nranks == 1 ? c->desc.nz : c->desc.k1 + 1;
+            // planes of x that exist: the slab plus one halo plane on either side, clipped to the domain
+            const int kv0 = std::max(0, c->desc.k0 - 1), kv1 = std::min(c->desc.nz, c->desc.k1 + 1);
             const int rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
             if (rc <= 0) return rc;
         }
@@ -433,7 +465,7 @@ static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
         q->owner = m; q->version = m->version;
     }
     if (s->joint_ready && joint_refresh(c, m)) return -1;
-    if (s->schur_mass && s->precond_tc && c->nranks == 1 && gell_refresh(c, m)) return -1;
+    if (s->schur_mass && s->precond_tc && gell_refresh(c, m)) return -1;
     if (s->schur_mass && schur_gamma_refresh(c, m, prow)) return -1;
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -736,11 +768,7 @@ static bool tc_ready(const tfb_ctx* c, int v) {
 
 static int tc_buffers(tfb_ctx* c) {
     tfb_solver_state* s = c->solver;
-    long long need = c->n_local / c->desc.dof;
-    if (c->nranks > 1) {
-        const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
-        need = std::max(need, (long long)c->desc.nz * cyme * c->desc.nx);
-    }
+    const long long need = c->n_local / c->desc.dof;
     if (need > s->tc32_cap) {
         for (auto& p : s->tc32) { cudaFree(p); p = nullptr; }
         for (auto& p : s->tc32) TFB_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)need * TFB_MAXVAR));
@@ -774,42 +802,74 @@ static int tc_planes(tfb_ctx* c, int nv, const int* bvar, float* const* in, floa
     return 0;
 }
 
-// Thomas factors of variable v for the current eigenvalues / coefficient / shift; modes = ex * ey columns
+// Thomas factors of variable v for the current eigenvalues / coefficient / shift.  z-slabs factor their own block and
+// set up the interface (spike) data of tfb_fdm_tc.cuh: one all-gather of four coefficients per mode, once per parameter set.
 static int tc_thomas_setup(tfb_ctx* c, int v) {
     tfb_solver_state* s = c->solver;
     FdmVar& f = s->var[v];
     if (!f.th_dirty) return 0;
-    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz;
-    const bool dist = c->nranks > 1;
-    const int ey = dist ? s->j0s[c->rank + 1] - s->j0s[c->rank] : ny, jofs = dist ? s->j0s[c->rank] : 0;
-    const long long modes = (long long)nx * ey, need = modes * nz;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, G = c->nranks;
+    const long long modes = (long long)nx * ny;
+    const int k0 = c->desc.k0;
+    const int mzl = std::max(0, std::min(c->desc.k1, f.m[2]) - k0);      // unknowns of this variable in the local block
+    const long long need = modes * std::max(1, c->nzl);
     if (need > f.th_cap) {
         cudaFree(f.th_inv); cudaFree(f.th_cp);
         f.th_inv = f.th_cp = nullptr;
         TFB_CUDA(cudaMalloc(&f.th_inv, sizeof(float) * (size_t)need));
         TFB_CUDA(cudaMalloc(&f.th_cp, sizeof(float) * (size_t)need));
+        if (G > 1) {
+            TFB_CHECK(G <= TFB_SPIKE_MAXG, "too many z-slabs for the interface system");
+            cudaFree(f.sp_v); cudaFree(f.sp_w); cudaFree(f.sp_coef); cudaFree(f.sp_coef_all); cudaFree(f.sp_weights);
+            TFB_CUDA(cudaMalloc(&f.sp_v, sizeof(float) * (size_t)need));
+            TFB_CUDA(cudaMalloc(&f.sp_w, sizeof(float) * (size_t)need));
+            TFB_CUDA(cudaMalloc(&f.sp_coef, sizeof(float) * 4 * (size_t)modes));
+            TFB_CUDA(cudaMalloc(&f.sp_coef_all, sizeof(float) * 4 * (size_t)modes * G));
+            TFB_CUDA(cudaMalloc(&f.sp_weights, sizeof(float) * 4 * (size_t)modes * G));
+        }
         f.th_cap = need;
     }
+    f.mz_local = mzl;
     tfbtc::ThomasVar t;
     t.lx = f.lam[0]; t.ly = f.lam[1]; t.zk = f.pencil[2]; t.inv = f.th_inv; t.cp = f.th_cp;
-    t.coef = f.coef; t.shift = f.shift; t.mz = f.m[2]; t.mx = f.m[0]; t.my = f.m[1];
+    t.coef = f.coef; t.shift = f.shift; t.k0 = k0; t.mz = mzl; t.mx = f.m[0]; t.my = f.m[1];
+    // an all-Neumann operator (pressure Poisson, pinned scalars) is singular in its constant mode: on one GPU the last
+    // pivot of that mode vanishes and is dropped; on slabs the top rank pins it explicitly so that every block is regular
+    t.pin_last = (G > 1 && c->rank == G - 1 && (v == c->desc.dim || f.pin_cell >= 0)) ? 1 : 0;
+    t.mu_eps = 1e-10 * f.maxden;
     const double thresh = 1e-12 * fabs(f.coef) * f.maxden;
-    tfbtc::tfb_thomas_setup_kernel<<<(unsigned)((modes + 127) / 128), 128, 0, c->stream>>>(t, nx, ey, jofs, nz, thresh);
+    const unsigned nb = (unsigned)((modes + 127) / 128);
+    tfbtc::tfb_thomas_setup_kernel<<<nb, 128, 0, c->stream>>>(t, nx, ny, 0, nz, thresh);
     TFB_LAUNCHED();
+    if (G > 1) {
+        tfbtc::SpikeVar sp;
+        sp.inv = f.th_inv; sp.cp = f.th_cp; sp.zk = f.pencil[2]; sp.v = f.sp_v; sp.w = f.sp_w; sp.coef4 = f.sp_coef;
+        sp.coef = f.coef; sp.k0 = k0; sp.mz = mzl; sp.nz_active = f.m[2]; sp.modes = modes;
+        const std::vector<double>& zk = f.pencil_h[2];
+        const double lo_g = (k0 > 0 && mzl > 0) ? f.coef * zk[k0] : 0.0;
+        const double up_g = (mzl > 0 && k0 + mzl < f.m[2]) ? f.coef * zk[2 * (size_t)nz + k0 + mzl - 1] : 0.0;
+        tfbtc::tfb_spike_setup_kernel<<<nb, 128, 0, c->stream>>>(sp);
+        tfbtc::tfb_spike_scale_kernel<<<nb, 128, 0, c->stream>>>(sp, lo_g, up_g);
+        TFB_LAUNCHED(); TFB_LAUNCHED();
+        if (tfb_allgather_f32(c, f.sp_coef, f.sp_coef_all, 4 * (size_t)modes)) return -1;
+        tfbtc::tfb_spike_weights_kernel<<<(unsigned)((modes + 63) / 64), 64, 0, c->stream>>>(G, c->rank, modes, f.sp_coef_all, f.sp_weights);
+        TFB_LAUNCHED();
+    }
     TFB_CUDA(cudaGetLastError());
     f.th_dirty = false;
     return 0;
 }
 
-// in-place tridiagonal solves along z of nv arrays laid out [k][modes]
-static int tc_thomas(tfb_ctx* c, int nv, const int* vars, float* const* x, long long modes) {
+// in-place tridiagonal solves along z of nv arrays laid out [k][modes] (z-slabs: the local blocks; `iface` then
+// receives the first / last unknown of every local solution)
+static int tc_thomas(tfb_ctx* c, int nv, const int* vars, float* const* x, long long modes, float* iface) {
     tfb_solver_state* s = c->solver;
     tfbtc::ThomasArgs a{};
     for (int q = 0; q < nv; q++) {
         const FdmVar& f = s->var[vars[q]];
-        a.x[q] = x[q]; a.inv[q] = f.th_inv; a.cp[q] = f.th_cp; a.zk[q] = f.pencil[2]; a.coef[q] = f.coef; a.mz[q] = f.m[2];
+        a.x[q] = x[q]; a.inv[q] = f.th_inv; a.cp[q] = f.th_cp; a.zk[q] = f.pencil[2]; a.coef[q] = f.coef; a.mz[q] = f.mz_local;
     }
-    a.narr = nv; a.nz = c->desc.nz; a.modes = modes;
+    a.narr = nv; a.nz = c->desc.nz; a.k0 = c->desc.k0; a.modes = modes; a.iface = iface;
     dim3 grid((unsigned)((modes + 127) / 128), nv);
     tfbtc::tfb_thomas_kernel<8><<<grid, 128, 0, c->stream>>>(a);
     TFB_LAUNCHED();
@@ -826,29 +886,29 @@ static int fdm_solve_tc(tfb_ctx* c, int nv, const int* vars, float* const* a, fl
         if (tc_thomas_setup(c, vars[q])) return -1;
     }
     if (tc_planes(c, nv, vars, a, b, false)) return -1;
+    const long long modes = (long long)nx * ny;
     if (c->nranks == 1) {
-        if (tc_thomas(c, nv, vars, b, (long long)nx * ny)) return -1;
+        if (tc_thomas(c, nv, vars, b, modes, nullptr)) return -1;
     } else {
-        // the z lines cross the slabs: transpose to pencils (all z, a chunk of y), sweep, transpose back
-        if (dist_setup(c)) return -1;
-        TfbChunks ch;
-        ch.n = c->nranks;
-        for (int r = 0; r <= c->nranks; r++) ch.j0[r] = s->j0s[r];
-        for (int r = 0; r < c->nranks; r++) ch.dsp[r] = s->a2a_dsp_slab[r];
-        const int cyme = s->j0s[c->rank + 1] - s->j0s[c->rank];
-        const long long ncell = (long long)nx * ny * nzl;
-        float *pen = (float*)s->pen[0], *sbuf = (float*)s->sbuf, *rbuf = (float*)s->rbuf;
-        for (int q = 0; q < nv; q++) {
-            k_a2a_pack<true, float><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, b[q], sbuf);
-            TFB_LAUNCHED();
-            if (tfb_alltoallv_bytes(c, sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, pen, s->a2a_cnt_pen, s->a2a_dsp_pen, 4)) return -1;
-            float* px[1] = {pen};
-            if (tc_thomas(c, 1, vars + q, px, (long long)nx * cyme)) return -1;
-            if (tfb_alltoallv_bytes(c, pen, s->a2a_cnt_pen, s->a2a_dsp_pen, rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, 4)) return -1;
-            k_a2a_pack<false, float><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nzl, ch, b[q], rbuf);
-            TFB_LAUNCHED();
+        // the z lines cross the slabs: local sweeps, one all-gather of the interface values, correction with the spikes
+        const int G = c->nranks;
+        if (!s->sp_send) {
+            TFB_CUDA(cudaMalloc(&s->sp_send, sizeof(float) * TFB_MAXVAR * 2 * (size_t)modes));
+            TFB_CUDA(cudaMalloc(&s->sp_recv, sizeof(float) * TFB_MAXVAR * 2 * (size_t)modes * G));
         }
-        (void)nz;
+        if (tc_thomas(c, nv, vars, b, modes, s->sp_send)) return -1;
+        if (tfb_allgather_f32(c, s->sp_send, s->sp_recv, (size_t)nv * 2 * modes)) return -1;
+        tfbtc::SpikeFixArgs fa{};
+        for (int q = 0; q < nv; q++) {
+            const FdmVar& f = s->var[vars[q]];
+            fa.x[q] = b[q]; fa.v[q] = f.sp_v; fa.w[q] = f.sp_w; fa.weights[q] = f.sp_weights; fa.mz[q] = f.mz_local;
+        }
+        fa.gathered = s->sp_recv; fa.narr = nv; fa.G = G; fa.modes = modes;
+        dim3 grid((unsigned)((modes + 127) / 128), nv);
+        tfbtc::tfb_spike_fix_kernel<<<grid, 128, 0, c->stream>>>(fa);
+        TFB_LAUNCHED();
+        TFB_CUDA(cudaGetLastError());
+        (void)nz; (void)nzl;
     }
     return tc_planes(c, nv, vars, b, out, true);
 }
@@ -874,6 +934,14 @@ static int gell_refresh(tfb_ctx* c, tfb_mat* m) {
     int misfit = 0;
     TFB_CUDA(cudaMemcpyAsync(&misfit, s->gell_misfit, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->nranks > 1) {      // every rank must take the same path: the fused head contains a halo exchange
+        double mf = misfit;
+        TFB_CUDA(cudaMemcpyAsync(s->d_scal + 100, &mf, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (tfb_allreduce_sum(c, s->d_scal + 100, 1)) return -1;
+        TFB_CUDA(cudaMemcpyAsync(&mf, s->d_scal + 100, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(cudaStreamSynchronize(c->stream));
+        misfit = mf != 0.0;
+    }
     s->gell_ok = misfit == 0;
     s->gell_owner = m; s->gell_version = m->version;
     return 0;
@@ -906,8 +974,11 @@ static int precond_fused_tc(tfb_ctx* c, int prow, const double* r, double* z) {
     ia.nv = dim; ia.dof = dof; ia.nx = c->desc.nx; ia.ny = c->desc.ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
     const unsigned nb = vec_blocks(ncell);
     tfbtc::tfb_tc_dp_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
+    TFB_LAUNCHED();
+    // the gradient of the top plane reaches into the slab above: its first plane of dp
+    if (tfb_halo_up_f32(c, s->dp32, s->dp32 + ncell, (size_t)c->desc.nx * c->desc.ny)) return -1;
     tfbtc::tfb_tc_pre_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
-    TFB_LAUNCHED(); TFB_LAUNCHED();
+    TFB_LAUNCHED();
     if (fdm_solve_tc(c, dim, vars, a, b, a)) return -1;
     tfbtc::tfb_tc_post_kernel<<<nb, 256, 0, c->stream>>>(ia, s->dp32, dim, r, z);
     TFB_LAUNCHED();
@@ -974,9 +1045,9 @@ static int poisson_solve(tfb_ctx* c, int pvar, long long pin_cell, FT* rp, FT* t
     return 0;
 }
 
-template <class BT> static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d_out);
+template <class BT> static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d_out, long long ld = 0);
 template <class BT> static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2 = nullptr,
-                                          const double* base = nullptr, double bscale = 1.0, double wscale = 1.0);
+                                          const double* base = nullptr, double bscale = 1.0, double wscale = 1.0, long long ld = 0);
 template <class BT> __global__ void k_store_scaled(long long n, const double* __restrict__ scal, int idx, const double* __restrict__ x, BT* __restrict__ y);
 
 // y = x on the rows of the selected variables, 0 elsewhere
@@ -1338,7 +1409,7 @@ static int apply_precond_t(tfb_ctx* c, tfb_mat* m, int prow, const double* r, do
     FT *c0 = (FT*)s->comp[0], *c1 = (FT*)s->comp[1], *c2 = (FT*)s->comp[2];
     double *ta = s->vec[0], *tb = s->vec[1], *tc = s->vec[2], *ru = s->vec[3];
     const unsigned vb = vec_blocks(ncell);
-    if (s->schur_mass && s->precond_tc && s->gell_ok && s->inner_its <= 0 && !s->joint_on && !smask && c->nranks == 1)
+    if (s->schur_mass && s->precond_tc && s->gell_ok && s->inner_its <= 0 && !s->joint_on && !smask)
         return precond_fused_tc(c, prow, r, z);
     TFB_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * n, c->stream));
     // ---- scalars: s = At^-1 r_s ; ru = r - B s (velocity rows) ----
@@ -1497,6 +1568,7 @@ extern "C" int tfb_fdm_set_pencil(tfb_ctx* c, int var, int axis, int m, const do
     std::vector<double> tab((size_t)4 * n, 0.0);
     for (int i = 0; i < m; i++) { tab[i] = lower[i]; tab[n + i] = diag[i]; tab[2 * n + i] = upper[i]; tab[3 * n + i] = mass[i]; }
     TFB_CUDA(cudaMemcpy(f.pencil[axis], tab.data(), sizeof(double) * 4 * n, cudaMemcpyHostToDevice));
+    f.pencil_h[axis] = tab;
     f.th_dirty = true;
     return 0;
 }
@@ -1535,8 +1607,13 @@ static int ensure_buffers(tfb_ctx* c, int krylov, bool single = false) {
         for (auto& d : diag) if (d == 0.0) d = 1.0;
         TFB_CUDA(cudaMemcpy(s->d_mass, diag.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
         for (auto& p : s->comp) TFB_CUDA(cudaMalloc(&p, sizeof(double) * ncell));
-        for (auto& p : s->vec) TFB_CUDA(cudaMalloc(&p, sizeof(double) * n));
-        TFB_CUDA(cudaMalloc(&s->d_scal, sizeof(double) * 64));
+        for (int i = 0; i < 8; i++) {
+            const size_t len = (size_t)n + 2 * (size_t)c->plane_rows;
+            TFB_CUDA(cudaMalloc(&s->vec_base[i], sizeof(double) * len));
+            TFB_CUDA(cudaMemset(s->vec_base[i], 0, sizeof(double) * len));
+            s->vec[i] = s->vec_base[i] + c->plane_rows;
+        }
+        TFB_CUDA(cudaMalloc(&s->d_scal, sizeof(double) * 128));
     }
     if (krylov > s->cap || (krylov > 0 && single != s->basis_single)) {
         cudaFree(s->d_V); cudaFree(s->d_Z); cudaFree(s->d_h);
@@ -1545,9 +1622,11 @@ static int ensure_buffers(tfb_ctx* c, int krylov, bool single = false) {
         size_t freeb = 0, total = 0;
         TFB_CUDA(cudaMemGetInfo(&freeb, &total));
         const size_t vbytes = single ? sizeof(float) : sizeof(double);
-        const size_t need = (size_t)n * ((size_t)krylov + 1) * vbytes + sizeof(double) * (size_t)n * krylov;
+        const size_t nn = (size_t)n + 2 * (size_t)c->plane_rows;      // room for the halo planes of every vector (idr_run)
+        const size_t need = nn * ((size_t)krylov + 1) * vbytes + sizeof(double) * (size_t)n * krylov;
         TFB_CHECK(need < freeb * 0.9, "Krylov basis does not fit in device memory; lower 'Restart'");
-        TFB_CUDA(cudaMalloc(&s->d_V, vbytes * (size_t)n * (krylov + 1)));
+        TFB_CUDA(cudaMalloc(&s->d_V, vbytes * nn * (krylov + 1)));
+        s->dv_stride = 0;
         s->basis_single = single;
         TFB_CUDA(cudaMalloc(&s->d_Z, sizeof(double) * (size_t)n * krylov));
         TFB_CUDA(cudaMalloc(&s->d_h, sizeof(double) * (krylov + 8)));
@@ -1558,13 +1637,14 @@ static int ensure_buffers(tfb_ctx* c, int krylov, bool single = false) {
 
 // h[0..nv) = V^T w   (one pass over the basis)
 template <class BT>
-static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d_out) {
+static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d_out, long long ld) {
     const long long n = c->n_local;
+    if (ld <= 0) ld = n;
     TFB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * nv, c->stream));
     const unsigned nb = (unsigned)std::min<long long>((n + 1023) / 1024, 148 * 8);
     for (int v0 = 0; v0 < nv; v0 += 512) {     // 8 warps x 512 partial sums = 32 KB of shared memory
         const int cnt = std::min(512, nv - v0);
-        k_all_dots<BT><<<nb, 256, sizeof(double) * 8 * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, w, d_out + v0);
+        k_all_dots<BT><<<nb, 256, sizeof(double) * 8 * cnt, c->stream>>>(n, V + (size_t)v0 * ld, ld, cnt, w, d_out + v0);
         TFB_LAUNCHED();
     }
     TFB_CUDA(cudaGetLastError());
@@ -1573,18 +1653,19 @@ static int multi_dot(tfb_ctx* c, const BT* V, int nv, const double* w, double* d
 // w += sign * V h   (one pass over the basis); d_nrm2 (optional, zeroed here) receives the LOCAL |w|^2
 template <class BT>
 static int multi_axpy(tfb_ctx* c, const BT* V, int nv, const double* d_h, double sign, double* w, double* d_nrm2,
-                      const double* base, double bscale, double wscale) {
+                      const double* base, double bscale, double wscale, long long ld) {
     const long long n = c->n_local;
+    if (ld <= 0) ld = n;
     TFB_CHECK((!base && wscale == 1.0) || nv <= 2048, "the general form of multi_axpy is single-chunk");
     if (nv == 0 && (base || wscale != 1.0)) {     // no basis vectors: only the scaling / base term
-        k_all_axpy<BT><<<vec_blocks(n), 256, sizeof(double), c->stream>>>(n, V, n, 0, d_h, sign, w, d_nrm2, base, bscale, wscale);
+        k_all_axpy<BT><<<vec_blocks(n), 256, sizeof(double), c->stream>>>(n, V, ld, 0, d_h, sign, w, d_nrm2, base, bscale, wscale);
         TFB_LAUNCHED();
     }
     if (d_nrm2) TFB_CUDA(cudaMemsetAsync(d_nrm2, 0, sizeof(double), c->stream));
     for (int v0 = 0; v0 < nv; v0 += 2048) {
         const int cnt = std::min(2048, nv - v0);
         const bool last = v0 + cnt >= nv;
-        k_all_axpy<BT><<<vec_blocks(n), 256, sizeof(double) * cnt, c->stream>>>(n, V + (size_t)v0 * n, n, cnt, d_h + v0, sign, w,
+        k_all_axpy<BT><<<vec_blocks(n), 256, sizeof(double) * cnt, c->stream>>>(n, V + (size_t)v0 * ld, ld, cnt, d_h + v0, sign, w,
                                                                           last ? d_nrm2 : nullptr, base, bscale, wscale);
         TFB_LAUNCHED();
     }
@@ -1655,6 +1736,7 @@ static int fgmres_run(tfb_mat* m, const double* b, double* x, const tfb_solve_op
     constexpr bool SINGLE = sizeof(BT) == 4;
     if (ensure_buffers(c, mk, SINGLE)) return -1;
     tfb_solver_state* s = c->solver;
+    s->dv_stride = 0;
     const int prow = o->pressure_row;
     cudaEvent_t e0, e1;
     TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
@@ -1841,6 +1923,7 @@ static int bicgstab_run(tfb_mat* m, const double* b, double* x, const tfb_solve_
     const long long n = c->n_local;
     if (ensure_buffers(c, 5, false)) return -1;
     tfb_solver_state* s = c->solver;
+    s->dv_stride = 0;
     const int prow = o->pressure_row;
     cudaEvent_t e0, e1;
     TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
@@ -2027,11 +2110,15 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
     double* d_x = s->vec[5];
     double* vh = s->vec[6];     // preconditioned vector
     double* tmp = s->vec[7];
-    double* G = s->d_V;                       // S vectors
-    double* U = G + (size_t)S * n;            // S vectors
-    double* r = U + (size_t)S * n;            // r and t adjacent: one fused pass gives (r.t, t.t)
-    double* t = r + n;
-    double* v = t + n;
+    // every vector of the recurrence sits between two planes of slack (stride nn), so each can be the input of a
+    // z-slab operator product without a ghosted copy
+    const long long nn = n + 2 * c->plane_rows;
+    s->dv_stride = nn; s->dv_count = 2 * S + 3;
+    double* G = s->d_V + c->plane_rows;       // S vectors
+    double* U = G + (size_t)S * nn;           // S vectors
+    double* r = U + (size_t)S * nn;           // r and t adjacent: one fused pass gives (r.t, t.t)
+    double* t = r + nn;
+    double* v = t + nn;
     double* d_dot = s->d_h;                   // [0,S) dots, [S,2S) coefficients, [2S] norm, [2S+1, 2S+3) pair
     double* d_coef = s->d_h + S;
     double* d_nrm = s->d_h + 2 * S;
@@ -2123,7 +2210,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
         if (cycles > 0 && relres > 0.5 * prev_true) { if (++stalled >= stall_limit) break; } else stalled = 0;
         prev_true = std::min(prev_true, relres);
         cycles++;
-        TFB_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)2 * S * n, c->stream));   // G and U
+        TFB_CUDA(cudaMemsetAsync(G - c->plane_rows, 0, sizeof(double) * (size_t)2 * S * nn, c->stream));   // G and U
         std::fill(M.begin(), M.end(), 0.0);
         for (int i = 0; i < S; i++) Mx(i, i) = 1.0;
         double om = 1.0;
@@ -2141,12 +2228,12 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
                 if (breakdown) break;
                 // v = r - sum_{i>=k} c_i G_i
                 if (put(d_coef, cf.data() + k, S - k)) return -1;
-                if (multi_axpy<double>(c, G + (size_t)k * n, S - k, d_coef, -1.0, v, nullptr, r, 1.0, 0.0)) return -1;
+                if (multi_axpy<double>(c, G + (size_t)k * nn, S - k, d_coef, -1.0, v, nullptr, r, 1.0, 0.0, nn)) return -1;
                 if (precond(v, vh, 0)) return -1;
                 // U_k = om * vh + sum_{i>=k} c_i U_i   (the old U_k is part of the sum)
-                double* Uk = U + (size_t)k * n;
-                double* Gk = G + (size_t)k * n;
-                if (multi_axpy<double>(c, Uk + n, S - k - 1, d_coef + 1, 1.0, Uk, nullptr, vh, om, cf[k])) return -1;
+                double* Uk = U + (size_t)k * nn;
+                double* Gk = G + (size_t)k * nn;
+                if (multi_axpy<double>(c, Uk + nn, S - k - 1, d_coef + 1, 1.0, Uk, nullptr, vh, om, cf[k], nn)) return -1;
                 if (spmv(c, m, Uk, Gk, prow)) return -1;                                            // G_k = A U_k
                 its++;
                 // bi-orthogonalise against p_0..p_{k-1}: all dots in one pass, recursion on the host
@@ -2163,8 +2250,8 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
                 }
                 if (k > 0) {
                     if (put(d_coef, al.data(), k)) return -1;
-                    if (multi_axpy<double>(c, G, k, d_coef, -1.0, Gk)) return -1;
-                    if (multi_axpy<double>(c, U, k, d_coef, -1.0, Uk)) return -1;
+                    if (multi_axpy<double>(c, G, k, d_coef, -1.0, Gk, nullptr, nullptr, 1.0, 1.0, nn)) return -1;
+                    if (multi_axpy<double>(c, U, k, d_coef, -1.0, Uk, nullptr, nullptr, 1.0, 1.0, nn)) return -1;
                 }
                 if (Mx(k, k) == 0.0) { breakdown = true; break; }
                 const double beta = f[k] / Mx(k, k);
@@ -2187,7 +2274,7 @@ static int idr_run(tfb_mat* m, const double* b, double* x, const tfb_solve_opts*
             if (spmv(c, m, vh, t, prow)) return -1;
             its++;
             double pr2[2], rn2 = 0.0;
-            if (multi_dot<double>(c, r, 2, t, d_pair)) return -1;                                   // (r.t, t.t)
+            if (multi_dot<double>(c, r, 2, t, d_pair, nn)) return -1;                               // (r.t, t.t)
             if (multi_dot<double>(c, r, 1, r, d_nrm)) return -1;
             if (fetch(pr2, d_pair, 2) || fetch(&rn2, d_nrm, 1)) return -1;
             if (pr2[1] == 0.0) { breakdown = true; break; }
