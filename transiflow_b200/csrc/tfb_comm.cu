@@ -167,3 +167,16 @@ int tfb_halo_up_f32(tfb_ctx* c, const float* first_plane, float* ghost_above, si
     TFB_LAUNCHED();
     return 0;
 }
+
+// the same for an fp64 plane (halo above the slab of a vector that has its slack planes in place)
+int tfb_halo_up_f64(tfb_ctx* c, const double* first_plane, double* ghost_above, size_t count) {
+    if (c->nranks <= 1) return 0;
+    TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    TFB_NCCL(nccl.GroupStart());
+    if (c->rank > 0) TFB_NCCL(nccl.Send(first_plane, count, NCCL_FLOAT64, c->rank - 1, comm, c->stream));
+    if (c->rank < c->nranks - 1) TFB_NCCL(nccl.Recv(ghost_above, count, NCCL_FLOAT64, c->rank + 1, comm, c->stream));
+    TFB_NCCL(nccl.GroupEnd());
+    TFB_LAUNCHED();
+    return 0;
+}

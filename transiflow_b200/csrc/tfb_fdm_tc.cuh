@@ -421,41 +421,53 @@ __global__ void __launch_bounds__(128) tfb_thomas_kernel(const ThomasArgs a) {
     const double coef = a.coef[q];
     const int mz = a.mz[q];
     const long long st = a.modes;
+    // software pipeline: the loads of block b+1 are issued before the dependent chain of block b runs
     float rp = 0.f;
-    for (int k0 = 0; k0 < mz; k0 += TB) {
-        float xv[TB], iv[TB], lv[TB];
+    float xv[TB], iv[TB], lv[TB], xn_[TB], in_[TB], ln_[TB];
+    auto load_fwd = [&](int k0, float (&xx)[TB], float (&ii)[TB], float (&ll)[TB]) {
 #pragma unroll
         for (int t = 0; t < TB; t++) {
             const int k = k0 + t;
             const bool ok = k < mz;
-            xv[t] = ok ? x[(long long)k * st] : 0.f;
-            iv[t] = ok ? inv[(long long)k * st] : 0.f;
-            lv[t] = (ok && k > 0) ? (float)(coef * lo[k]) : 0.f;
+            xx[t] = ok ? x[(long long)k * st] : 0.f;
+            ii[t] = ok ? inv[(long long)k * st] : 0.f;
+            ll[t] = (ok && k > 0) ? (float)(coef * lo[k]) : 0.f;
         }
+    };
+    load_fwd(0, xv, iv, lv);
+    for (int k0 = 0; k0 < mz; k0 += TB) {
+        if (k0 + TB < mz) load_fwd(k0 + TB, xn_, in_, ln_);
 #pragma unroll
         for (int t = 0; t < TB; t++) {
             rp = (xv[t] - lv[t] * rp) * iv[t];
             if (k0 + t < mz) x[(long long)(k0 + t) * st] = rp;
         }
+#pragma unroll
+        for (int t = 0; t < TB; t++) { xv[t] = xn_[t]; iv[t] = in_[t]; lv[t] = ln_[t]; }
     }
     float xn = 0.f, xlast = 0.f;
-    for (int k1 = mz; k1 > 0; k1 -= TB) {
-        float xv[TB], cv[TB];
+    auto load_bwd = [&](int k1, float (&xx)[TB], float (&cc)[TB]) {
 #pragma unroll
         for (int t = 0; t < TB; t++) {
             const int k = k1 - 1 - t;
             const bool ok = k >= 0;
-            xv[t] = ok ? x[(long long)k * st] : 0.f;
-            cv[t] = ok ? cp[(long long)k * st] : 0.f;
+            xx[t] = ok ? x[(long long)k * st] : 0.f;
+            cc[t] = ok ? cp[(long long)k * st] : 0.f;
         }
+    };
+    load_bwd(mz, xv, iv);
+    for (int k1 = mz; k1 > 0; k1 -= TB) {
+        if (k1 - TB > 0) load_bwd(k1 - TB, xn_, in_);
 #pragma unroll
         for (int t = 0; t < TB; t++) {
             if (k1 - 1 - t >= 0) {
-                xn = xv[t] - cv[t] * xn;
+                xn = xv[t] - iv[t] * xn;
                 x[(long long)(k1 - 1 - t) * st] = xn;
                 if (k1 - 1 - t == mz - 1) xlast = xn;
             }
         }
+#pragma unroll
+        for (int t = 0; t < TB; t++) { xv[t] = xn_[t]; iv[t] = in_[t]; }
     }
     if (a.iface) {
         a.iface[((long long)q * 2 + 0) * st + m] = xn;       // first unknown (computed last)
@@ -711,6 +723,72 @@ __global__ void __launch_bounds__(256) tfb_tc_post_kernel(const IntArgs a, const
             z[row] = wall ? -r[row] : (double)a.comp[v][cell];
         }
         z[cell * a.dof + pvar] = (double)dp[cell];
+    }
+}
+
+// Vectorised head / tail for the 3-D velocity-pressure layout (dof = 4): blockIdx.y is the plane, one thread per cell moves
+// the cell's four fp64 values as two 16-byte accesses (a warp covers 1 KB contiguously) and the SoA arrays coalesced;
+// index arithmetic is 32-bit with one division per cell.  The head recomputes the pressure update of the neighbouring
+// cells from r_p directly (no separate dp pass; `r` must have its halo plane above the slab in place on z-slabs).
+// ihx/ihy/ihz are reciprocal cell widths (1 / |cell| = ihx ihy ihz).
+struct Pre4Args {
+    float* comp[3];
+    float* dp;
+    const float* gval;
+    const double* ihx; const double* ihy; const double* ihz;
+    double gamma;
+    long long ncell, pin_local;
+    int nx, ny, k0;
+};
+__global__ void __launch_bounds__(256) tfb_tc_pre4_kernel(const Pre4Args a, const double* __restrict__ r) {
+    const unsigned plane_cells = (unsigned)a.nx * (unsigned)a.ny;
+    const unsigned kl = blockIdx.y;
+    const long long cell0 = (long long)kl * plane_cells;
+    const double ihz = a.ihz[a.k0 + kl], ihz1 = a.ihz[a.k0 + kl + 1];
+    const double2* __restrict__ r2 = reinterpret_cast<const double2*>(r);
+    float* __restrict__ c0 = a.comp[0];
+    float* __restrict__ c1 = a.comp[1];
+    float* __restrict__ c2 = a.comp[2];
+    for (unsigned pc = blockIdx.x * blockDim.x + threadIdx.x; pc < plane_cells; pc += gridDim.x * blockDim.x) {
+        const unsigned j = pc / (unsigned)a.nx, i = pc - j * (unsigned)a.nx;
+        const long long cell = cell0 + pc;
+        const double2 uv = r2[cell * 2], wp = r2[cell * 2 + 1];
+        const double ihxy = a.ihx[i] * a.ihy[j];
+        auto dp_of = [&](long long cc, double rp, double ivol) { return (double)(float)(cc == a.pin_local ? -rp : a.gamma * rp * ivol); };
+        const double d0 = dp_of(cell, wp.y, ihxy * ihz);
+        a.dp[cell] = (float)d0;
+        const float* g = a.gval + cell;
+        const float gu0 = g[0], gu1 = g[a.ncell], gv0 = g[2 * a.ncell], gv1 = g[3 * a.ncell], gw0 = g[4 * a.ncell], gw1 = g[5 * a.ncell];
+        double au = uv.x - (double)gu0 * d0, av = uv.y - (double)gv0 * d0, aw = wp.x - (double)gw0 * d0;
+        if (gu1 != 0.f) au -= (double)gu1 * dp_of(cell + 1, r[(cell + 1) * 4 + 3], (a.ihx[i + 1] * a.ihy[j]) * ihz);
+        if (gv1 != 0.f) av -= (double)gv1 * dp_of(cell + a.nx, r[(cell + a.nx) * 4 + 3], (a.ihx[i] * a.ihy[j + 1]) * ihz);
+        if (gw1 != 0.f) aw -= (double)gw1 * dp_of(cell + plane_cells, r[(cell + plane_cells) * 4 + 3], ihxy * ihz1);
+        c0[cell] = (float)au; c1[cell] = (float)av; c2[cell] = (float)aw;
+    }
+}
+__global__ void __launch_bounds__(256) tfb_tc_post4_kernel(const IntArgs a, const float* __restrict__ dp,
+                                                           const double* __restrict__ r, double* __restrict__ z) {
+    const unsigned plane_cells = (unsigned)a.nx * (unsigned)a.ny;
+    const unsigned kl = blockIdx.y;
+    const int k = a.k0 + (int)kl;
+    const long long cell0 = (long long)kl * plane_cells;
+    double2* __restrict__ z2 = reinterpret_cast<double2*>(z);
+    const float* __restrict__ c0 = a.comp[0];
+    const float* __restrict__ c1 = a.comp[1];
+    const float* __restrict__ c2 = a.comp[2];
+    for (unsigned pc = blockIdx.x * blockDim.x + threadIdx.x; pc < plane_cells; pc += gridDim.x * blockDim.x) {
+        const unsigned j = pc / (unsigned)a.nx, i = pc - j * (unsigned)a.nx;
+        const long long cell = cell0 + pc;
+        const bool wu = (int)i >= a.mx[0] || (int)j >= a.my[0] || k >= a.mz[0];
+        const bool wv = (int)i >= a.mx[1] || (int)j >= a.my[1] || k >= a.mz[1];
+        const bool ww = (int)i >= a.mx[2] || (int)j >= a.my[2] || k >= a.mz[2];
+        double2 uv, wp;
+        uv.x = wu ? -r[cell * 4 + 0] : (double)c0[cell];
+        uv.y = wv ? -r[cell * 4 + 1] : (double)c1[cell];
+        wp.x = ww ? -r[cell * 4 + 2] : (double)c2[cell];
+        wp.y = (double)dp[cell];
+        z2[cell * 2] = uv;
+        z2[cell * 2 + 1] = wp;
     }
 }
 #endif  // __CUDACC__

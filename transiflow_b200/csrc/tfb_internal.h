@@ -85,5 +85,6 @@ int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
 int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
                   double* recv, const long long* rcount, const long long* rdispl);
 int tfb_halo_up_f32(tfb_ctx* c, const float* first_plane, float* ghost_above, size_t count);
+int tfb_halo_up_f64(tfb_ctx* c, const double* first_plane, double* ghost_above, size_t count);
 int tfb_allgather_f32(tfb_ctx* c, const float* send, float* recv, size_t count);
 void tfb_solver_free(tfb_solver_state* s);

@@ -122,6 +122,7 @@ struct tfb_solver_state {
     float* tc32[2] = {nullptr, nullptr};   // fp32 SoA work arrays, TFB_MAXVAR x ncell (pencil-sized with z-slabs) each
     long long tc32_cap = 0;
     // fused head / tail of the scaled-mass preconditioner: two-slot copy of the gradient block, pressure update
+    double* d_ih[3] = {nullptr, nullptr, nullptr};   // reciprocal cell widths per axis
     float* gell = nullptr;        // [dim][2][ncell]
     float* dp32 = nullptr;        // ncell + one plane
     int* gell_misfit = nullptr;
@@ -153,6 +154,7 @@ void tfb_solver_free(tfb_solver_state* s) {
     cudaFree(s->sp_send); cudaFree(s->sp_recv);
     for (auto& p : s->tc32) cudaFree(p);
     cudaFree(s->gell); cudaFree(s->dp32); cudaFree(s->gell_misfit);
+    for (auto p : s->d_ih) cudaFree(p);
     for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
     cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab);
     cudaFree(s->d_mass);
@@ -870,8 +872,17 @@ static int tc_thomas(tfb_ctx* c, int nv, const int* vars, float* const* x, long 
         a.x[q] = x[q]; a.inv[q] = f.th_inv; a.cp[q] = f.th_cp; a.zk[q] = f.pencil[2]; a.coef[q] = f.coef; a.mz[q] = f.mz_local;
     }
     a.narr = nv; a.nz = c->desc.nz; a.k0 = c->desc.k0; a.modes = modes; a.iface = iface;
-    dim3 grid((unsigned)((modes + 127) / 128), nv);
-    tfbtc::tfb_thomas_kernel<8><<<grid, 128, 0, c->stream>>>(a);
+    static int tb = -1, bs = 128;
+    if (tb < 0) {
+        const char* e = getenv("TFB_THOMAS_TB");
+        tb = e ? atoi(e) : 8;
+        if (const char* b2 = getenv("TFB_THOMAS_BS")) bs = atoi(b2);
+    }
+    dim3 grid((unsigned)((modes + bs - 1) / bs), nv);
+    if (tb == 16) tfbtc::tfb_thomas_kernel<16><<<grid, bs, 0, c->stream>>>(a);
+    else if (tb == 32) tfbtc::tfb_thomas_kernel<32><<<grid, bs, 0, c->stream>>>(a);
+    else if (tb == 4) tfbtc::tfb_thomas_kernel<4><<<grid, bs, 0, c->stream>>>(a);
+    else tfbtc::tfb_thomas_kernel<8><<<grid, bs, 0, c->stream>>>(a);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -925,6 +936,15 @@ static int gell_refresh(tfb_ctx* c, tfb_mat* m) {
         TFB_CUDA(cudaMalloc(&s->dp32, sizeof(float) * (size_t)(ncell + plane)));
         TFB_CUDA(cudaMemset(s->dp32, 0, sizeof(float) * (size_t)(ncell + plane)));
         TFB_CUDA(cudaMalloc(&s->gell_misfit, sizeof(int)));
+        const int nax[3] = {c->desc.nx, c->desc.ny, c->desc.nz};
+        for (int ax = 0; ax < 3; ax++) {      // 1 / (cell width): row 0 of the metric table of the axis
+            std::vector<double> h(nax[ax]);
+            TFB_CUDA(cudaMemcpy(h.data(), c->d_met[ax], sizeof(double) * nax[ax], cudaMemcpyDeviceToHost));
+            for (auto& x : h) x = 1.0 / x;
+            TFB_CUDA(cudaMalloc(&s->d_ih[ax], sizeof(double) * (nax[ax] + 1)));
+            TFB_CUDA(cudaMemset(s->d_ih[ax], 0, sizeof(double) * (nax[ax] + 1)));
+            TFB_CUDA(cudaMemcpy(s->d_ih[ax], h.data(), sizeof(double) * nax[ax], cudaMemcpyHostToDevice));
+        }
     }
     TFB_CUDA(cudaMemsetAsync(s->gell_misfit, 0, sizeof(int), c->stream));
     tfbtc::GEll g{s->gell, s->gell_misfit};
@@ -973,14 +993,32 @@ static int precond_fused_tc(tfb_ctx* c, int prow, const double* r, double* z) {
     pa.dof = dof; pa.dim = dim; pa.nx = c->desc.nx; pa.ny = c->desc.ny; pa.k0 = c->desc.k0;
     ia.nv = dim; ia.dof = dof; ia.nx = c->desc.nx; ia.ny = c->desc.ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
     const unsigned nb = vec_blocks(ncell);
-    tfbtc::tfb_tc_dp_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
-    TFB_LAUNCHED();
-    // the gradient of the top plane reaches into the slab above: its first plane of dp
-    if (tfb_halo_up_f32(c, s->dp32, s->dp32 + ncell, (size_t)c->desc.nx * c->desc.ny)) return -1;
-    tfbtc::tfb_tc_pre_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
-    TFB_LAUNCHED();
+    // dof = 4 and an input vector that can take its halo plane in place: row-mapped head and tail, no separate dp pass
+    const bool rowmapped = dof == 4 && dim == 3 && (c->nranks == 1 || ghost_capable(c, r));
+    if (rowmapped) {
+        if (c->nranks > 1 && tfb_halo_up_f64(c, r, const_cast<double*>(r) + c->n_local, (size_t)c->plane_rows)) return -1;
+        tfbtc::Pre4Args p4{};
+        for (int v = 0; v < 3; v++) p4.comp[v] = a[v];
+        p4.dp = s->dp32; p4.gval = s->gell; p4.ihx = s->d_ih[0]; p4.ihy = s->d_ih[1]; p4.ihz = s->d_ih[2];
+        p4.gamma = s->gamma; p4.ncell = ncell; p4.pin_local = pa.pin_local;
+        p4.nx = c->desc.nx; p4.ny = c->desc.ny; p4.k0 = c->desc.k0;
+        const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(((long long)c->desc.nx * c->desc.ny + 255) / 256, 64));
+        tfbtc::tfb_tc_pre4_kernel<<<dim3(gx, c->nzl), 256, 0, c->stream>>>(p4, r);
+        TFB_LAUNCHED();
+    } else {
+        tfbtc::tfb_tc_dp_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
+        TFB_LAUNCHED();
+        // the gradient of the top plane reaches into the slab above: its first plane of dp
+        if (tfb_halo_up_f32(c, s->dp32, s->dp32 + ncell, (size_t)c->desc.nx * c->desc.ny)) return -1;
+        tfbtc::tfb_tc_pre_kernel<<<nb, 256, 0, c->stream>>>(pa, r);
+        TFB_LAUNCHED();
+    }
     if (fdm_solve_tc(c, dim, vars, a, b, a)) return -1;
-    tfbtc::tfb_tc_post_kernel<<<nb, 256, 0, c->stream>>>(ia, s->dp32, dim, r, z);
+    if (rowmapped) {
+        const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>(((long long)c->desc.nx * c->desc.ny + 255) / 256, 64));
+        tfbtc::tfb_tc_post4_kernel<<<dim3(gx, c->nzl), 256, 0, c->stream>>>(ia, s->dp32, r, z);
+    }
+    else tfbtc::tfb_tc_post_kernel<<<nb, 256, 0, c->stream>>>(ia, s->dp32, dim, r, z);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
@@ -2036,11 +2074,11 @@ static int bicgstab_run(tfb_mat* m, const double* b, double* x, const tfb_solve_
 }
 
 
-// Shadow vectors of IDR(s) are never stored: entry (vector j, GLOBAL row g) is byte j%8 of a 64-bit hash of (g, j/8),
-// mapped to [-127.5, 127.5], so a z-slab run uses the same shadow space as a single-GPU run and the s dot products
-// P^T w cost one pass over w instead of s + 1 vector reads (and s vectors of HBM).
-__device__ __forceinline__ unsigned long long tfb_shadow_hash(unsigned long long grow, unsigned group) {
-    unsigned long long h = grow * 0x9E3779B97F4A7C15ull + (unsigned long long)(group + 1) * 0xD1B54A32D192ED03ull;
+// Shadow vectors of IDR(s) are never stored: entry (vector j, GLOBAL row g) is +1 or -1 according to bit j of a 64-bit hash
+// of g (Rademacher vectors), so a z-slab run uses the same shadow space as a single-GPU run and the s dot products P^T w
+// cost one pass over w -- s sign flips and additions per entry -- instead of s + 1 vector reads (and s vectors of HBM).
+__device__ __forceinline__ unsigned long long tfb_shadow_hash(unsigned long long grow) {
+    unsigned long long h = grow * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
     h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
     return h;
 }
@@ -2050,16 +2088,18 @@ __global__ void __launch_bounds__(256) k_shadow_dots(long long n, long long row0
     double acc[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) acc[j] = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double wi = w[i];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double wv[4];
 #pragma unroll
-        for (int g = 0; g < NS / 8; g++) {
-            const unsigned long long h = tfb_shadow_hash((unsigned long long)(row0 + i), (unsigned)g);
+        for (int u = 0; u < 4; u++) wv[u] = i0 + u * stride < n ? w[i0 + u * stride] : 0.0;      // four loads in flight
 #pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const double pj = (double)(int)((h >> (8 * b)) & 0xffull) - 127.5;
-                acc[g * 8 + b] += pj * wi;
-            }
+        for (int u = 0; u < 4; u++) {
+            const long long wbits = __double_as_longlong(wv[u]);
+            const unsigned long long h = tfb_shadow_hash((unsigned long long)(row0 + i0 + u * stride));
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+                acc[j] += __longlong_as_double(wbits ^ (long long)(((h >> (2 * j + 7)) & 1ull) << 63));
         }
     }
     __shared__ double red[8][NS];
