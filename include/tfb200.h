@@ -75,6 +75,10 @@ int tfb_mat_set_values(tfb_mat* mat, const double* vals_in);   /* H2D */
  * (`jacobian(x) - mass / (theta * dt)`, TimeIntegration.py:58); d has one entry per local row.  Every row
  * with d != 0 must have a structural diagonal (all rows with mass do). dst may equal src. */
 int tfb_mat_add_diag(tfb_mat* dst, const tfb_mat* src, double alpha, const double* d);
+/* Tell the solver that `mat` is J + shift * M with M the mass matrix (what tfb_mat_add_diag produced for TimeIntegration's
+ * J - M / (theta dt) or a shifted eigenproblem J - sigma M): the fast-diagonalisation basis is M-orthonormal, so the block
+ * preconditioner solves the shifted diffusion operators exactly instead of ignoring the shift. */
+int tfb_mat_set_shift(tfb_mat* mat, double shift);
 
 /* Interface.rhs -> Discretization.rhs (Discretization.py:367-390); host in, host out. */
 int tfb_rhs(tfb_ctx* ctx, const double* state, double* out);

@@ -48,10 +48,12 @@ static int run_case(int rows, int cols, int m1, int m2, int narr, int nplanes, b
     auto kern = tfb_fdm_plane_kernel<KC, STAGES>;
     const size_t smem = plane_kernel_smem<KC, STAGES>();
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
     const long long items = (long long)narr * nplanes;
-    const int grid = (int)std::min<long long>(items, 148ll * std::max(occ, 1));
+    const int per_sm = getenv("TFB_PROTO_PER_SM") ? atoi(getenv("TFB_PROTO_PER_SM")) : std::max(std::min(occ, 2), 1);
+    const int grid = (int)std::min<long long>(items, 148ll * per_sm);
     kern<<<grid, THREADS, smem>>>(a);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

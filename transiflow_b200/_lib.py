@@ -48,7 +48,7 @@ class TfbSolveInfo(ctypes.Structure):
 EXPORTS = [
     'tfb_device_count', 'tfb_last_error', 'tfb_config_name', 'tfb_create', 'tfb_destroy', 'tfb_set_params',
     'tfb_sizes', 'tfb_get_pattern', 'tfb_mat_create', 'tfb_mat_destroy', 'tfb_mat_get_values',
-    'tfb_mat_set_values', 'tfb_mat_add_diag', 'tfb_rhs', 'tfb_jacobian', 'tfb_mass_diag', 'tfb_state_upload',
+    'tfb_mat_set_values', 'tfb_mat_add_diag', 'tfb_mat_set_shift', 'tfb_rhs', 'tfb_jacobian', 'tfb_mass_diag', 'tfb_state_upload',
     'tfb_assemble_resident', 'tfb_rhs_download', 'tfb_sync', 'tfb_event_record', 'tfb_event_elapsed_ms',
     'tfb_flush_l2', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_spmv_bench', 'tfb_solve', 'tfb_fdm_set', 'tfb_fdm_set_pencil', 'tfb_fdm_pin', 'tfb_joint_set', 'tfb_joint_apply', 'tfb_precond_apply', 'tfb_precond_apply_opts', 'tfb_nccl_unique_id', 'tfb_comm_init',
 ]

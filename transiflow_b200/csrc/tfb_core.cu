@@ -1,10 +1,14 @@
 // libtfb200 core: context management, fixed-pattern construction, assembly launches.
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_reduce.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "tfb_assemble.cuh"
 #include "tfb_spmv_march.cuh"
+
+struct TfbWiden { __host__ __device__ long long operator()(int v) const { return (long long)v; } };
 
 thread_local std::string g_tfb_err;
 int64_t g_tfb_launches = 0;
@@ -99,6 +103,7 @@ extern "C" void tfb_destroy(tfb_ctx* c) {
     cudaFree(c->d_row_ptr);
     cudaFree(c->d_col);
     cudaFree(c->d_flush);
+    cudaFree(c->d_massdiag);
     for (double* p : c->vals_pool) cudaFree(p);
     tfb_solver_free(c->solver);
     for (int e = 0; e < 16; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
@@ -156,6 +161,22 @@ static int build_pattern_t(tfb_ctx* c) {
     tfb_count_kernel<Cfg><<<nb, bs, 0, c->stream>>>(g, c->desc.k0, nrows, d_counts);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
+    {   // the device pattern is int32: refuse grids whose slab holds 2^31 or more structural non-zeros (a 330^3 cavity
+        // still fits in 180 GB) instead of letting the scan wrap around
+        long long* d_total = nullptr;
+        void* t2 = nullptr;
+        size_t t2_bytes = 0;
+        TFB_CUDA(cudaMalloc(&d_total, sizeof(long long)));
+        auto as64 = thrust::make_transform_iterator(d_counts, TfbWiden());
+        TFB_CUDA(cub::DeviceReduce::Sum(nullptr, t2_bytes, as64, d_total, nrows, c->stream));
+        TFB_CUDA(cudaMalloc(&t2, t2_bytes));
+        TFB_CUDA(cub::DeviceReduce::Sum(t2, t2_bytes, as64, d_total, nrows, c->stream));
+        long long total = 0;
+        TFB_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(t2); cudaFree(d_total);
+        if (total >= (long long)INT32_MAX) { cudaFree(d_counts); return tfb_fail(__FILE__, __LINE__, "tfb_build_pattern", "2^31 or more structural non-zeros per slab: split the grid over more GPUs"); }
+    }
     TFB_CUDA(cudaMalloc(&c->d_row_ptr, sizeof(int) * (nrows + 1)));
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -272,10 +293,10 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
     size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
     auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned configured_devices = 0;       // the attribute is per device
+    if (!((configured_devices >> (c->desc.device & 31)) & 1u)) {
         TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured_devices |= 1u << (c->desc.device & 31);
     }
     dim3 block(32, Cfg::DOF, TJ);
     dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, c->nzl);
@@ -305,10 +326,10 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     const int nlaunch = c->chunk0 >= 0 ? std::min(c->chunkn, nchunks - a.kc0) : nchunks;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
     auto kern = tfb_assemble_march_kernel<Cfg, DO_J, DO_F, TJ, KCH, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned configured_devices = 0;       // the attribute is per device
+    if (!((configured_devices >> (c->desc.device & 31)) & 1u)) {
         TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured_devices |= 1u << (c->desc.device & 31);
     }
     dim3 block(32, Cfg::DOF, TJ);
     dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, nlaunch);
@@ -385,7 +406,7 @@ extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f)
         int rc = tfb_halo_exchange(c, c->d_state);
         if (rc) return rc;
     }
-    if (do_j) m->version = tfb_next_version();
+    if (do_j) { m->version = tfb_next_version(); m->shift = 0.0; }
     return dispatch_assemble(c, m, do_j, do_f);
 }
 
@@ -449,6 +470,7 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
         TFB_CUDA(cudaEventRecord(c->ev_up[ch], c->s_h2d));
     }
     m->version = tfb_next_version();
+    m->shift = 0.0;
     for (int ch = 0; ch < nch; ch++) {
         const int p0 = ch * PCH, p1 = std::min(p0 + PCH, c->nzl);
         TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[ch], 0));
@@ -486,15 +508,14 @@ extern "C" int tfb_jacobian(tfb_ctx* c, const double* state, tfb_mat* m, double*
 extern "C" int tfb_mass_diag(tfb_ctx* c, double* diag_out) {
     TFB_CHECK(c && diag_out, "null argument");
     TFB_CUDA(cudaSetDevice(c->desc.device));
-    double* d = nullptr;
-    TFB_CUDA(cudaMalloc(&d, sizeof(double) * c->n_local));
+    if (!c->d_massdiag) TFB_CUDA(cudaMalloc(&c->d_massdiag, sizeof(double) * c->n_local));   // kept: callers ask repeatedly
+    double* d = c->d_massdiag;
     const int bs = 256;
     tfb_mass_kernel<<<(unsigned)((c->n_local + bs - 1) / bs), bs, 0, c->stream>>>(c->grid(), c->desc.k0, c->n_local, d);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     TFB_CUDA(cudaMemcpyAsync(diag_out, d, sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
     TFB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
     return 0;
 }
 
@@ -565,12 +586,30 @@ static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_globa
         a.prow_cell_k = (int)(cell / ((long long)c->desc.nx * c->desc.ny));
     }
     a.rowmask = rowmask; a.colmask = colmask;
+    if (c->plane_nnz < 0) {
+        // non-zeros of one plane away from the z walls (their CSR layouts are shifted copies of each other): difference
+        // of the first offsets of two consecutive planes without wall flags, if the slab holds such a pair
+        c->plane_nnz = 0;
+        const int nz = c->desc.nz, kfar2 = tfb_far2_index(nz);
+        for (int kl = 0; kl + 1 < c->nzl; kl++) {
+            const int k = c->desc.k0 + kl;
+            auto flagged = [&](int kk) { return kk == 0 || kk == nz - 1 || kk == kfar2; };
+            if (flagged(k) || flagged(k + 1)) continue;
+            int two[2] = {0, 0};
+            TFB_CUDA(cudaMemcpy(&two[0], c->d_row_ptr + (size_t)kl * c->plane_rows, sizeof(int), cudaMemcpyDeviceToHost));
+            TFB_CUDA(cudaMemcpy(&two[1], c->d_row_ptr + (size_t)(kl + 1) * c->plane_rows, sizeof(int), cudaMemcpyDeviceToHost));
+            c->plane_nnz = two[1] - two[0];
+            break;
+        }
+    }
+    a.plane_nnz = c->plane_nnz;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(true);
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device: set it when this instantiation meets a device for the first time
+    static unsigned configured_devices = 0;
+    if (!((configured_devices >> (c->desc.device & 31)) & 1u)) {
         TFB_CUDA(cudaFuncSetAttribute(tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TFB_CUDA(cudaFuncSetAttribute(tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured_devices |= 1u << (c->desc.device & 31);
     }
     dim3 block(32, Cfg::DOF, TJ);
     dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (c->nzl + TFB_KCH - 1) / TFB_KCH);
@@ -627,6 +666,13 @@ extern "C" int tfb_mat_add_diag(tfb_mat* dst, const tfb_mat* src, double alpha, 
     cudaFree(dd);
     cudaFree(dmiss);
     dst->version = tfb_next_version();
+    dst->shift = src->shift;
     TFB_CHECK(miss == 0, "a row with a non-zero diagonal update has no structural diagonal");
+    return 0;
+}
+
+extern "C" int tfb_mat_set_shift(tfb_mat* m, double shift) {
+    TFB_CHECK(m, "null argument");
+    m->shift = shift;
     return 0;
 }

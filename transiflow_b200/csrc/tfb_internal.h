@@ -34,6 +34,7 @@ struct tfb_ctx {
     int64_t plane_rows;         // nx*ny*dof
     int64_t n_local, n_global, row0;
     int64_t nnz = 0;
+    int plane_nnz = -1;         // structural non-zeros of a plane away from the z walls (-1: not determined yet)
     cudaStream_t stream = nullptr;
     // geometry on the device
     double* d_met[3] = {nullptr, nullptr, nullptr};
@@ -52,6 +53,7 @@ struct tfb_ctx {
     int* d_col = nullptr;       // nnz, GLOBAL columns
     bool have_pattern = false;
     // scratch for L2 flush
+    double* d_massdiag = nullptr;   // tfb_mass_diag result buffer
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
     cudaEvent_t ev[16] = {};
@@ -74,6 +76,7 @@ struct tfb_mat {
     tfb_ctx* ctx;
     double* d_vals = nullptr;
     uint64_t version = 0;       // bumped whenever values change (invalidates the preconditioner)
+    double shift = 0.0;         // the matrix is (an assembled Jacobian) + shift * (mass matrix): tfb_mat_set_shift
 };
 
 uint64_t tfb_next_version();

@@ -450,6 +450,12 @@ static int gell_refresh(tfb_ctx* c, tfb_mat* m);
 static int sub_refresh(tfb_ctx* c, tfb_mat* m, int prow) {
     tfb_solver_state* s = c->solver;
     const int dof = c->desc.dof, dim = c->desc.dim;
+    // J + shift * M: the diffusion sub-solves of every variable with mass carry the shift (exact in the M-orthonormal basis)
+    for (int v = 0; v < dof; v++) {
+        if (v == dim) continue;
+        FdmVar& f = s->var[v];
+        if (f.shift != m->shift) { f.shift = m->shift; f.th_dirty = true; }
+    }
     const unsigned velmask = (1u << dim) - 1u, pmask = 1u << dim, smask = ((1u << dof) - 1u) & ~(velmask | pmask);
     if (s->sub_prow != prow || !s->subG.row_ptr) {
         if (sub_build(c, s->subG, prow, velmask, pmask)) return -1;
@@ -556,13 +562,13 @@ k_axis_gemm(const FT* __restrict__ A, FT* __restrict__ C, const FT* __restrict__
 // starting at global (0, jofs, kofs); m* = active global extents
 template <class FT>
 __global__ void k_fdm_scale(int ex, int ey, int ez, int jofs, int kofs, int mx, int my, int mz, const double* __restrict__ lx,
-                            const double* __restrict__ ly, const double* __restrict__ lz, double coef, double thresh,
+                            const double* __restrict__ ly, const double* __restrict__ lz, double coef, double shift, double thresh,
                             FT* __restrict__ t) {
     const long long ncell = (long long)ex * ey * ez;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(c % ex), j = jofs + (int)((c / ex) % ey), k = kofs + (int)(c / ((long long)ex * ey));
         if (i < mx && j < my && k < mz) {
-            const double den = coef * (lx[i] + ly[j] + (lz ? lz[k] : 0.0));
+            const double den = coef * (lx[i] + ly[j] + (lz ? lz[k] : 0.0)) + shift;
             t[c] = fabs(den) > thresh ? (FT)((double)t[c] / den) : (FT)0;
         }
     }
@@ -710,7 +716,7 @@ static int fdm_solve(tfb_ctx* c, int v, FT* in, FT* tmp, FT* out) {
             std::swap(cur, oth);
         }
         k_fdm_scale<FT><<<vec_blocks(ncell), 256, 0, c->stream>>>(nx, ny, nz, 0, 0, mx, my, mz, f.lam[0], f.lam[1],
-                                                             three ? f.lam[2] : nullptr, f.coef, thresh, cur);
+                                                             three ? f.lam[2] : nullptr, f.coef, f.shift, thresh, cur);
         TFB_LAUNCHED();
         if (three) {
             if (axis_gemm(c, true, cur, oth, Q[2], mz, nx * ny, mz, mz, 1, (long long)nx * ny, 0, 1)) return -1;
@@ -733,7 +739,7 @@ static int fdm_solve(tfb_ctx* c, int v, FT* in, FT* tmp, FT* out) {
         if (tfb_alltoallv_bytes(c, sbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, pen0, s->a2a_cnt_pen, s->a2a_dsp_pen, (int)sizeof(FT))) return -1;
         if (axis_gemm(c, false, pen0, pen1, Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
         k_fdm_scale<FT><<<vec_blocks(npen), 256, 0, c->stream>>>(nx, cyme, nz, s->j0s[c->rank], 0, mx, my, mz, f.lam[0], f.lam[1],
-                                                            f.lam[2], f.coef, thresh, pen1);
+                                                            f.lam[2], f.coef, f.shift, thresh, pen1);
         TFB_LAUNCHED();
         if (axis_gemm(c, true, pen1, pen0, Q[2], mz, (int)lines, mz, mz, 1, lines, 0, 1)) return -1;
         if (tfb_alltoallv_bytes(c, pen0, s->a2a_cnt_pen, s->a2a_dsp_pen, rbuf, s->a2a_cnt_slab, s->a2a_dsp_slab, (int)sizeof(FT))) return -1;

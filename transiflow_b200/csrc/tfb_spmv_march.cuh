@@ -23,6 +23,7 @@ struct TfbSpmvArgs {
     int k0, nzl;
     int prow_cell_i, prow_cell_j, prow_cell_k, pvar;   // pinned pressure unknown (pvar < 0: none)
     unsigned rowmask, colmask;                          // 0 = all
+    int plane_nnz;            // structural non-zeros of a plane away from the z walls (0: unknown, always read row_ptr)
 };
 
 __device__ __forceinline__ void tfb_mbar_init(unsigned long long* bar, unsigned count) {
@@ -56,7 +57,7 @@ __device__ __forceinline__ double tfb_row_dot(const double* __restrict__ v, unsi
         for (int s = 0; s < Cfg::nslot(D1); s++) {
             int d2, dx, dy, dz;
             Cfg::slot(D1, s, d2, dx, dy, dz);
-            if (!MASKED || ((a.colmask >> d2) & 1u)) acc[s & 3] += v[s] * P(d2, dx, dy, dz);
+            if (!MASKED || ((a.colmask >> d2) & 1u)) acc[s & 3] = fma(v[s], P(d2, dx, dy, dz), acc[s & 3]);
         }
     } else {
         int pos = 0;
@@ -67,7 +68,7 @@ __device__ __forceinline__ double tfb_row_dot(const double* __restrict__ v, unsi
             if (full || ((m >> s) & 1u)) {
                 bool take = !MASKED || ((a.colmask >> d2) & 1u);
                 if (pin_near && d2 == a.pvar && i + dx == a.prow_cell_i && j + dy == a.prow_cell_j && k + dz == a.prow_cell_k) take = false;
-                if (take) acc[s & 3] += v[pos] * P(d2, dx, dy, dz);
+                if (take) acc[s & 3] = fma(v[pos], P(d2, dx, dy, dz), acc[s & 3]);
                 pos++;
             }
         }
@@ -157,8 +158,9 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
     int rp = valid ? a.row_ptr[row] : 0;
     __syncthreads();   // barriers initialised
     // values of the first plane
-    auto load_span = [&](int buf, long long rr0) {
-        const int gb = a.row_ptr[rr0], ge = a.row_ptr[rr0 + rlen];
+    int cur_gb = 0, cur_ge = 0;      // CSR span of the line in the plane loaded last (leader threads)
+    auto load_span = [&](int buf, int gb, int ge) {
+        cur_gb = gb; cur_ge = ge;
         sm_span[buf][jl][0] = gb;
         sm_span[buf][jl][1] = ge;
         const int ga = gb & ~1;
@@ -166,7 +168,7 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
         tfb_mbar_expect_tx(&sm_bar[buf][jl], bytes);
         if (bytes) tfb_bulk_load(sm_val + (buf * TJ + jl) * LINE_CAP, a.vals + ga, bytes, &sm_bar[buf][jl]);
     };
-    if (leader) load_span(0, r0);
+    if (leader) load_span(0, a.row_ptr[r0], a.row_ptr[r0 + rlen]);
 
     TfbCell c;
     tfb_cell_flags<0>(g, i, j, a.k0 + kbeg, c);
@@ -190,8 +192,16 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
         if (more) {
             deposit(s3, pre);
             if (kl + 2 < kend) fetch(k + 3, pre);
-            if (valid) rp_next = a.row_ptr[row + plane];
-            if (leader) load_span(buf ^ 1, r0 + plane);     // values of the next plane, one step ahead
+            // The row lengths of a plane depend on k only through its z-wall flags: between two planes without flags every
+            // CSR offset moves by the same amount, so row_ptr (a dependent global load in front of the bulk load and of
+            // the first multiply of the next step) is only read next to the walls.
+            const bool flagged = k == 0 || k == g.nz - 1 || k == kfar2 || k + 1 == g.nz - 1 || k + 1 == kfar2;
+            const bool shift = a.plane_nnz > 0 && !flagged;
+            if (valid) rp_next = shift ? rp + a.plane_nnz : a.row_ptr[row + plane];
+            if (leader) {                                   // values of the next plane, one step ahead
+                if (shift) load_span(buf ^ 1, cur_gb + a.plane_nnz, cur_ge + a.plane_nnz);
+                else load_span(buf ^ 1, a.row_ptr[r0 + plane], a.row_ptr[r0 + plane + rlen]);
+            }
         }
         if (j < g.ny) tfb_mbar_wait(&sm_bar[buf][jl], (step >> 1) & 1);
         if (valid) {

@@ -75,7 +75,7 @@ class DeviceMatrix:
         self.shape = (interface.n, interface.n)
         self.dtype = numpy.dtype(numpy.float64)
         self._host = None
-        self._complex_shift = None       # (sigma, mass diagonal) of a complex shifted matrix J - sigma M (eigs)
+        self._shift = 0.0                # the matrix is J + _shift * M (M: mass matrix), see _plus_diagonal
 
     @property
     def data(self):
@@ -175,6 +175,16 @@ class DeviceMatrix:
         numpy.add.at(d, coo.row, coo.data)
         out = DeviceMatrix(self.interface)
         check(_lib.lib().tfb_mat_add_diag(out._h, self._h, ctypes.c_double(sign), ptr(d)))
+        # J + a M with M the mass matrix (time stepping: -1 / (theta dt); shifted eigenproblems: -sigma): tell the solver,
+        # whose fast-diagonalisation basis is M-orthonormal, so that the preconditioner carries the shift exactly
+        mass = self.interface._mass_diagonal()
+        nz = mass != 0
+        out._shift = self._shift
+        if numpy.any(nz) and not numpy.any(d[~nz]):
+            ratio = d[nz] / mass[nz]
+            if numpy.ptp(ratio) <= 1e-12 * max(abs(ratio[0]), 1e-300):
+                out._shift = self._shift + sign * float(ratio[0])
+                check(_lib.lib().tfb_mat_set_shift(out._h, ctypes.c_double(out._shift)))
         return out
 
     def __add__(self, other):
@@ -396,6 +406,13 @@ class Interface:
         check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
         mat._host = None
         return mat, out
+
+    def _mass_diagonal(self):
+        if getattr(self, '_mass_diag', None) is None:
+            diag = numpy.empty(self.n_local)
+            check(_lib.lib().tfb_mass_diag(self._ctx, ptr(diag)))
+            self._mass_diag = diag
+        return self._mass_diag
 
     def mass_matrix(self):
         '''M as scipy csc (diagonal; pressure rows empty); replaces Discretization.mass_matrix
