@@ -30,6 +30,20 @@ def main():
     hdr, units, val = rows[0], rows[1], rows[2]
     print('# ' + comment)
     print('# command: ' + command)
+    if '--all' in sys.argv:
+        # one block per captured launch (a report that holds several kernels)
+        ki = hdr.index('Kernel Name')
+        for val in rows[2:]:
+            print('## kernel: ' + val[ki])
+            stalls = []
+            for h, u, v in zip(hdr, units, val):
+                if h in KEEP:
+                    print('%s,%s,%s' % (h, u, v))
+                elif 'issue_stalled' in h and h.endswith('per_issue_active.ratio'):
+                    stalls.append((float(v.replace(',', '')), h))
+            for v, h in sorted(stalls, reverse=True)[:5]:
+                print('%s,ratio,%.3f' % (h, v))
+        return
     stalls = []
     for h, u, v in zip(hdr, units, val):
         if h in KEEP:
