@@ -93,6 +93,13 @@ int tfb_mass_diag(tfb_ctx* ctx, double* diag_out);
 int tfb_state_upload(tfb_ctx* ctx, const double* state);
 int tfb_assemble_resident(tfb_ctx* ctx, tfb_mat* mat, int do_jacobian, int do_rhs);
 int tfb_rhs_download(tfb_ctx* ctx, double* out);
+/* Device-resident continuation fast path: a corrector iteration of Continuation.newton evaluates
+ * rhs(x; mu), rhs(x; mu + delta) and jacobian(x) for the SAME state (Continuation.py:126,145-150).  The host shim keeps
+ * the state resident between those calls: tfb_host_checksum (64-bit wrapping sum and xor of the words, multi-threaded --
+ * any single changed entry changes it) tells it whether a host vector is the one already in HBM, tfb_upload_count counts
+ * the state uploads of a context. */
+int tfb_host_checksum(const double* p, int64_t n, uint64_t out[2]);
+int64_t tfb_upload_count(tfb_ctx* ctx);
 int tfb_sync(tfb_ctx* ctx);
 
 /* CUDA-event timers on the ctx's stream. slot in [0,16). */

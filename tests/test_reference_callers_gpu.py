@@ -56,6 +56,39 @@ def test_reference_continuation_drives_the_b200_interface(transiflow, bordered):
     assert numpy.abs(x - g['x']).max() <= 1e-8 * scale
 
 
+def test_corrector_iterations_upload_the_state_once(transiflow):
+    """Device-resident continuation fast path: a corrector iteration of the UNMODIFIED Continuation
+    evaluates rhs(x; mu), rhs(x; mu + delta) and jacobian(x) for the same x (Continuation.py:126,145-150); the state is
+    uploaded once for the three, recognised by an exact checksum, so in-place edits of single entries are still seen."""
+    from transiflow_b200 import Interface
+    it = Interface(dict(LDC), 16, 16)
+    x = 0.01 * numpy.random.default_rng(0).standard_normal(it.n)
+    calls = {'rhs': 0, 'jacobian': 0}
+    rhs0, jac0 = it.rhs, it.jacobian
+    it.rhs = lambda s: (calls.__setitem__('rhs', calls['rhs'] + 1), rhs0(s))[1]
+    it.jacobian = lambda s: (calls.__setitem__('jacobian', calls['jacobian'] + 1), jac0(s))[1]
+    cont = transiflow.Continuation(it)
+    with contextlib.redirect_stdout(io.StringIO()):
+        x0 = cont.newton(x.copy())
+        before, calls['rhs'], calls['jacobian'] = it.state_uploads, 0, 0
+        cont.continuation(x0, 'Reynolds Number', 0, 20, 10)
+    uploads = it.state_uploads - before
+    assert calls['jacobian'] > 0 and calls['rhs'] >= 2 * calls['jacobian']
+    # one upload per distinct state: every corrector iteration has one (three evaluations), plus the converged checks
+    assert uploads <= calls['rhs'] - calls['jacobian'], (uploads, calls)
+    # an in-place edit of a single entry is a different state
+    f0 = rhs0(x0)
+    x0[7] += 1e-9
+    n0 = it.state_uploads
+    f1 = rhs0(x0)
+    assert it.state_uploads == n0 + 1 and not numpy.array_equal(f0, f1)
+    # opting out restores one upload per call
+    it.parameters['State Cache'] = False
+    n0 = it.state_uploads
+    rhs0(x0), rhs0(x0)
+    assert it.state_uploads == n0 + 2
+
+
 def test_reference_time_integration_drives_the_b200_interface(transiflow):
     """Implicit Euler of the reference (theta = 1): mass_matrix() @ v, jacobian(x) - mass / (theta dt) on the
     DeviceMatrix, solve."""

@@ -180,6 +180,29 @@ def test_mass_shifted_matrices_carry_the_shift_into_the_preconditioner(grid):
         assert numpy.linalg.norm(Ah.tocsr() @ y - b) <= 1e-8 * numpy.linalg.norm(b)
 
 
+@pytest.mark.parametrize('params', [{'Reynolds Number': 100},
+                                    {'Problem Type': 'Rayleigh-Benard', 'Rayleigh Number': 500.0, 'Prandtl Number': 10.0,
+                                     'Biot Number': 1.0, 'X-max': 10}])
+def test_semi_2d_grids_solve_like_the_spsolve_path(params):
+    """dim = 3 on an nz = 1 grid (the reference compares 2-D and semi-2-D continuations, tests/test_continuation.py:84-93):
+    Newton updates within 1e-8 of the pinned SuperLU solve, and the (u, v, p) part equal to the 2-D problem's."""
+    from oracle.tf_oracle import Oracle, direct_solve
+    from transiflow_b200 import Interface
+    nx, ny = 12, 10
+    p3 = dict(params, **{'Iterative Solver': {'Maximum Iterations': 2000, 'Restart': 2000}})
+    it = Interface(p3, nx, ny, 1, dim=3)
+    orc = Oracle(dict(params), nx, ny, 1, dim=3)
+    x = numpy.zeros(it.n)
+    for _ in range(2):
+        f = it.rhs(x)
+        jac = it.jacobian(x)
+        dx = it.solve(jac, -f)
+        assert it.last_solve['converged'], it.last_solve
+        want = direct_solve(orc.jacobian_csr(x), -orc.rhs(x), orc.dim, orc.dof)
+        assert numpy.abs(dx - want).max() <= 1e-8 * numpy.abs(want).max(), it.last_solve
+        x = x + dx
+
+
 def test_structured_spmv_matches_csr_kernel_and_scipy():
     """3-D grids use the column-index-free marching SpMV; it must agree with scipy on ragged grids."""
     for params, nx, ny, nz in (({'Reynolds Number': 100}, 37, 9, 19),

@@ -49,7 +49,7 @@ EXPORTS = [
     'tfb_device_count', 'tfb_last_error', 'tfb_config_name', 'tfb_create', 'tfb_destroy', 'tfb_set_params',
     'tfb_sizes', 'tfb_get_pattern', 'tfb_mat_create', 'tfb_mat_destroy', 'tfb_mat_get_values',
     'tfb_mat_set_values', 'tfb_mat_add_diag', 'tfb_mat_set_shift', 'tfb_rhs', 'tfb_jacobian', 'tfb_mass_diag', 'tfb_state_upload',
-    'tfb_assemble_resident', 'tfb_rhs_download', 'tfb_sync', 'tfb_event_record', 'tfb_event_elapsed_ms',
+    'tfb_assemble_resident', 'tfb_rhs_download', 'tfb_host_checksum', 'tfb_upload_count', 'tfb_sync', 'tfb_event_record', 'tfb_event_elapsed_ms',
     'tfb_flush_l2', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_spmv_bench', 'tfb_solve', 'tfb_fdm_set', 'tfb_fdm_set_pencil', 'tfb_fdm_pin', 'tfb_joint_set', 'tfb_joint_apply', 'tfb_precond_apply', 'tfb_precond_apply_opts', 'tfb_nccl_unique_id', 'tfb_comm_init',
 ]
 
@@ -65,8 +65,10 @@ def lib():
         L.tfb_last_error.restype = ctypes.c_char_p
         L.tfb_config_name.restype = ctypes.c_char_p
         L.tfb_launch_count.restype = ctypes.c_int64
+        L.tfb_upload_count.restype = ctypes.c_int64
+        L.tfb_upload_count.argtypes = [ctypes.c_void_p]
         for name in EXPORTS:
-            if name not in ('tfb_last_error', 'tfb_config_name', 'tfb_launch_count', 'tfb_destroy', 'tfb_mat_destroy'):
+            if name not in ('tfb_last_error', 'tfb_config_name', 'tfb_launch_count', 'tfb_upload_count', 'tfb_destroy', 'tfb_mat_destroy'):
                 getattr(L, name).restype = ctypes.c_int
         L.tfb_destroy.restype = None
         L.tfb_mat_destroy.restype = None

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <thread>
 #include "tfb_assemble.cuh"
 #include "tfb_spmv_march.cuh"
 
@@ -394,6 +395,33 @@ extern "C" int tfb_state_upload(tfb_ctx* c, const double* state) {
     TFB_CHECK(c && state, "null argument");
     TFB_CUDA(cudaSetDevice(c->desc.device));
     TFB_CUDA(cudaMemcpyAsync(c->d_state + c->plane_rows, state, sizeof(double) * c->n_local, cudaMemcpyHostToDevice, c->stream));
+    c->state_uploads++;
+    return 0;
+}
+
+extern "C" int64_t tfb_upload_count(tfb_ctx* c) { return c ? c->state_uploads : -1; }
+
+// 64-bit wrapping sum and xor of the words of a host vector, split over a few threads (memory-bandwidth bound: about
+// 1 ms for the 67 MB state of a 128^3 cavity, against 3-8 ms for its upload)
+extern "C" int tfb_host_checksum(const double* p, int64_t n, uint64_t out[2]) {
+    TFB_CHECK(p && n >= 0 && out, "bad arguments");
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(p);
+    const int nt = n < (1 << 16) ? 1 : (int)std::min<int64_t>(16, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+    std::vector<uint64_t> sum(nt, 0), x(nt, 0);
+    auto work = [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, xx = 0;
+        int64_t i = a;
+        for (; i + 4 <= b; i += 4) { s0 += w[i]; s1 += w[i + 1] * 3u; s2 += w[i + 2] * 5u; s3 += w[i + 3] * 7u; xx ^= w[i] ^ w[i + 1] ^ w[i + 2] ^ w[i + 3]; }
+        for (; i < b; i++) { s0 += w[i]; xx ^= w[i]; }
+        sum[t] = s0 + s1 + s2 + s3; x[t] = xx;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    out[0] = out[1] = 0;
+    for (int t = 0; t < nt; t++) { out[0] += sum[t] * (uint64_t)(2 * t + 1); out[1] ^= x[t]; }
     return 0;
 }
 
@@ -471,6 +499,7 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
     }
     m->version = tfb_next_version();
     m->shift = 0.0;
+    c->state_uploads++;
     for (int ch = 0; ch < nch; ch++) {
         const int p0 = ch * PCH, p1 = std::min(p0 + PCH, c->nzl);
         TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[ch], 0));

@@ -34,6 +34,7 @@ struct tfb_ctx {
     int64_t plane_rows;         // nx*ny*dof
     int64_t n_local, n_global, row0;
     int64_t nnz = 0;
+    int64_t state_uploads = 0;  // host -> device copies of the state (tfb_upload_count)
     int plane_nnz = -1;         // structural non-zeros of a plane away from the z walls (-1: not determined yet)
     cudaStream_t stream = nullptr;
     // geometry on the device

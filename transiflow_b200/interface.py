@@ -267,6 +267,7 @@ class Interface:
         check(L.tfb_sizes(self._ctx, ctypes.byref(nloc), ctypes.byref(nnz), None, ctypes.byref(row0)))
         self.nnz, self.n_local, self.row0 = nnz.value, nloc.value, row0.value
         self._pattern = None
+        self._resident_key = None
         self._param_key = None
         self.last_solve = None
         # result vectors of rhs / jacobian_rhs / solve come from recycled page-locked buffers on large grids
@@ -339,8 +340,8 @@ class Interface:
         self._sync_params()
         if self._fdm_key == self._param_key:
             return
-        if self.config.fold:
-            raise NotImplementedError('solve() on semi-2D (dim=3, nz=1) grids')
+        # semi-2D grids (dim = 3, nz = 1): the z-offsets fold onto the cell itself, so the z parts of every diffusion
+        # stencil cancel and the sub-solves are the 2-D fast-diagonalisation solves (w is one more scalar in x and y)
         pencils = []
         for v, a, m, Q, lam, coef in hostprep.fdm_operators(self.config, self._prm, self._mets, self.nx, self.ny, self.nz, pencils):
             check(_lib.lib().tfb_fdm_set(self._ctx, v, a, m, ptr(Q), ptr(lam), ctypes.c_double(coef)))
@@ -375,12 +376,37 @@ class Interface:
             self._pattern = (row_ptr, col)
         return self._pattern
 
+    # ---- device-resident state: rhs(x; mu), rhs(x; mu + delta) and jacobian(x) of one corrector
+    # iteration (Continuation.py:126,145-150) upload x once.  A host vector is recognised by its address, length and a
+    # 64-bit checksum of all its words (any single changed entry changes it), so in-place edits are never missed.
+    def _ensure_state(self, state):
+        '''Make `state` the state resident in HBM; returns True if it had to be uploaded.'''
+        L = _lib.lib()
+        key = None
+        if self.parameters.get('State Cache', True):
+            cs = (ctypes.c_uint64 * 2)()
+            check(L.tfb_host_checksum(ptr(state), ctypes.c_int64(state.size), cs))
+            key = (state.ctypes.data, state.size, cs[0], cs[1])
+            if key == self._resident_key:
+                return False
+        check(L.tfb_state_upload(self._ctx, ptr(state)))
+        self._resident_key = key
+        return True
+
+    @property
+    def state_uploads(self):
+        '''Host -> device copies of the state so far (tfb_upload_count).'''
+        return int(_lib.lib().tfb_upload_count(self._ctx))
+
     def rhs(self, state):
         '''F(x); replaces Discretization.rhs (Discretization.py:367-390).'''
         self._sync_params()
         state = as_f64(state)
         out = self._result_vector()
-        check(_lib.lib().tfb_rhs(self._ctx, ptr(state), ptr(out)))
+        L = _lib.lib()
+        self._ensure_state(state)
+        check(L.tfb_assemble_resident(self._ctx, None, 0, 1))
+        check(L.tfb_rhs_download(self._ctx, ptr(out)))
         return out
 
     def jacobian(self, state):
@@ -388,7 +414,13 @@ class Interface:
         self._sync_params()
         state = as_f64(state)
         mat = DeviceMatrix(self)
-        check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, None))
+        L = _lib.lib()
+        if self._resident_key is not None and not self._ensure_state(state):
+            check(L.tfb_assemble_resident(self._ctx, mat._h, 1, 0))       # the state is already in HBM
+            check(L.tfb_sync(self._ctx))
+        else:
+            check(L.tfb_jacobian(self._ctx, ptr(state), mat._h, None))    # (pipelined) upload + assembly
+            self._resident_key = None                                     # uploaded by the library: checksum not taken
         return mat
 
     def jacobian_rhs(self, state):
@@ -398,12 +430,14 @@ class Interface:
         mat = DeviceMatrix(self)
         out = self._result_vector()
         check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
+        self._resident_key = None
         return mat, out
 
     def jacobian_rhs_into(self, state, mat, out):
         '''Fused J(x), F(x) into an existing DeviceMatrix / host buffer (no allocations).'''
         self._sync_params()
         check(_lib.lib().tfb_jacobian(self._ctx, ptr(state), mat._h, ptr(out)))
+        self._resident_key = None
         mat._host = None
         return mat, out
 
