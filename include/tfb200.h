@@ -150,6 +150,13 @@ typedef struct {
 } tfb_solve_info;
 int tfb_solve(tfb_mat* mat, const double* b, double* x, const tfb_solve_opts* opts, tfb_solve_info* info);
 
+/* Interface.solve for 2-D grids by a direct method, the counterpart of SciPy.Interface.direct_solve (SciPy.py:204-258:
+ * SuperLU, factors cached on the matrix): block-tridiagonal elimination over the grid lines with one dense, pivoted
+ * inverse per line (csrc/tfb_direct.cu), fp64, one step of iterative refinement.  The factors stay with `mat` until its
+ * values change, so the second solve of a corrector step only substitutes.  info->setup_ms: factorisation time of this
+ * call (0 when reused).  Returns 0, 1 (residual above 1e-8: use tfb_solve), <0 on errors (e.g. a singular line block). */
+int tfb_direct_solve(tfb_mat* mat, const double* b, double* x, int pressure_row, tfb_solve_info* info);
+
 /* Fast-diagonalisation data of the block preconditioner: for variable `var` and axis `axis`
  * the m x m M-orthonormal eigenvector matrix Q (row-major) and eigenvalues lam of the 1-D pencil
  * (K, M) of that variable's diffusion stencil incl. wall folds; coef = the operator's scalar

@@ -126,7 +126,9 @@ def test_complex_right_hand_side_is_solved_by_parts():
     J[:, 3] = 0
     J[3, 3] = -1
     assert numpy.linalg.norm(J.tocsr() @ y - b) <= 1e-8 * numpy.linalg.norm(b)
-    assert numpy.array_equal(y.real, it.solve(jac, b.real.copy()))
+    # the same solve as a purely real one (bitwise up to the order of the atomic partial sums of the Krylov reductions)
+    again = it.solve(jac, b.real.copy())
+    assert numpy.abs(y.real - again).max() <= 1e-12 * numpy.abs(again).max()
 
 
 def test_time_integration_operators():
@@ -155,13 +157,39 @@ def test_time_integration_operators():
     assert numpy.linalg.norm(r) <= 1e-8 * numpy.linalg.norm(b)
 
 
+@pytest.mark.parametrize('name', ['ldc2d_24', 'dhc2d_16', 'qg_16', 'amoc_16'])
+def test_direct_solve_on_2d_grids_matches_superlu(name):
+    """2-D grids are solved directly by default (block-tridiagonal elimination over the grid lines, csrc/tfb_direct.cu):
+    spsolve-grade agreement with the reference's SuperLU answer, factors reused for the second solve of a matrix."""
+    params, nx, ny, nz = NEWTON_CASES[name]
+    g = numpy.load(os.path.join(GEN, 'newton_' + name + '.npz'))
+    from transiflow_b200 import Interface
+    it = Interface(dict(params), nx, ny, nz)
+    jac = it.jacobian(g['x'])
+    y = it.solve(jac, g['b'])
+    assert it.last_solve['method'] == 'Direct' and it.last_solve['converged'] and it.last_solve['setup_ms'] > 0
+    scale = numpy.abs(g['y']).max()
+    assert numpy.abs(y - g['y']).max() <= 1e-9 * scale, numpy.abs(y - g['y']).max() / scale
+    y2 = it.solve(jac, 2 * g['b'])
+    assert it.last_solve['setup_ms'] == 0                      # cached factors, like jac.lu in SciPy.py:142-152
+    assert numpy.abs(y2 - 2 * g['y']).max() <= 1e-9 * 2 * scale
+    # a new Jacobian is factored again; the Krylov solver remains available on request
+    jac2 = it.jacobian(0.5 * g['x'])
+    it.solve(jac2, g['b'])
+    assert it.last_solve['setup_ms'] > 0
+    it.parameters['Iterative Solver'] = {'Method': 'FGMRES', 'Maximum Iterations': 2000, 'Restart': 2000}
+    yk = it.solve(jac, g['b'])
+    assert it.last_solve['method'] == 'FGMRES'
+    assert numpy.abs(yk - g['y']).max() <= 1e-8 * scale
+
+
 @pytest.mark.parametrize('grid', [(8, 8, 8), (24, 24, 1)])
 def test_mass_shifted_matrices_carry_the_shift_into_the_preconditioner(grid):
     """J - M / (theta dt) with a small time step (and J - sigma M with a large shift) are dominated by the mass term; the
     fast-diagonalisation basis is M-orthonormal, so the block preconditioner solves the shifted diffusion operators
     exactly and the iteration count must not blow up (it did when the shift was ignored)."""
     nx, ny, nz = grid
-    it = _iface({'Reynolds Number': 100}, nx, ny, nz)
+    it = _iface({'Reynolds Number': 100, 'Iterative Solver': {'Method': 'FGMRES'}}, nx, ny, nz)
     x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
     jac, mass = it.jacobian(x), it.mass_matrix()
     b = numpy.random.default_rng(1).uniform(-1, 1, it.n)

@@ -21,6 +21,7 @@ UNITS = [
     ('tfb_core.cu', ['-fmad=false']),
     ('tfb_solver.cu', []),
     ('tfb_comm.cu', []),
+    ('tfb_direct.cu', []),
 ]
 
 

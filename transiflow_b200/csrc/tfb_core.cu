@@ -250,6 +250,7 @@ extern "C" void tfb_mat_destroy(tfb_mat* m) {
     if (!m) return;
     tfb_ctx* c = m->ctx;
     cudaSetDevice(c->desc.device);
+    tfb_direct_free(m);
     if (m->d_vals && c->vals_pool.size() < 2) {
         cudaDeviceSynchronize();            // what cudaFree did implicitly: nothing in flight still reads the buffer
         c->vals_pool.push_back(m->d_vals);

@@ -1,0 +1,391 @@
+// Direct solve for the 2-D configurations (lid-driven / heated cavity, double gyre, AMOC): the counterpart of the
+// SciPy backend's SuperLU path (interface/SciPy.py:131-162,204-258) where the Krylov solver loses to it.
+//
+// Rows are ordered i-fastest, so with one grid line (all cells of a j, all unknowns: m = dof * nx) as a block the pinned
+// Jacobian is BLOCK TRIDIAGONAL: line j couples to lines j-1, j, j+1 only.  Block elimination over the lines,
+//     S_0 = B_0,   S_j = B_j - L_j S_{j-1}^-1 U_{j-1},
+// keeps one dense m x m inverse per line (ny * m^2 doubles: 1.7 GB for AMOC 256 x 128, 20 MB for the 64 x 64 heated
+// cavity); L_j, U_j stay sparse (they are read from the CSR matrix).  A solve is then two dense matrix-vector products
+// per line.  S_j^-1 is formed by in-place Gauss-Jordan elimination with partial pivoting INSIDE the block, which is what
+// makes the saddle-point structure (zero pressure diagonal) harmless; the elimination runs as one persistent kernel,
+// all CTAs co-resident, two grid barriers per column.  Everything is fp64; the factors are cached on the tfb_mat like
+// `jac.lu` on the reference's matrices, so the second solve of a corrector step only pays the substitution.
+#include <math.h>
+#include <algorithm>
+#include <vector>
+#include "tfb_internal.h"
+
+struct tfb_direct_factor {
+    int m = 0, nl = 0, prow = -2;
+    uint64_t version = ~0ull;
+    double* Sinv = nullptr;     // nl x m x m
+    double* S = nullptr;        // m x m work (Gauss-Jordan runs here)
+    double* W = nullptr;        // m x m work: L_j S_{j-1}^-1
+    double* colbuf = nullptr;   // m
+    double* rowbuf = nullptr;   // m
+    int* piv = nullptr;         // m
+    int* colsrc = nullptr;      // m
+    unsigned* bar = nullptr;    // grid barrier counter + status word
+    double* y = nullptr;        // n work vectors
+    double* z = nullptr;
+    double* rr = nullptr;
+    float factor_ms = 0.f;
+};
+
+void tfb_direct_free(tfb_mat* mat) {
+    tfb_direct_factor* f = (tfb_direct_factor*)mat->direct;
+    if (!f) return;
+    cudaFree(f->Sinv); cudaFree(f->S); cudaFree(f->W); cudaFree(f->colbuf); cudaFree(f->rowbuf); cudaFree(f->piv);
+    cudaFree(f->colsrc); cudaFree(f->bar); cudaFree(f->y); cudaFree(f->z); cudaFree(f->rr);
+    delete f;
+    mat->direct = nullptr;
+}
+
+// ---- blocks of line j out of the CSR matrix (pinned: row prow is -1 on the diagonal, column prow dropped) ----
+// dense[(r - j m) * m + (c - (j + which) m)] = A(r, c) for the entries of the rows of line j whose column lies in line j + which
+__global__ void k_dense_block(int m, int line, int which, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                              const double* __restrict__ vals, int prow, double* __restrict__ dense) {
+    const int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rl >= m) return;
+    const long long r = (long long)line * m + rl;
+    const long long c0 = (long long)(line + which) * m;
+    if (r == prow) { if (which == 0) dense[(long long)rl * m + rl] = -1.0; return; }
+    for (int e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+        const long long c = col[e];
+        if (c == prow || c < c0 || c >= c0 + m) continue;
+        dense[(long long)rl * m + (c - c0)] = vals[e];
+    }
+}
+// W[r][q] = sum_a L_j(r, a) Sinv_prev[a][q]   (rows of line j, columns a in line j - 1)
+__global__ void k_sparse_times_dense(int m, int line, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                     const double* __restrict__ vals, int prow, const double* __restrict__ Sprev, double* __restrict__ W) {
+    const int rl = blockIdx.y;
+    const long long r = (long long)line * m + rl;
+    const long long c0 = (long long)(line - 1) * m;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < m; q += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        if (r != prow)
+            for (int e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+                const long long c = col[e];
+                if (c == prow || c < c0 || c >= c0 + m) continue;
+                acc += vals[e] * Sprev[(c - c0) * m + q];
+            }
+        W[(long long)rl * m + q] = acc;
+    }
+}
+// S[r][c] -= sum_b W[r][b] U_{j-1}(b, c): one thread per (r, b), atomics on S (several b reach the same c)
+__global__ void k_dense_times_sparse_sub(int m, int line, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                         const double* __restrict__ vals, int prow, const double* __restrict__ W, double* __restrict__ S) {
+    const int bl = blockIdx.x * blockDim.x + threadIdx.x;      // row b of line j-1
+    const int rl = blockIdx.y;
+    if (bl >= m) return;
+    const long long b = (long long)(line - 1) * m + bl;
+    if (b == prow) return;
+    const double w = W[(long long)rl * m + bl];
+    if (w == 0.0) return;
+    const long long c0 = (long long)line * m;
+    for (int e = row_ptr[b]; e < row_ptr[b + 1]; e++) {
+        const long long c = col[e];
+        if (c == prow || c < c0 || c >= c0 + m) continue;
+        atomicAdd(&S[(long long)rl * m + (c - c0)], -w * vals[e]);
+    }
+}
+
+// ---- in-place Gauss-Jordan inversion with partial pivoting, persistent multi-CTA kernel ----
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& epoch) {
+    __syncthreads();
+    if (nblocks == 1) return;
+    if (threadIdx.x == 0) {
+        epoch++;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned target = epoch * nblocks;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+        } while (seen < target);
+        __threadfence();      // gpu-scope fence: the CTA's L1 must not serve lines written by other CTAs before the barrier
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_gauss_jordan(int m, double* __restrict__ A, double* __restrict__ colbuf, double* __restrict__ rowbuf,
+                                                      int* __restrict__ piv, int* __restrict__ colsrc, unsigned* __restrict__ bar,
+                                                      double* __restrict__ out, double tiny) {
+    __shared__ double s_val[256];
+    __shared__ int s_row[256];
+    __shared__ int s_p;
+    unsigned epoch = 0;
+    const unsigned nb = gridDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+    const long long mm = (long long)m * m;
+    for (int k = 0; k < m; k++) {
+        // pivot row of column k (every CTA scans the column itself: no exchange, deterministic tie-break)
+        double best = -1.0;
+        int brow = k;
+        for (int i = k + threadIdx.x; i < m; i += blockDim.x) {
+            const double v = fabs(A[(long long)i * m + k]);
+            if (v > best) { best = v; brow = i; }
+        }
+        // warp-level reduction, then the eight warp results
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v = __shfl_xor_sync(0xffffffffu, best, o);
+            const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
+            if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
+        }
+        if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_row[threadIdx.x >> 5] = brow; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+                if (s_val[w] > s_val[0] || (s_val[w] == s_val[0] && s_row[w] < s_row[0])) { s_val[0] = s_val[w]; s_row[0] = s_row[w]; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_p = s_row[0];
+            if (blockIdx.x == 0) { piv[k] = s_row[0]; if (!(s_val[0] > tiny)) bar[1] = 1u; }    // singular block
+        }
+        __syncthreads();
+        const int p = s_p;
+        // rows k and p swap (column k excepted: it is rewritten from colbuf below); old row p -> rowbuf, column k -> colbuf
+        for (long long j = gtid; j < m; j += gsz) {
+            const double ap = A[(long long)p * m + j];
+            rowbuf[j] = ap;
+            if (p != k && j != k) A[(long long)p * m + j] = A[(long long)k * m + j];
+            double cv = A[j * m + k];                                   // j doubles as a row index here
+            if (j == k) cv = A[(long long)p * m + k];
+            else if (j == p) cv = A[(long long)k * m + k];
+            colbuf[j] = cv;
+        }
+        grid_barrier(bar, nb, epoch);
+        const double pivinv = 1.0 / colbuf[k];
+        for (long long e = gtid; e < mm; e += gsz) {
+            const int i = (int)(e / m), j = (int)(e - (long long)i * m);
+            double v;
+            if (i == k) v = j == k ? pivinv : rowbuf[j] * pivinv;
+            else {
+                const double f = colbuf[i];
+                v = j == k ? -f * pivinv : A[e] - f * (rowbuf[j] * pivinv);
+            }
+            A[e] = v;
+        }
+        grid_barrier(bar, nb, epoch);
+    }
+    // inverse of the row-permuted matrix -> inverse: undo the swaps on the columns, composed into one gather
+    if (gtid == 0) {
+        for (int c = 0; c < m; c++) colsrc[c] = c;
+        for (int k = m - 1; k >= 0; k--) {
+            const int p = piv[k];
+            if (p != k) { const int t = colsrc[k]; colsrc[k] = colsrc[p]; colsrc[p] = t; }
+        }
+    }
+    grid_barrier(bar, nb, epoch);
+    for (long long e = gtid; e < mm; e += gsz) {
+        const int i = (int)(e / m), j = (int)(e - (long long)i * m);
+        out[e] = A[(long long)i * m + colsrc[j]];
+    }
+}
+
+// ---- substitution ----
+// z = Sinv_j * y_j  (dense m x m times vector; one warp per row)
+__global__ void __launch_bounds__(256) k_dense_matvec(int m, const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= m) return;
+    const double* a = A + (long long)row * m;
+    double acc = 0.0;
+    for (int j = lane; j < m; j += 32) acc += a[j] * x[j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = acc;
+}
+// t_j = src_j - (block of line j towards line j + which) * v_{j + which}
+__global__ void k_line_residual(int m, int line, int which, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                const double* __restrict__ vals, int prow, const double* __restrict__ src, const double* __restrict__ v,
+                                double* __restrict__ t) {
+    const int rl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rl >= m) return;
+    const long long r = (long long)line * m + rl;
+    const long long c0 = (long long)(line + which) * m;
+    double acc = src[r];
+    if (r != prow)
+        for (int e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+            const long long c = col[e];
+            if (c == prow || c < c0 || c >= c0 + m) continue;
+            acc -= vals[e] * v[c];
+        }
+    t[r] = acc;
+}
+__global__ void k_pinned_residual(long long n, const int* __restrict__ row_ptr, const int* __restrict__ col, const double* __restrict__ vals,
+                                  int prow, const double* __restrict__ b, const double* __restrict__ x, double* __restrict__ r) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double acc = b[row];
+    if (row == prow) acc += x[row];
+    else
+        for (int e = row_ptr[row]; e < row_ptr[row + 1]; e++)
+            if (col[e] != prow) acc -= vals[e] * x[col[e]];
+    r[row] = acc;
+}
+__global__ void k_vec_add(long long n, const double* __restrict__ a, double* __restrict__ x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += a[i];
+}
+__global__ void k_norm2(long long n, const double* __restrict__ a, double* __restrict__ out) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += a[i] * a[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+static int direct_factor(tfb_mat* mat, int prow) {
+    tfb_ctx* c = mat->ctx;
+    const int dof = c->desc.dof, nx = c->desc.nx, ny = c->desc.ny;
+    const int m = dof * nx, nl = ny * c->desc.nz;
+    tfb_direct_factor* f = (tfb_direct_factor*)mat->direct;
+    if (f && f->version == mat->version && f->prow == prow) return 0;
+    if (!f) {
+        f = new tfb_direct_factor();
+        mat->direct = f;
+        f->m = m; f->nl = nl;
+        const size_t mm = (size_t)m * m;
+        size_t freeb = 0, total = 0;
+        TFB_CUDA(cudaMemGetInfo(&freeb, &total));
+        TFB_CHECK(sizeof(double) * mm * (nl + 2) < freeb * 0.8, "the line inverses of the direct solve do not fit in device memory");
+        TFB_CUDA(cudaMalloc(&f->Sinv, sizeof(double) * mm * nl));
+        TFB_CUDA(cudaMalloc(&f->S, sizeof(double) * mm));
+        TFB_CUDA(cudaMalloc(&f->W, sizeof(double) * mm));
+        TFB_CUDA(cudaMalloc(&f->colbuf, sizeof(double) * m));
+        TFB_CUDA(cudaMalloc(&f->rowbuf, sizeof(double) * m));
+        TFB_CUDA(cudaMalloc(&f->piv, sizeof(int) * m));
+        TFB_CUDA(cudaMalloc(&f->colsrc, sizeof(int) * m));
+        TFB_CUDA(cudaMalloc(&f->bar, sizeof(unsigned) * 2));
+        TFB_CUDA(cudaMalloc(&f->y, sizeof(double) * c->n_local));
+        TFB_CUDA(cudaMalloc(&f->z, sizeof(double) * c->n_local));
+        TFB_CUDA(cudaMalloc(&f->rr, sizeof(double) * (c->n_local + 2)));
+    }
+    cudaEvent_t e0, e1;
+    TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
+    TFB_CUDA(cudaEventRecord(e0, c->stream));
+    const size_t mm = (size_t)m * m;
+    // the persistent elimination kernel needs all its CTAs resident at once
+    int per_sm = 0, sms = 0;
+    TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gauss_jordan, 256, 0));
+    TFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->desc.device));
+    // tiny blocks: one CTA (barriers are __syncthreads); otherwise ~8 elements per thread, at most two CTAs per SM
+    const int gj_grid = mm <= 256 * 16 ? 1
+                                       : (int)std::max<long long>(1, std::min<long long>((long long)sms * std::min(per_sm, 2), ((long long)mm + 256 * 8 - 1) / (256 * 8)));
+    double amax = 0.0;   // scale for the singularity test: largest |value| of the matrix
+    {
+        std::vector<double> probe(std::min<size_t>((size_t)c->nnz, 4096));
+        TFB_CUDA(cudaMemcpyAsync(probe.data(), mat->d_vals, sizeof(double) * probe.size(), cudaMemcpyDeviceToHost, c->stream));
+        TFB_CUDA(cudaStreamSynchronize(c->stream));
+        for (double v : probe) amax = std::max(amax, fabs(v));
+    }
+    const double tiny = 1e-14 * std::max(amax, 1e-300);
+    const unsigned rb = (unsigned)((m + 127) / 128);
+    for (int j = 0; j < nl; j++) {
+        TFB_CUDA(cudaMemsetAsync(f->S, 0, sizeof(double) * mm, c->stream));
+        k_dense_block<<<rb, 128, 0, c->stream>>>(m, j, 0, c->d_row_ptr, c->d_col, mat->d_vals, prow, f->S);
+        TFB_LAUNCHED();
+        if (j > 0) {
+            const double* Sprev = f->Sinv + (size_t)(j - 1) * mm;
+            k_sparse_times_dense<<<dim3((unsigned)std::min(8, (m + 255) / 256), m), 256, 0, c->stream>>>(m, j, c->d_row_ptr, c->d_col, mat->d_vals, prow, Sprev, f->W);
+            k_dense_times_sparse_sub<<<dim3(rb, m), 128, 0, c->stream>>>(m, j, c->d_row_ptr, c->d_col, mat->d_vals, prow, f->W, f->S);
+            TFB_LAUNCHED(); TFB_LAUNCHED();
+        }
+        TFB_CUDA(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * 2, c->stream));
+        k_gauss_jordan<<<gj_grid, 256, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        TFB_LAUNCHED();
+        TFB_CUDA(cudaGetLastError());
+    }
+    unsigned status[2] = {0, 0};
+    TFB_CUDA(cudaMemcpyAsync(status, f->bar, sizeof(unsigned) * 2, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaEventRecord(e1, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&f->factor_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    TFB_CHECK(status[1] == 0, "direct solve: a line block is numerically singular");
+    f->version = mat->version;
+    f->prow = prow;
+    return 0;
+}
+
+// x = (pinned matrix)^-1 b on the device, factors of `mat` in place
+static int direct_substitute(tfb_mat* mat, int prow, const double* d_b, double* d_x) {
+    tfb_ctx* c = mat->ctx;
+    tfb_direct_factor* f = (tfb_direct_factor*)mat->direct;
+    const int m = f->m, nl = f->nl;
+    const size_t mm = (size_t)m * m;
+    const unsigned rb = (unsigned)((m + 127) / 128), wb = (unsigned)((m + 7) / 8);
+    // forward: y_j = b_j - L_j z_{j-1},  z_j = Sinv_j y_j
+    for (int j = 0; j < nl; j++) {
+        const double* src = d_b;
+        if (j > 0) {
+            k_line_residual<<<rb, 128, 0, c->stream>>>(m, j, -1, c->d_row_ptr, c->d_col, mat->d_vals, prow, d_b, f->z, f->y);
+            src = f->y;
+        }
+        k_dense_matvec<<<wb, 256, 0, c->stream>>>(m, f->Sinv + (size_t)j * mm, src + (size_t)j * m, f->z + (size_t)j * m);
+        TFB_LAUNCHED(); TFB_LAUNCHED();
+    }
+    // backward: x_j = z_j - Sinv_j (U_j x_{j+1})
+    TFB_CUDA(cudaMemcpyAsync(d_x + (size_t)(nl - 1) * m, f->z + (size_t)(nl - 1) * m, sizeof(double) * m, cudaMemcpyDeviceToDevice, c->stream));
+    for (int j = nl - 2; j >= 0; j--) {
+        // y_j := U_j x_{j+1}  (as 0 - (-U x)): reuse k_line_residual with a zero source
+        TFB_CUDA(cudaMemsetAsync(f->y + (size_t)j * m, 0, sizeof(double) * m, c->stream));
+        k_line_residual<<<rb, 128, 0, c->stream>>>(m, j, +1, c->d_row_ptr, c->d_col, mat->d_vals, prow, f->y, d_x, f->y);   // y_j = -U_j x_{j+1}
+        k_dense_matvec<<<wb, 256, 0, c->stream>>>(m, f->Sinv + (size_t)j * mm, f->y + (size_t)j * m, d_x + (size_t)j * m);  // = -Sinv U x
+        k_vec_add<<<rb, 128, 0, c->stream>>>(m, f->z + (size_t)j * m, d_x + (size_t)j * m);
+        TFB_LAUNCHED(); TFB_LAUNCHED(); TFB_LAUNCHED();
+    }
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Interface.solve through the direct path: host vectors, pressure pinned at `prow`.  One step of iterative refinement
+// brings the answer to spsolve grade.  info->setup_ms = time of the factorisation (0 when the cached factors were reused).
+extern "C" int tfb_direct_solve(tfb_mat* mat, const double* b, double* x, int prow, tfb_solve_info* info) {
+    TFB_CHECK(mat && b && x, "null argument");
+    tfb_ctx* c = mat->ctx;
+    TFB_CHECK(c->nranks == 1, "the direct solve is single-GPU");
+    TFB_CHECK(c->desc.nz == 1, "the direct solve is for 2-D grids (one line of cells per block)");
+    TFB_CUDA(cudaSetDevice(c->desc.device));
+    const long long n = c->n_local;
+    const bool had = mat->direct && ((tfb_direct_factor*)mat->direct)->version == mat->version && ((tfb_direct_factor*)mat->direct)->prow == prow;
+    if (direct_factor(mat, prow)) return -1;
+    tfb_direct_factor* f = (tfb_direct_factor*)mat->direct;
+    cudaEvent_t e0, e1;
+    TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
+    TFB_CUDA(cudaEventRecord(e0, c->stream));
+    double *d_b = nullptr, *d_x = nullptr, *d_dx = nullptr;
+    TFB_CUDA(cudaMalloc(&d_b, sizeof(double) * n));
+    TFB_CUDA(cudaMalloc(&d_x, sizeof(double) * n));
+    TFB_CUDA(cudaMalloc(&d_dx, sizeof(double) * n));
+    TFB_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    if (direct_substitute(mat, prow, d_b, d_x)) return -1;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    double norms[2] = {0.0, 0.0};
+    for (int ref = 0; ref < 2; ref++) {
+        k_pinned_residual<<<nb, 256, 0, c->stream>>>(n, c->d_row_ptr, c->d_col, mat->d_vals, prow, d_b, d_x, f->rr);
+        TFB_LAUNCHED();
+        if (ref == 1) break;
+        if (direct_substitute(mat, prow, f->rr, d_dx)) return -1;
+        k_vec_add<<<nb, 256, 0, c->stream>>>(n, d_dx, d_x);
+        TFB_LAUNCHED();
+    }
+    TFB_CUDA(cudaMemsetAsync(f->rr + n, 0, sizeof(double) * 2, c->stream));
+    k_norm2<<<64, 256, 0, c->stream>>>(n, f->rr, f->rr + n);
+    k_norm2<<<64, 256, 0, c->stream>>>(n, d_b, f->rr + n + 1);
+    TFB_LAUNCHED(); TFB_LAUNCHED();
+    TFB_CUDA(cudaMemcpyAsync(norms, f->rr + n, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaMemcpyAsync(x, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    TFB_CUDA(cudaEventRecord(e1, c->stream));
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_b); cudaFree(d_x); cudaFree(d_dx);
+    const double relres = norms[1] > 0.0 ? sqrt(norms[0] / norms[1]) : sqrt(norms[0]);
+    if (info) {
+        info->iters = 1; info->relres = relres; info->converged = relres <= 1e-10;
+        info->setup_ms = had ? 0.f : f->factor_ms; info->solve_ms = ms;
+    }
+    return relres <= 1e-8 ? 0 : 1;
+}

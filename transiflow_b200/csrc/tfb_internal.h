@@ -78,6 +78,7 @@ struct tfb_mat {
     double* d_vals = nullptr;
     uint64_t version = 0;       // bumped whenever values change (invalidates the preconditioner)
     double shift = 0.0;         // the matrix is (an assembled Jacobian) + shift * (mass matrix): tfb_mat_set_shift
+    void* direct = nullptr;     // cached factors of the 2-D direct solve (tfb_direct.cu), keyed on `version`
 };
 
 uint64_t tfb_next_version();
@@ -92,3 +93,4 @@ int tfb_halo_up_f32(tfb_ctx* c, const float* first_plane, float* ghost_above, si
 int tfb_halo_up_f64(tfb_ctx* c, const double* first_plane, double* ghost_above, size_t count);
 int tfb_allgather_f32(tfb_ctx* c, const float* send, float* recv, size_t count);
 void tfb_solver_free(tfb_solver_state* s);
+void tfb_direct_free(tfb_mat* mat);

@@ -533,6 +533,21 @@ class Interface:
         # preconditioner (the orthogonalisation against an un-restarted basis is 45 % of an FGMRES solve at 128^3),
         # FGMRES otherwise and as the fallback whenever IDR does not reach the tolerance
         method = str(its.get('Method', 'auto')).lower()
+        # 'Method': 'Direct' (2-D grids; the default there): block-tridiagonal elimination over the grid lines with pivoted
+        # dense line inverses on the device, the counterpart of the reference's SuperLU solve.  Factors are cached on the
+        # matrix, so the second solve of a corrector step only substitutes.  Falls back to the Krylov solver when the
+        # line inverses do not fit or a line block is singular.
+        line = self.dof * self.nx
+        direct_ok = self.nz == 1 and self.slab == (0, self.nz) and 8.0 * line * line * (self.ny + 2) < 40e9
+        if method == 'direct' and not direct_ok:
+            raise ValueError("'Method': 'Direct' is for single-GPU 2-D grids whose line inverses fit in device memory")
+        if method == 'direct' or (method == 'auto' and direct_ok):
+            y = self._direct_solve(jac, b, prow)
+            if y is not None:
+                return y
+            if method == 'direct':
+                raise RuntimeError('direct solve failed: ' + str(self.last_solve))
+            method = 'auto'
         o.method = _lib.METHOD_BICGSTAB if method == 'bicgstab' else _lib.METHOD_FGMRES
         o.stall_cycles = int(its.get('Stagnation Cycles', 0))
         # 'Scalar Coupling': 'joint' (default where available: 3-D Rayleigh-Benard) solves w and T together and
@@ -601,6 +616,22 @@ class Interface:
             warnings.warn('B200 solve: %s stopped at relative residual %.3e after %d iterations (tolerance %.1e)'
                           % (self.last_solve['method'], info.relres, self.last_solve['iterations'], o.tol), RuntimeWarning)
         self._debug_print('%s: %d iterations, relres %.3e' % (self.last_solve['method'], info.iters, info.relres))
+        return y
+
+    def _direct_solve(self, jac, b, prow):
+        info = _lib.TfbSolveInfo()
+        y = self._result_vector()
+        L = _lib.lib()
+        rc = L.tfb_direct_solve(jac._h, ptr(b), ptr(y), ctypes.c_int(prow), ctypes.byref(info))
+        if rc != 0:
+            self.last_solve = {'iterations': 0, 'relres': float(info.relres) if rc > 0 else float('nan'), 'converged': False,
+                               'setup_ms': 0.0, 'solve_ms': 0.0, 'method': 'Direct', 'schur': '-', 'precond_precision': '-',
+                               'error': L.tfb_last_error().decode() if rc < 0 else 'residual %.2e' % info.relres}
+            self._debug_print('direct solve not usable (%s), using the Krylov solver' % self.last_solve['error'])
+            return None
+        self.last_solve = {'iterations': 1, 'relres': info.relres, 'converged': True, 'setup_ms': info.setup_ms,
+                           'solve_ms': info.solve_ms, 'method': 'Direct', 'schur': '-', 'precond_precision': '-'}
+        self._debug_print('Direct: factor %.1f ms, solve %.1f ms, relres %.3e' % (info.setup_ms, info.solve_ms, info.relres))
         return y
 
     def _bordered_solve(self, jac, rhs, rhs2, V, W, C):
