@@ -109,10 +109,11 @@ def cpu_port_cells_per_s(grid, planes, repeats=1):
     return grid * grid * planes / best, lib().tfo_num_threads(), best
 
 
-def python_reference_sample(n=16):
-    '''The UNMODIFIED Python reference (SciPy backend, pip-installed under baseline/_ref) on a small instance of the
-    same problem, on this box's host: Interface.rhs + Interface.jacobian (single-threaded Python) and Interface.solve
-    (SuperLU).  About 10 s; None when the package is not there.'''
+def python_reference_sample(n=16, grid2d=None):
+    '''The UNMODIFIED Python reference (SciPy backend, pip-installed under baseline/_ref) on this box's host:
+    Interface.rhs + Interface.jacobian (single-threaded Python) and Interface.solve (SuperLU) -- on a small n^3 instance
+    of the 3-D workload (about 10 s), or on the full (nx, ny) grid of a 2-D configuration.  None when the package is
+    not there.'''
     ref = os.path.join(ROOT, 'baseline', '_ref')
     if not os.path.isdir(os.path.join(ref, 'transiflow')):
         return None
@@ -120,6 +121,20 @@ def python_reference_sample(n=16):
     try:
         from transiflow import Interface as RefInterface
         params = {k: v for k, v in PARAMS.items() if k != 'Iterative Solver'}
+        if grid2d:
+            it = RefInterface(dict(params), grid2d[0], grid2d[1])
+            x = numpy.random.default_rng(0).uniform(-0.01, 0.01, it.vector().size)
+            t0 = time.perf_counter()
+            f = it.rhs(x)
+            t1 = time.perf_counter()
+            jac = it.jacobian(x)
+            t2 = time.perf_counter()
+            it.solve(jac, -f)
+            t3 = time.perf_counter()
+            cells = grid2d[0] * grid2d[1]
+            return {'grid': [grid2d[0], grid2d[1], 1], 'rhs_s': t1 - t0, 'jacobian_s': t2 - t1, 'solve_s': t3 - t2,
+                    'assembly_cells_per_s': cells / (t2 - t0), 'newton_steps_per_s': 1.0 / (t3 - t0), 'cores': 1,
+                    'note': 'unmodified reference, SciPy backend, the same grid and parameters'}
         it = RefInterface(dict(params), n, n, n)
         x = numpy.random.default_rng(0).uniform(-0.1, 0.1, n * n * n * 4)
         t0 = time.perf_counter()
@@ -226,17 +241,19 @@ def solve_roofline(it, step, peak_gbs):
     if step.get('method') == 'IDR':
         s = 8
         # vectors of 8n bytes moved per product by IDR(s) in the bi-orthogonal form, averaged over k = 0..s-1 and the
-        # omega step: v = r - G c (s-k+2), U_k (s-k+2), P^T G_k (s+1), bi-orthogonalisation of G_k, U_k (2(k+2)),
-        # r, x updates (6)
-        per_k = [(s - k + 2) + (s - k + 2) + (s + 1) + 2 * (k + 2) + 6 for k in range(s)]
-        comp['recurrence_vectors'] = 8 * n * (sum(per_k) + 12) // (s + 1)
+        # omega step: v = r - G c (s-k+2), U_k (s-k+2), P^T G_k (1), fused bi-orthogonalisation + update sweeps (2(k+4))
+        # (shadow vectors are generated on the fly: P^T G_k reads G_k only; the bi-orthogonalisation of G_k / U_k is fused
+        # with the update of r / x: k + 4 vectors per family)
+        per_k = [(s - k + 2) + (s - k + 2) + 1 + 2 * (k + 4) for k in range(s)]
+        comp['recurrence_vectors'] = 8 * n * (sum(per_k) + 10) // (s + 1)
     else:
         its = max(1, step['iterations'])
         comp['orthogonalisation_vectors'] = 8 * n * (its + 6)       # mean basis size its/2, read twice, plus w, z
     if step.get('precond') == 'tf32x3':
-        # r read, z written (fp64); fp32 planes of the `dim` velocity components: split off (w), x/y forward (r+w), Thomas
-        # (r+w + two factor arrays), x/y backward (r+w), merged (r); gradient product with the compact G (16 B per row)
-        comp['preconditioner'] = 16 * n + dim * ncell * 4 * 10 + 16 * dim * ncell
+        # r read, z written (fp64); per cell: two-slot gradient block (2 floats per velocity row), fp32 planes of the `dim`
+        # velocity components written by the head, x/y forward (r+w), Thomas (r+w + two factor arrays), x/y backward (r+w),
+        # read by the tail, pressure update (w+r)
+        comp['preconditioner'] = 16 * n + ncell * (8 * dim + 4 * dim + 8 * dim + 16 * dim + 8 * dim + 4 * dim + 8)
     else:
         comp['preconditioner'] = 16 * n + dim * ncell * 8 * 14       # six fp64 transforms (r+w) + scaling + (de)interleave
     total = sum(comp.values())
@@ -374,7 +391,6 @@ def main():
     if two_d:
         PARAMS.clear()
         PARAMS.update(two_d[0])
-        PARAMS['Iterative Solver'] = {'Maximum Iterations': 4000, 'Restart': 4000}
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -535,7 +551,9 @@ def main():
                   'fnorm_before': [h['fnorm'] for h in timed], 'all_converged': all(h['converged'] for h in hist),
                   'tolerance': 1e-10, 'unknowns': it.n,
                   'krylov_method': it.last_solve.get('method'),
-                  'solver': ('FGMRES + LSC block preconditioner, coupled (w,T) line solve + inner GMRES on the (u,T) block'
+                  'solver': ('direct: block-tridiagonal elimination over the grid lines, pivoted dense line inverses (csrc/tfb_direct.cu)'
+                             if it.last_solve.get('method') == 'Direct' else
+                             'FGMRES + LSC block preconditioner, coupled (w,T) line solve + inner GMRES on the (u,T) block'
                              if args.problem == 'rb' else
                              ('IDR(8)' if it.last_solve.get('method') == 'IDR' else 'FGMRES')
                              + (' + block preconditioner (FDM velocity solves, scaled-mass Schur complement)'
@@ -547,12 +565,15 @@ def main():
         # per-product roofline of the solve: algorithmic bytes of one IDR(s) operator product over
         # the measured time per product of the last timed solve
         try:
-            newton['roofline'] = solve_roofline(it, timed[-1], measured_peaks()[0])
+            if not two_d:
+                newton['roofline'] = solve_roofline(it, timed[-1], measured_peaks()[0])
         except Exception as e:     # noqa: BLE001
             newton['roofline'] = {'error': str(e)}
         # the same linear system with the fp64 SIMT preconditioner (the tensor-core path only steers the iteration: both
         # reach the same 1e-10 true residual) -- shows what the tcgen05 transforms buy
         try:
+            if two_d:
+                raise RuntimeError('not applicable to the direct solve of 2-D grids')
             saved = it.parameters.get('Iterative Solver')
             it.parameters['Iterative Solver'] = dict(saved or {}, **{'Preconditioner Precision': 'double'})
             it.solve(jac, -f)
@@ -622,6 +643,11 @@ def main():
         line['parity_slabs'] = slab_gate
     if rb_strong is not None:
         line['rb_strong'] = rb_strong
+    if not args.no_cpu_baseline and world == 1 and two_d:
+        pyref = python_reference_sample(grid2d=(two_d[1], two_d[2]))
+        line['cpu_baseline'] = {'value': pyref['assembly_cells_per_s'] if pyref and 'error' not in pyref else None, 'unit': 'cells/s',
+                                'cores': 1, 'kind': 'reference', 'sample': 'the full %dx%d grid, unmodified reference (SciPy backend)' % (two_d[1], two_d[2]),
+                                'python_reference': pyref}
     if not args.no_cpu_baseline and world == 1 and not two_d:
         planes = max(2, min(grid, 32))
         v, cores, dt = cpu_port_cells_per_s(grid, planes, repeats=2)

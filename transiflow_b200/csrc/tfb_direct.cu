@@ -11,6 +11,7 @@
 // all CTAs co-resident, two grid barriers per column.  Everything is fp64; the factors are cached on the tfb_mat like
 // `jac.lu` on the reference's matrices, so the second solve of a corrector step only pays the substitution.
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include "tfb_internal.h"
@@ -109,11 +110,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, un
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_gauss_jordan(int m, double* __restrict__ A, double* __restrict__ colbuf, double* __restrict__ rowbuf,
+template <int NT>
+__global__ void __launch_bounds__(NT) k_gauss_jordan(int m, double* __restrict__ A, double* __restrict__ colbuf, double* __restrict__ rowbuf,
                                                       int* __restrict__ piv, int* __restrict__ colsrc, unsigned* __restrict__ bar,
                                                       double* __restrict__ out, double tiny) {
-    __shared__ double s_val[256];
-    __shared__ int s_row[256];
+    __shared__ double s_val[32];
+    __shared__ int s_row[32];
     __shared__ int s_p;
     unsigned epoch = 0;
     const unsigned nb = gridDim.x;
@@ -158,15 +160,15 @@ __global__ void __launch_bounds__(256) k_gauss_jordan(int m, double* __restrict_
         }
         grid_barrier(bar, nb, epoch);
         const double pivinv = 1.0 / colbuf[k];
-        for (long long e = gtid; e < mm; e += gsz) {
-            const int i = (int)(e / m), j = (int)(e - (long long)i * m);
-            double v;
-            if (i == k) v = j == k ? pivinv : rowbuf[j] * pivinv;
-            else {
-                const double f = colbuf[i];
-                v = j == k ? -f * pivinv : A[e] - f * (rowbuf[j] * pivinv);
+        // one row per CTA at a time, threads along the row: coalesced, no index divisions
+        for (int i = blockIdx.x; i < m; i += gridDim.x) {
+            double* __restrict__ arow = A + (long long)i * m;
+            if (i == k) {
+                for (int j = threadIdx.x; j < m; j += blockDim.x) arow[j] = j == k ? pivinv : rowbuf[j] * pivinv;
+            } else {
+                const double f = colbuf[i] * pivinv;
+                for (int j = threadIdx.x; j < m; j += blockDim.x) arow[j] = j == k ? -f : arow[j] - f * rowbuf[j];
             }
-            A[e] = v;
         }
         grid_barrier(bar, nb, epoch);
     }
@@ -179,10 +181,86 @@ __global__ void __launch_bounds__(256) k_gauss_jordan(int m, double* __restrict_
         }
     }
     grid_barrier(bar, nb, epoch);
-    for (long long e = gtid; e < mm; e += gsz) {
-        const int i = (int)(e / m), j = (int)(e - (long long)i * m);
-        out[e] = A[(long long)i * m + colsrc[j]];
+    for (int i = blockIdx.x; i < m; i += gridDim.x)
+        for (int j = threadIdx.x; j < m; j += blockDim.x) out[(long long)i * m + j] = A[(long long)i * m + colsrc[j]];
+    (void)mm;
+}
+
+// the same elimination for a block that fits in shared memory (m <= 160): one CTA, no global round trips per column
+__global__ void __launch_bounds__(1024) k_gauss_jordan_smem(int m, const double* __restrict__ Ain, int* __restrict__ piv_g, unsigned* __restrict__ bar,
+                                                            double* __restrict__ out, double tiny) {
+    extern __shared__ double sm[];
+    double* A = sm;                       // m x (m + 1): padded rows, column accesses are conflict-free
+    const int ld = m + 1;
+    double* colbuf = A + (size_t)m * ld;
+    double* rowbuf = colbuf + m;
+    int* piv = reinterpret_cast<int*>(rowbuf + m);
+    int* colsrc = piv + m;
+    __shared__ double s_val[32];
+    __shared__ int s_row[32];
+    __shared__ int s_p;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < m * m; e += nt) A[(e / m) * ld + (e % m)] = Ain[e];
+    __syncthreads();
+    for (int k = 0; k < m; k++) {
+        double best = -1.0;
+        int brow = k;
+        for (int i = k + tid; i < m; i += nt) {
+            const double v = fabs(A[i * ld + k]);
+            if (v > best) { best = v; brow = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v = __shfl_xor_sync(0xffffffffu, best, o);
+            const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
+            if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
+        }
+        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_row[tid >> 5] = brow; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (nt >> 5); w++)
+                if (s_val[w] > s_val[0] || (s_val[w] == s_val[0] && s_row[w] < s_row[0])) { s_val[0] = s_val[w]; s_row[0] = s_row[w]; }
+            s_p = s_row[0];
+            piv[k] = s_row[0];
+            if (!(s_val[0] > tiny)) bar[1] = 1u;
+        }
+        __syncthreads();
+        const int p = s_p;
+        for (int j = tid; j < m; j += nt) {
+            const double ap = A[p * ld + j];
+            rowbuf[j] = ap;
+            double cv = A[j * ld + k];
+            if (j == k) cv = A[p * ld + k];
+            else if (j == p) cv = A[k * ld + k];
+            colbuf[j] = cv;
+        }
+        __syncthreads();
+        if (p != k)
+            for (int j = tid; j < m; j += nt)
+                if (j != k) A[p * ld + j] = A[k * ld + j];
+        __syncthreads();
+        const double pivinv = 1.0 / colbuf[k];
+        for (int i = tid >> 5; i < m; i += (nt >> 5)) {        // one warp per row, lanes along the row
+            double* arow = A + i * ld;
+            if (i == k) {
+                for (int j = tid & 31; j < m; j += 32) arow[j] = j == k ? pivinv : rowbuf[j] * pivinv;
+            } else {
+                const double f = colbuf[i] * pivinv;
+                for (int j = tid & 31; j < m; j += 32) arow[j] = j == k ? -f : arow[j] - f * rowbuf[j];
+            }
+        }
+        __syncthreads();
     }
+    if (tid == 0) {
+        for (int c = 0; c < m; c++) colsrc[c] = c;
+        for (int k = m - 1; k >= 0; k--) {
+            const int p = piv[k];
+            if (p != k) { const int t = colsrc[k]; colsrc[k] = colsrc[p]; colsrc[p] = t; }
+        }
+    }
+    __syncthreads();
+    for (int i = tid >> 5; i < m; i += (nt >> 5))
+        for (int j = tid & 31; j < m; j += 32) out[i * m + j] = A[i * ld + colsrc[j]];
+    (void)piv_g;
 }
 
 // ---- substitution ----
@@ -267,11 +345,17 @@ static int direct_factor(tfb_mat* mat, int prow) {
     const size_t mm = (size_t)m * m;
     // the persistent elimination kernel needs all its CTAs resident at once
     int per_sm = 0, sms = 0;
-    TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gauss_jordan, 256, 0));
+    TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gauss_jordan<256>, 256, 0));
     TFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->desc.device));
     // tiny blocks: one CTA (barriers are __syncthreads); otherwise ~8 elements per thread, at most two CTAs per SM
-    const int gj_grid = mm <= 256 * 16 ? 1
-                                       : (int)std::max<long long>(1, std::min<long long>((long long)sms * std::min(per_sm, 2), ((long long)mm + 256 * 8 - 1) / (256 * 8)));
+    static int single_max = -1;        // largest line block handled by ONE 1024-thread CTA (barriers are __syncthreads)
+    if (single_max < 0) { const char* e = getenv("TFB_DIRECT_SINGLE_MAX"); single_max = e ? atoi(e) : 128; }
+    const bool single = m <= single_max;
+    const size_t gj_smem = sizeof(double) * ((size_t)m * (m + 1) + 2 * (size_t)m) + sizeof(int) * 2 * (size_t)m;
+    const bool in_smem = gj_smem <= 200 * 1024;
+    if (in_smem) TFB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_smem));
+    const int gj_grid = single ? 1
+                               : (int)std::max<long long>(1, std::min<long long>((long long)sms * std::min(per_sm, 2), ((long long)mm + 256 * 8 - 1) / (256 * 8)));
     double amax = 0.0;   // scale for the singularity test: largest |value| of the matrix
     {
         std::vector<double> probe(std::min<size_t>((size_t)c->nnz, 4096));
@@ -292,7 +376,9 @@ static int direct_factor(tfb_mat* mat, int prow) {
             TFB_LAUNCHED(); TFB_LAUNCHED();
         }
         TFB_CUDA(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * 2, c->stream));
-        k_gauss_jordan<<<gj_grid, 256, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        if (in_smem) k_gauss_jordan_smem<<<1, 1024, gj_smem, c->stream>>>(m, f->S, f->piv, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        else if (single) k_gauss_jordan<1024><<<1, 1024, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        else k_gauss_jordan<256><<<gj_grid, 256, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
         TFB_LAUNCHED();
         TFB_CUDA(cudaGetLastError());
     }
