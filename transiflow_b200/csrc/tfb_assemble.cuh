@@ -25,6 +25,8 @@ struct TfbAsmArgs {
     int k0, nzl;
     int kc0;                  // first z-chunk handled by this launch (pipelined host path)
     int kstep;                // planes per z-chunk of this launch (<= KCH; the host pipeline uses half chunks)
+    int kofs0, klim;          // the chunks start at local plane kofs0 and stop before klim (z-slabs: interior planes first,
+                              // the two planes next to the halo after the exchange has landed)
 };
 
 template <class Cfg>
@@ -261,7 +263,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
     const int tid = (jl * DOF + d1) * 32 + il;
     const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
-    const int kbeg = (blockIdx.z + a.kc0) * a.kstep, kend = min(kbeg + a.kstep, a.nzl);   // local planes
+    const int kbeg = a.kofs0 + (blockIdx.z + a.kc0) * a.kstep, kend = min(kbeg + a.kstep, a.klim);   // local planes
     const int kofs = 1 - a.k0;
     const long long plane = (long long)g.nx * g.ny * DOF;
 

@@ -111,7 +111,17 @@ int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const
 // One-layer halo exchange of a slab vector stored with ghost planes:
 // [ghost below | owned planes | ghost above], plane = nx*ny*dof doubles.
 // Rank r owns planes directly above rank r-1 (z-slab order = rank order).
-int tfb_halo_exchange(tfb_ctx* c, double* v) {
+int tfb_halo_exchange(tfb_ctx* c, double* v) { return tfb_halo_exchange_on(c, v, c->stream); }
+
+// side stream + events for exchanges that run next to the interior part of a kernel
+int tfb_comm_stream(tfb_ctx* c) {
+    if (c->s_comm) return 0;
+    TFB_CUDA(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+    for (auto& e : c->ev_comm) TFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
+int tfb_halo_exchange_on(tfb_ctx* c, double* v, cudaStream_t stream) {
     if (c->nranks <= 1) return 0;
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
     ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
@@ -122,12 +132,12 @@ int tfb_halo_exchange(tfb_ctx* c, double* v) {
     double* ghost_hi = v + pl * (c->nzl + 1);
     TFB_NCCL(nccl.GroupStart());
     if (c->rank > 0) {
-        TFB_NCCL(nccl.Send(first_owned, pl, NCCL_FLOAT64, c->rank - 1, comm, c->stream));
-        TFB_NCCL(nccl.Recv(ghost_lo, pl, NCCL_FLOAT64, c->rank - 1, comm, c->stream));
+        TFB_NCCL(nccl.Send(first_owned, pl, NCCL_FLOAT64, c->rank - 1, comm, stream));
+        TFB_NCCL(nccl.Recv(ghost_lo, pl, NCCL_FLOAT64, c->rank - 1, comm, stream));
     }
     if (c->rank < c->nranks - 1) {
-        TFB_NCCL(nccl.Send(last_owned, pl, NCCL_FLOAT64, c->rank + 1, comm, c->stream));
-        TFB_NCCL(nccl.Recv(ghost_hi, pl, NCCL_FLOAT64, c->rank + 1, comm, c->stream));
+        TFB_NCCL(nccl.Send(last_owned, pl, NCCL_FLOAT64, c->rank + 1, comm, stream));
+        TFB_NCCL(nccl.Recv(ghost_hi, pl, NCCL_FLOAT64, c->rank + 1, comm, stream));
     }
     TFB_NCCL(nccl.GroupEnd());
     TFB_LAUNCHED();

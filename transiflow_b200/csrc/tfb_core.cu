@@ -108,6 +108,8 @@ extern "C" void tfb_destroy(tfb_ctx* c) {
     for (double* p : c->vals_pool) cudaFree(p);
     tfb_solver_free(c->solver);
     for (int e = 0; e < 16; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+    for (auto e : c->ev_comm) if (e) cudaEventDestroy(e);
+    if (c->s_comm) cudaStreamDestroy(c->s_comm);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -292,6 +294,7 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     a.nzl = c->nzl;
     a.kc0 = 0;
     a.kstep = 1;
+    a.kofs0 = 0; a.klim = c->nzl;
     constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
     size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
     auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ, MINB>;
@@ -323,7 +326,9 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     a.k0 = c->desc.k0;
     a.nzl = c->nzl;
     a.kstep = (c->chunk0 >= 0 && c->chunk_planes > 0) ? std::min(c->chunk_planes, KCH) : KCH;
-    const int nchunks = (c->nzl + a.kstep - 1) / a.kstep;
+    a.kofs0 = c->win1 >= 0 ? c->win0 : 0;
+    a.klim = c->win1 >= 0 ? c->win1 : c->nzl;
+    const int nchunks = (a.klim - a.kofs0 + a.kstep - 1) / a.kstep;
     a.kc0 = c->chunk0 >= 0 ? c->chunk0 : 0;
     const int nlaunch = c->chunk0 >= 0 ? std::min(c->chunkn, nchunks - a.kc0) : nchunks;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
@@ -431,11 +436,31 @@ extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f)
     TFB_CHECK(do_j || do_f, "nothing to do");
     TFB_CHECK(!do_j || (m && m->ctx == c), "matrix does not belong to this context");
     TFB_CUDA(cudaSetDevice(c->desc.device));
+    if (do_j) { m->version = tfb_next_version(); m->shift = 0.0; }
     if (c->nranks > 1) {
+        const bool marching = c->desc.dim == 3 && c->desc.nz > 1;
+        if (marching && c->nzl >= 4 && getenv("TFB_OVERLAP")) {
+            // the interior planes do not read the halo: exchange it on a side stream while they are assembled, then the
+            // two planes next to it.  OPT-IN (TFB_OVERLAP=1): green in the 2-rank parity test, but the 128^3 bench on
+            // 2 GPUs hung with it (unresolved), so the default exchanges the halo in front of the kernel
+            if (tfb_comm_stream(c)) return -1;
+            TFB_CUDA(cudaEventRecord(c->ev_comm[0], c->stream));
+            TFB_CUDA(cudaStreamWaitEvent(c->s_comm, c->ev_comm[0], 0));
+            if (tfb_halo_exchange_on(c, c->d_state, c->s_comm)) return -1;
+            TFB_CUDA(cudaEventRecord(c->ev_comm[1], c->s_comm));
+            c->win0 = 1; c->win1 = c->nzl - 1;
+            int rc = dispatch_assemble(c, m, do_j, do_f);
+            TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm[1], 0));
+            c->win0 = 0; c->win1 = 1;
+            if (!rc) rc = dispatch_assemble(c, m, do_j, do_f);
+            c->win0 = c->nzl - 1; c->win1 = c->nzl;
+            if (!rc) rc = dispatch_assemble(c, m, do_j, do_f);
+            c->win0 = 0; c->win1 = -1;
+            return rc;
+        }
         int rc = tfb_halo_exchange(c, c->d_state);
         if (rc) return rc;
     }
-    if (do_j) { m->version = tfb_next_version(); m->shift = 0.0; }
     return dispatch_assemble(c, m, do_j, do_f);
 }
 
@@ -633,6 +658,8 @@ static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_globa
         }
     }
     a.plane_nnz = c->plane_nnz;
+    a.kofs0 = c->win1 >= 0 ? c->win0 : 0;
+    a.klim = c->win1 >= 0 ? c->win1 : c->nzl;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(true);
     // the attribute is per device: set it when this instantiation meets a device for the first time
     static unsigned configured_devices = 0;
@@ -642,7 +669,7 @@ static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_globa
         configured_devices |= 1u << (c->desc.device & 31);
     }
     dim3 block(32, Cfg::DOF, TJ);
-    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (c->nzl + TFB_KCH - 1) / TFB_KCH);
+    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, (a.klim - a.kofs0 + TFB_KCH - 1) / TFB_KCH);
     if (rowmask || colmask) tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, true><<<grid, block, smem, c->stream>>>(a);
     else tfb_spmv_march_kernel<Cfg, TJ, TFB_KCH, false><<<grid, block, smem, c->stream>>>(a);
     TFB_LAUNCHED();

@@ -62,6 +62,10 @@ struct tfb_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[TFB_MAX_CHUNKS] = {}, ev_k[TFB_MAX_CHUNKS] = {};
     int chunk0 = -1, chunkn = 0, chunk_planes = 0;
+    int win0 = 0, win1 = -1;    // plane window [win0, win1) of the next assembly launch (win1 < 0: the whole slab)
+    // z-slabs: the halo exchange runs on its own stream next to the interior planes of the kernel that needs it
+    cudaStream_t s_comm = nullptr;
+    cudaEvent_t ev_comm[2] = {nullptr, nullptr};
     tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
     // value buffers of destroyed matrices, kept for the next tfb_mat_create: a Newton loop makes one Jacobian per
     // step and cudaMalloc/cudaFree of ~1 GB next to a 60 GB Krylov basis cost up to 0.6 s per call (measured)
@@ -86,6 +90,8 @@ int tfb_build_pattern(tfb_ctx* ctx);
 int tfb_spmv_structured(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
                         int prow, unsigned rowmask, unsigned colmask, const double* rowscale);
 int tfb_halo_exchange(tfb_ctx* ctx, double* d_vec_with_ghosts);
+int tfb_halo_exchange_on(tfb_ctx* ctx, double* d_vec_with_ghosts, cudaStream_t stream);
+int tfb_comm_stream(tfb_ctx* c);
 int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
 int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
                   double* recv, const long long* rcount, const long long* rdispl);

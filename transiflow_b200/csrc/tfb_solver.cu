@@ -247,17 +247,35 @@ static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, un
                 const double* rowscale = nullptr) {
     const long long threads = c->n_local * 8;
     const unsigned nb = (unsigned)((threads + 255) / 256);
+    static int use_structured = -1;
+    if (use_structured < 0) { const char* e = getenv("TFB_SPMV_CSR"); use_structured = !(e && e[0] == '1'); }
+    // planes of x that exist: the slab plus one halo plane on either side, clipped to the domain
+    const int kv0 = std::max(0, c->desc.k0 - 1), kv1 = std::min(c->desc.nz, c->desc.k1 + 1);
+    const bool marching = use_structured && c->desc.dim == 3 && c->desc.nz > 1;
+    if (c->nranks > 1 && marching && c->nzl >= 4 && ghost_capable(c, x) && getenv("TFB_OVERLAP")) {
+        // z-slabs: the halo planes of x travel on a side stream while the interior planes are multiplied; the two planes
+        // next to the halo follow when it has landed
+        if (dist_setup(c) || tfb_comm_stream(c)) return -1;
+        TFB_CUDA(cudaEventRecord(c->ev_comm[0], c->stream));
+        TFB_CUDA(cudaStreamWaitEvent(c->s_comm, c->ev_comm[0], 0));
+        if (tfb_halo_exchange_on(c, const_cast<double*>(x) - c->plane_rows, c->s_comm)) return -1;
+        TFB_CUDA(cudaEventRecord(c->ev_comm[1], c->s_comm));
+        const double* xs = x - c->row0;
+        c->win0 = 1; c->win1 = c->nzl - 1;
+        int rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
+        TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm[1], 0));
+        c->win0 = 0; c->win1 = 1;
+        if (rc == 0) rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
+        c->win0 = c->nzl - 1; c->win1 = c->nzl;
+        if (rc == 0) rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
+        c->win0 = 0; c->win1 = -1;
+        if (rc <= 0) return rc;
+    }
     const double* xs = nullptr;
     if (ghosted(c, x, &xs)) return -1;
-    {   // true 3-D grids: structured kernel that never reads the column indices
-        static int use_structured = -1;
-        if (use_structured < 0) { const char* e = getenv("TFB_SPMV_CSR"); use_structured = !(e && e[0] == '1'); }
-        if (use_structured) {
-            // planes of x that exist: the slab plus one halo plane on either side, clipped to the domain
-            const int kv0 = std::max(0, c->desc.k0 - 1), kv1 = std::min(c->desc.nz, c->desc.k1 + 1);
-            const int rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
-            if (rc <= 0) return rc;
-        }
+    if (use_structured) {   // true 3-D grids: structured kernel that never reads the column indices
+        const int rc = tfb_spmv_structured(c, m, xs, kv0, kv1, y, prow, rowmask, colmask, rowscale);
+        if (rc <= 0) return rc;
     }
     const int pl = local_prow(c, prow);
     if (rowmask)

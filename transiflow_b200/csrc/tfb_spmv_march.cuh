@@ -24,6 +24,7 @@ struct TfbSpmvArgs {
     int prow_cell_i, prow_cell_j, prow_cell_k, pvar;   // pinned pressure unknown (pvar < 0: none)
     unsigned rowmask, colmask;                          // 0 = all
     int plane_nnz;            // structural non-zeros of a plane away from the z walls (0: unknown, always read row_ptr)
+    int kofs0, klim;          // local planes [kofs0, klim) of this launch
 };
 
 __device__ __forceinline__ void tfb_mbar_init(unsigned long long* bar, unsigned count) {
@@ -106,7 +107,7 @@ tfb_spmv_march_kernel(const TfbSpmvArgs a) {
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
     const int tid = (jl * DOF + d1) * 32 + il;
     const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
-    const int kbeg = blockIdx.z * KCH, kend = min(kbeg + KCH, a.nzl);
+    const int kbeg = a.kofs0 + blockIdx.z * KCH, kend = min(kbeg + KCH, a.klim);
     const long long plane = (long long)g.nx * g.ny * DOF;
 
     int l_src[NPT], l_dst[NPT];
