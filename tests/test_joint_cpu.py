@@ -141,6 +141,25 @@ def test_line_solve_equals_the_dense_mode_solve():
         assert numpy.allclose(w[:nz - 1, q], y[1::2], rtol=1e-9, atol=1e-12)
 
 
+def test_factor_then_substitute_equals_the_one_shot_line_solve():
+    '''The device path factors every mode once per matrix and only substitutes per application.'''
+    m = JointModel(PARAMS, 6, 5, 9)
+    nz = m.nz
+    rng = numpy.random.default_rng(3)
+    mus = numpy.ascontiguousarray(-rng.uniform(0.1, 30.0, 5))
+    w = rng.standard_normal((nz, 5)); w[nz - 1] = 0
+    T = rng.standard_normal((nz, 5))
+    w1, T1, w2, T2 = w.copy(), T.copy(), w.copy(), T.copy()
+    al = numpy.empty((2 * nz, 5)); be = numpy.empty((2 * nz, 5))
+    fac = numpy.zeros((4, 2 * nz - 1, 5))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L = _lib()
+    L.tfh_joint_lines(nz, P(m.zc), 5, P(mus), ctypes.c_double(m.cv), ctypes.c_double(m.cT), P(w1), P(T1), P(al), P(be))
+    L.tfh_joint_factor_substitute(nz, P(m.zc), 5, P(mus), ctypes.c_double(m.cv), ctypes.c_double(m.cT), P(w2), P(T2), P(fac))
+    assert numpy.allclose(T2, T1, rtol=1e-12, atol=1e-14)
+    assert numpy.allclose(w2[:nz - 1], w1[:nz - 1], rtol=1e-12, atol=1e-14)
+
+
 def _gmres_steps(op, prec, b, k):
     '''relative residuals of right-preconditioned GMRES after 1..k steps'''
     beta = numpy.linalg.norm(b)

@@ -92,3 +92,89 @@ TFB_HD void tfb_joint_line(int nz, const double* __restrict__ zc, double mu, dou
         y2 = y1; y1 = y;
     }
 }
+
+// ---- the same solve split into a factorisation (once per matrix) and a substitution (every application) ----
+// The pivots and the eliminated bands depend on (mode, row) but not on the right-hand side.  tfb_joint_factor_line
+// stores, for row i of the interleaved system, the modified first sub-diagonal s1', 1 / pivot and the two upper bands
+// (FT: float on the tensor-core path); tfb_joint_substitute_line then needs two fused multiply-adds per band and unknown
+// and no division.  Entry i of a factor array sits at [i * stride].
+template <class FT>
+TFB_HD void tfb_joint_factor_line(int nz, const double* __restrict__ zc, double mu, double cv, double cT, long long stride,
+                                  FT* __restrict__ s1p, FT* __restrict__ piv, FT* __restrict__ al, FT* __restrict__ be) {
+    const double* KW_LO = zc + TFB_JZ_KW_LO * nz; const double* KW_D = zc + TFB_JZ_KW_D * nz;
+    const double* KW_UP = zc + TFB_JZ_KW_UP * nz; const double* MW = zc + TFB_JZ_MW * nz;
+    const double* KT_LO = zc + TFB_JZ_KT_LO * nz; const double* KT_D = zc + TFB_JZ_KT_D * nz;
+    const double* KT_UP = zc + TFB_JZ_KT_UP * nz; const double* MT = zc + TFB_JZ_MT * nz;
+    const double* B0 = zc + TFB_JZ_B0 * nz; const double* BP = zc + TFB_JZ_BP * nz;
+    const double* C0 = zc + TFB_JZ_C0 * nz; const double* CM = zc + TFB_JZ_CM * nz;
+    double a2p = 0.0, b2p = 0.0, a1p = 0.0, b1p = 0.0;
+    for (int k = 0; k < nz; k++) {
+        {
+            const double s2 = k > 0 ? cT * KT_LO[k] : 0.0;
+            double s1 = k > 0 ? CM[k] : 0.0;
+            double d = cT * (mu * MT[k] + KT_D[k]);
+            double c1 = k < nz - 1 ? C0[k] : 0.0;
+            const double c2 = k < nz - 1 ? cT * KT_UP[k] : 0.0;
+            s1 -= s2 * a2p; d -= s2 * b2p;
+            d -= s1 * a1p; c1 -= s1 * b1p;
+            const double inv = 1.0 / d;
+            a2p = a1p; b2p = b1p;
+            a1p = c1 * inv; b1p = c2 * inv;
+            const long long o = (2LL * k) * stride;
+            s1p[o] = (FT)s1; piv[o] = (FT)inv; al[o] = (FT)a1p; be[o] = (FT)b1p;
+        }
+        if (k < nz - 1) {
+            const double s2 = k > 0 ? cv * KW_LO[k] : 0.0;
+            double s1 = B0[k];
+            double d = cv * (mu * MW[k] + KW_D[k]);
+            double c1 = BP[k];
+            const double c2 = k < nz - 2 ? cv * KW_UP[k] : 0.0;
+            s1 -= s2 * a2p; d -= s2 * b2p;
+            d -= s1 * a1p; c1 -= s1 * b1p;
+            const double inv = 1.0 / d;
+            a2p = a1p; b2p = b1p;
+            a1p = c1 * inv; b1p = c2 * inv;
+            const long long o = (2LL * k + 1) * stride;
+            s1p[o] = (FT)s1; piv[o] = (FT)inv; al[o] = (FT)a1p; be[o] = (FT)b1p;
+        }
+    }
+}
+
+// w, T: right-hand sides on entry, solution on exit (plane k at [k * stride]); arithmetic in AT (float or double)
+template <class AT, class VT, class FT>
+TFB_HD void tfb_joint_substitute_line(int nz, const double* __restrict__ zc, double cv, double cT, long long stride,
+                                      VT* __restrict__ w, VT* __restrict__ T, const FT* __restrict__ s1p,
+                                      const FT* __restrict__ piv, const FT* __restrict__ al, const FT* __restrict__ be) {
+    const double* KW_LO = zc + TFB_JZ_KW_LO * nz;
+    const double* KT_LO = zc + TFB_JZ_KT_LO * nz;
+    AT g1 = 0, g2 = 0;        // g_{i-1}, g_{i-2}
+    for (int k = 0; k < nz; k++) {
+        {
+            const long long o = (2LL * k) * stride;
+            const AT s2 = k > 0 ? (AT)(cT * KT_LO[k]) : (AT)0;
+            const AT g = ((AT)T[k * stride] - s2 * g2 - (AT)s1p[o] * g1) * (AT)piv[o];
+            T[k * stride] = (VT)g;
+            g2 = g1; g1 = g;
+        }
+        if (k < nz - 1) {
+            const long long o = (2LL * k + 1) * stride;
+            const AT s2 = k > 0 ? (AT)(cv * KW_LO[k]) : (AT)0;
+            const AT g = ((AT)w[k * stride] - s2 * g2 - (AT)s1p[o] * g1) * (AT)piv[o];
+            w[k * stride] = (VT)g;
+            g2 = g1; g1 = g;
+        }
+    }
+    AT y1 = 0, y2 = 0;
+    for (int k = nz - 1; k >= 0; k--) {
+        if (k < nz - 1) {
+            const long long o = (2LL * k + 1) * stride;
+            const AT y = (AT)w[k * stride] - (AT)al[o] * y1 - (AT)be[o] * y2;
+            w[k * stride] = (VT)y;
+            y2 = y1; y1 = y;
+        }
+        const long long o = (2LL * k) * stride;
+        const AT y = (AT)T[k * stride] - (AT)al[o] * y1 - (AT)be[o] * y2;
+        T[k * stride] = (VT)y;
+        y2 = y1; y1 = y;
+    }
+}

@@ -91,6 +91,9 @@ struct tfb_solver_state {
     double* d_jz = nullptr;       // TFB_JZ_ROWS x nz coefficient table
     double* jbuf[2] = {nullptr, nullptr};   // 2 x ncell each: [w planes | T planes]
     double* jab = nullptr;        // 4 x ncell: the two upper bands of the line factorisations
+    float* jfac = nullptr;        // tensor-core path: 4 x (2 nz - 1) x modes factors of every mode (tfb_joint_factor_line)
+    const tfb_mat* jfac_owner = nullptr;
+    uint64_t jfac_version = ~0ull;
     const tfb_mat* jz_owner = nullptr;
     uint64_t jz_version = ~0ull;
     int sub_prow = -2;
@@ -156,7 +159,7 @@ void tfb_solver_free(tfb_solver_state* s) {
     cudaFree(s->gell); cudaFree(s->dp32); cudaFree(s->gell_misfit);
     for (auto p : s->d_ih) cudaFree(p);
     for (SubCsr* q : {&s->subG, &s->subD, &s->subB, &s->subC}) { cudaFree(q->row_ptr); cudaFree(q->col); cudaFree(q->src); cudaFree(q->vals); }
-    cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab);
+    cudaFree(s->d_jz); cudaFree(s->jbuf[0]); cudaFree(s->jbuf[1]); cudaFree(s->jab); cudaFree(s->jfac);
     cudaFree(s->d_mass);
     for (auto p : s->comp) cudaFree(p);
     for (auto p : s->vec_base) cudaFree(p);
@@ -1164,6 +1167,115 @@ k_joint_lines(int ex, int ey, int jofs, int nz, const double* __restrict__ zc, c
     tfb_joint_line(nz, s_zc, mu, cv, cT, modes, w + m, T + m, al + m, be + m);
 }
 
+// factor every horizontal mode once per matrix / substitute per application (tensor-core path, fp32 storage)
+__global__ void __launch_bounds__(128)
+k_joint_factor(int ex, int ey, int nz, const double* __restrict__ zc, const double* __restrict__ lx, const double* __restrict__ ly,
+               double cv, double cT, float* __restrict__ fac) {
+    extern __shared__ double s_zc[];
+    for (int q = threadIdx.x; q < TFB_JZ_ROWS * nz; q += blockDim.x) s_zc[q] = zc[q];
+    __syncthreads();
+    const long long modes = (long long)ex * ey, span = (long long)(2 * nz - 1) * modes;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= modes) return;
+    const double mu = lx[m % ex] + ly[m / ex];
+    tfb_joint_factor_line<float>(nz, s_zc, mu, cv, cT, modes, fac + m, fac + span + m, fac + 2 * span + m, fac + 3 * span + m);
+}
+// Substitution of tfb_joint_substitute_line (csrc/tfb_joint.h, the tested statement of the recurrences) with the loads of
+// KB planes (2 KB rows of the interleaved system) issued ahead of the dependent chain, software-pipelined: one thread per
+// mode would otherwise pay a memory latency per row.
+template <int KB>
+__global__ void __launch_bounds__(128)
+k_joint_substitute(int ex, int ey, int nz, const double* __restrict__ zc, double cv, double cT, float* __restrict__ w,
+                   float* __restrict__ T, const float* __restrict__ fac) {
+    extern __shared__ double s_zc[];
+    for (int q = threadIdx.x; q < TFB_JZ_ROWS * nz; q += blockDim.x) s_zc[q] = zc[q];
+    __syncthreads();
+    const long long st = (long long)ex * ey, span = (long long)(2 * nz - 1) * st;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= st) return;
+    const double* KW_LO = s_zc + TFB_JZ_KW_LO * nz;
+    const double* KT_LO = s_zc + TFB_JZ_KT_LO * nz;
+    float* wp = w + m;
+    float* Tp = T + m;
+    const float* s1p = fac + m;
+    const float* piv = fac + span + m;
+    const float* al = fac + 2 * span + m;
+    const float* be = fac + 3 * span + m;
+    // ---- forward: g_i = (r_i - s2_i g_{i-2} - s1'_i g_{i-1}) / pivot_i, rows (T_k, w_k) of KB planes per block ----
+    float rT[KB], rw[KB], a0[KB], p0[KB], a1[KB], p1[KB], nT[KB], nw[KB], na0[KB], np0[KB], na1[KB], np1[KB];
+    auto load_f = [&](int k0, float (&xT)[KB], float (&xw)[KB], float (&s0)[KB], float (&q0)[KB], float (&s1)[KB], float (&q1)[KB]) {
+#pragma unroll
+        for (int t = 0; t < KB; t++) {
+            const int k = k0 + t;
+            const bool okT = k < nz, okw = k < nz - 1;
+            xT[t] = okT ? Tp[(long long)k * st] : 0.f;
+            s0[t] = okT ? s1p[(2LL * k) * st] : 0.f;
+            q0[t] = okT ? piv[(2LL * k) * st] : 0.f;
+            xw[t] = okw ? wp[(long long)k * st] : 0.f;
+            s1[t] = okw ? s1p[(2LL * k + 1) * st] : 0.f;
+            q1[t] = okw ? piv[(2LL * k + 1) * st] : 0.f;
+        }
+    };
+    float g1 = 0.f, g2 = 0.f;
+    load_f(0, rT, rw, a0, p0, a1, p1);
+    for (int k0 = 0; k0 < nz; k0 += KB) {
+        if (k0 + KB < nz) load_f(k0 + KB, nT, nw, na0, np0, na1, np1);
+#pragma unroll
+        for (int t = 0; t < KB; t++) {
+            const int k = k0 + t;
+            if (k < nz) {
+                const float s2 = k > 0 ? (float)(cT * KT_LO[k]) : 0.f;
+                const float g = (rT[t] - s2 * g2 - a0[t] * g1) * p0[t];
+                Tp[(long long)k * st] = g;
+                g2 = g1; g1 = g;
+            }
+            if (k < nz - 1) {
+                const float s2 = k > 0 ? (float)(cv * KW_LO[k]) : 0.f;
+                const float g = (rw[t] - s2 * g2 - a1[t] * g1) * p1[t];
+                wp[(long long)k * st] = g;
+                g2 = g1; g1 = g;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KB; t++) { rT[t] = nT[t]; rw[t] = nw[t]; a0[t] = na0[t]; p0[t] = np0[t]; a1[t] = na1[t]; p1[t] = np1[t]; }
+    }
+    // ---- backward: y_i = g_i - al_i y_{i+1} - be_i y_{i+2} ----
+    auto load_b = [&](int k1, float (&xT)[KB], float (&xw)[KB], float (&s0)[KB], float (&q0)[KB], float (&s1)[KB], float (&q1)[KB]) {
+#pragma unroll
+        for (int t = 0; t < KB; t++) {
+            const int k = k1 - 1 - t;
+            const bool okT = k >= 0, okw = k >= 0 && k < nz - 1;
+            xT[t] = okT ? Tp[(long long)k * st] : 0.f;
+            s0[t] = okT ? al[(2LL * k) * st] : 0.f;
+            q0[t] = okT ? be[(2LL * k) * st] : 0.f;
+            xw[t] = okw ? wp[(long long)k * st] : 0.f;
+            s1[t] = okw ? al[(2LL * k + 1) * st] : 0.f;
+            q1[t] = okw ? be[(2LL * k + 1) * st] : 0.f;
+        }
+    };
+    float y1 = 0.f, y2 = 0.f;
+    load_b(nz, rT, rw, a0, p0, a1, p1);
+    for (int k1 = nz; k1 > 0; k1 -= KB) {
+        if (k1 - KB > 0) load_b(k1 - KB, nT, nw, na0, np0, na1, np1);
+#pragma unroll
+        for (int t = 0; t < KB; t++) {
+            const int k = k1 - 1 - t;
+            if (k >= 0 && k < nz - 1) {
+                const float y = rw[t] - a1[t] * y1 - p1[t] * y2;
+                wp[(long long)k * st] = y;
+                y2 = y1; y1 = y;
+            }
+            if (k >= 0) {
+                const float y = rT[t] - a0[t] * y1 - p0[t] * y2;
+                Tp[(long long)k * st] = y;
+                y2 = y1; y1 = y;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KB; t++) { rT[t] = nT[t]; rw[t] = nw[t]; a0[t] = na0[t]; p0[t] = np0[t]; a1[t] = na1[t]; p1[t] = np1[t]; }
+    }
+}
+
 __global__ void k_negate_var(long long ncell, int dof, int v, const double* __restrict__ r, double* __restrict__ z) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x)
         z[i * dof + v] = -r[i * dof + v];
@@ -1265,7 +1377,6 @@ static int joint_solve_tc(tfb_ctx* c, const double* r, double* z) {
     TFB_CHECK(tc_ready(c, wv) && s->var[sv].present && f.m[0] == nx && f.m[1] == ny, "tensor-core basis of the vertical velocity missing");
     const long long plane = (long long)nx * ny, ncell = plane * nzl;
     if (tc_buffers(c)) return -1;
-    if (!s->jab) TFB_CUDA(cudaMalloc(&s->jab, sizeof(double) * 4 * ncell));
     float* a[2] = {s->tc32[0], s->tc32[0] + s->tc32_cap};
     float* b[2] = {s->tc32[1], s->tc32[1] + s->tc32_cap};
     const int basis[2] = {wv, wv};
@@ -1275,8 +1386,16 @@ static int joint_solve_tc(tfb_ctx* c, const double* r, double* z) {
     TFB_LAUNCHED();
     if (tc_planes(c, 2, basis, a, b, false)) return -1;
     const size_t jsmem = sizeof(double) * TFB_JZ_ROWS * nz;
-    k_joint_lines<float><<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(
-        nx, ny, 0, nz, s->d_jz, f.lam[0], f.lam[1], f.coef, s->var[sv].coef, b[0], b[1], s->jab, s->jab + 2 * ncell);
+    if (!s->jfac) TFB_CUDA(cudaMalloc(&s->jfac, sizeof(float) * 4 * (size_t)(2 * nz - 1) * plane));
+    if (s->jfac_owner != s->jz_owner || s->jfac_version != s->jz_version) {
+        // the couplings were re-read for this matrix (joint_refresh): factor all modes once, every application substitutes
+        k_joint_factor<<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(nx, ny, nz, s->d_jz, f.lam[0], f.lam[1], f.coef,
+                                                                                   s->var[sv].coef, s->jfac);
+        TFB_LAUNCHED();
+        s->jfac_owner = s->jz_owner; s->jfac_version = s->jz_version;
+    }
+    k_joint_substitute<4><<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(nx, ny, nz, s->d_jz, f.coef, s->var[sv].coef,
+                                                                                   b[0], b[1], s->jfac);
     TFB_LAUNCHED();
     if (tc_planes(c, 2, basis, b, a, true)) return -1;
     tfbtc::IntArgs ia{};
@@ -1316,10 +1435,60 @@ static int velocity_fdm(tfb_ctx* c, const double* r, double* z, int skip = -1) {
 // Approximate inverse of the block the velocity sub-solve works on.  Default: the velocity block,
 // one FDM (diffusion) solve per component.  Coupled mode (Rayleigh-Benard): the (velocity, scalar)
 // block -- horizontal components by FDM, (w, T) by the coupled line solve.
+// Tensor-core version of the coupled block: u, v (diffusion solves) and (w, T) (coupled line solve) share one pass of
+// the plane kernel in each direction -- four arrays per launch instead of two launches of two.
+static int block_fdm_tc_joint(tfb_ctx* c, const double* r, double* z) {
+    tfb_solver_state* s = c->solver;
+    const int nx = c->desc.nx, ny = c->desc.ny, nz = c->desc.nz, dof = c->desc.dof;
+    const int wv = s->joint_w, sv = s->joint_s;
+    const FdmVar& fw = s->var[wv];
+    TFB_CHECK(tc_ready(c, 0) && tc_ready(c, 1) && tc_ready(c, wv) && s->var[sv].present && fw.m[0] == nx && fw.m[1] == ny,
+              "tensor-core data of the coupled block missing");
+    const long long plane = (long long)nx * ny, ncell = plane * c->nzl;
+    if (tc_buffers(c)) return -1;
+    if (tc_thomas_setup(c, 0) || tc_thomas_setup(c, 1)) return -1;
+    const int vars[4] = {0, 1, wv, sv}, basis[4] = {0, 1, wv, wv};
+    float *a[4], *b[4];
+    tfbtc::DeintArgs da{};
+    tfbtc::IntArgs ia{};
+    for (int q = 0; q < 4; q++) {
+        a[q] = s->tc32[0] + (size_t)q * s->tc32_cap;
+        b[q] = s->tc32[1] + (size_t)q * s->tc32_cap;
+        da.comp[q] = a[q]; da.var[q] = vars[q];
+        ia.comp[q] = a[q]; ia.var[q] = vars[q];
+        const FdmVar& f = s->var[vars[q]];
+        ia.mx[q] = q < 2 ? f.m[0] : nx; ia.my[q] = q < 2 ? f.m[1] : ny;
+        ia.mz[q] = q < 2 ? f.m[2] : (q == 2 ? nz - 1 : nz);      // top-wall rows of w: -r
+    }
+    da.nv = 4; da.dof = dof; da.ncell = ncell;
+    ia.nv = 4; ia.dof = dof; ia.nx = nx; ia.ny = ny; ia.k0 = c->desc.k0; ia.ncell = ncell;
+    tfbtc::tfb_deint_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(da, r, nullptr);
+    TFB_LAUNCHED();
+    if (tc_planes(c, 4, basis, a, b, false)) return -1;
+    if (tc_thomas(c, 2, vars, b, plane, nullptr)) return -1;
+    const size_t jsmem = sizeof(double) * TFB_JZ_ROWS * nz;
+    if (!s->jfac) TFB_CUDA(cudaMalloc(&s->jfac, sizeof(float) * 4 * (size_t)(2 * nz - 1) * plane));
+    if (s->jfac_owner != s->jz_owner || s->jfac_version != s->jz_version) {
+        k_joint_factor<<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(nx, ny, nz, s->d_jz, fw.lam[0], fw.lam[1], fw.coef,
+                                                                                   s->var[sv].coef, s->jfac);
+        TFB_LAUNCHED();
+        s->jfac_owner = s->jz_owner; s->jfac_version = s->jz_version;
+    }
+    k_joint_substitute<4><<<(unsigned)((plane + 127) / 128), 128, jsmem, c->stream>>>(nx, ny, nz, s->d_jz, fw.coef, s->var[sv].coef,
+                                                                                   b[2], b[3], s->jfac);
+    TFB_LAUNCHED();
+    if (tc_planes(c, 4, basis, b, a, true)) return -1;
+    tfbtc::tfb_int_kernel<<<vec_blocks(ncell), 256, 0, c->stream>>>(ia, r, nullptr, z);
+    TFB_LAUNCHED();
+    TFB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <class FT>
 static int block_fdm(tfb_ctx* c, const double* r, double* z) {
     tfb_solver_state* s = c->solver;
     if (!s->joint_on) return velocity_fdm<FT>(c, r, z);
+    if (s->precond_tc && c->nranks == 1 && c->desc.dim == 3) return block_fdm_tc_joint(c, r, z);
     if (velocity_fdm<FT>(c, r, z, s->joint_w)) return -1;
     return joint_solve(c, r, z);
 }
