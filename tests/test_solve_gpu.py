@@ -131,6 +131,57 @@ def test_complex_right_hand_side_is_solved_by_parts():
     assert numpy.abs(y.real - again).max() <= 1e-12 * numpy.abs(again).max()
 
 
+def test_complex_shifted_matrices_are_solved_on_the_device():
+    """`beta * J - alpha * M` with complex alpha, the matrix the reference's JaDa glue hands to solve() (JaDa.py:90,
+    149-151,187; SuperLU on a complex matrix there): solved with a complex Krylov iteration on device operators."""
+    import scipy.sparse.linalg
+    it = _iface({'Reynolds Number': 50}, 6, 6, 6)
+    x = numpy.random.default_rng(0).uniform(-0.1, 0.1, it.n)
+    jac, mass = it.jacobian(x), it.mass_matrix()
+    shifted = 1.0 * jac - (0.3 + 0.7j) * mass                  # scipy complex matrix, as JaDa builds it
+    assert numpy.iscomplexobj(shifted.data)
+    rng = numpy.random.default_rng(2)
+    b = rng.uniform(-1, 1, it.n) + 1j * rng.uniform(-1, 1, it.n)
+    y = it.solve(shifted, b)
+    assert it.last_solve['converged'], it.last_solve
+    A = shifted.tolil()
+    A[3, :] = 0
+    A[:, 3] = 0
+    A[3, 3] = -1
+    bb = b.copy()
+    bb[3] = 0
+    want = scipy.sparse.linalg.spsolve(A.tocsc(), bb)
+    assert numpy.abs(y - want).max() <= 1e-8 * numpy.abs(want).max()
+
+
+def test_eigs_with_a_complex_target():
+    """'Target': 1 + 3j style targets (the reference's test configuration stores one, tests/test_interface.py:97):
+    eigenvalues closest to a complex shift, against the dense generalized eigenvalues of the oracle's pinned pencil."""
+    import scipy.linalg
+    from oracle.tf_oracle import Oracle
+    from transiflow_b200 import Interface
+    params = {'Problem Type': 'Lid-driven Cavity', 'Reynolds Number': 100.0, 'Lid Velocity': 1.0}
+    nx = ny = 8
+    o = Oracle(dict(params), nx, ny, 1)
+    state = 0.05 * numpy.random.default_rng(3).standard_normal(o.n)
+    J = o.jacobian_csr(state).tolil()
+    J[o.dim, :] = 0
+    J[:, o.dim] = 0
+    J[o.dim, o.dim] = -1
+    mco, mj, mb = o.mass_matrix()
+    M = numpy.zeros(o.n)
+    M[mj] = mco
+    lam = scipy.linalg.eig(J.toarray(), numpy.diag(M), right=False)
+    lam = lam[numpy.isfinite(lam)]
+    target, num = -20.0 + 5.0j, 3
+    want = lam[numpy.argsort(numpy.abs(lam - target))[:num]]
+    params['Eigenvalue Solver'] = {'Target': target, 'Number of Eigenvalues': num, 'Tolerance': 1e-8}
+    it = Interface(params, nx, ny, 1)
+    got = it.eigs(state)
+    dist = numpy.abs(want[:num - 1, None] - got[None, :]).min(axis=1)
+    assert dist.max() <= 1e-6 * max(1.0, numpy.abs(want).max())
+
+
 def test_time_integration_operators():
     """TimeIntegration._newton (TimeIntegration.py:40-73) builds `jacobian(x) - mass / (theta*dt)` and
     `mass @ v` with the backend's matrix types and hands the result to solve()."""

@@ -17,21 +17,22 @@ import numpy
 def shift_invert_arnoldi(apply_op, n, num=5, target=0.0, tol=1e-7, max_dim=60, v0=None, real_cap=100.0):
     '''Eigenvalues (and Ritz vectors) of the pencil closest to ``target``.
 
-    apply_op(v) must return ``(J - target M)^-1 M v`` for a real vector v.
+    apply_op(v) must return ``(J - target M)^-1 M v``; the Arnoldi basis is complex when the target is.
     Returns ``(eigenvalues[num], vectors[n, num], converged)``; eigenvalues are sorted like the
     reference (descending real part, values with real part >= real_cap last,
     BaseInterface.py:349-361).
     '''
     rng = numpy.random.default_rng(1234)
-    v = numpy.array(v0, dtype=float) if v0 is not None else rng.standard_normal(n)
+    dtype = numpy.complex128 if isinstance(target, complex) else float
+    v = numpy.array(v0, dtype=dtype) if v0 is not None else rng.standard_normal(n).astype(dtype)
     # start in the range of the operator: removes the components the mass matrix annihilates
     v = apply_op(v)
     nrm = numpy.linalg.norm(v)
     if not numpy.isfinite(nrm) or nrm == 0.0:
         raise RuntimeError('shift-invert operator returned a zero / non-finite vector')
     m = max(int(max_dim), num + 2)
-    V = numpy.zeros((n, m + 1))
-    H = numpy.zeros((m + 1, m))
+    V = numpy.zeros((n, m + 1), dtype=dtype)
+    H = numpy.zeros((m + 1, m), dtype=dtype)
     V[:, 0] = v / nrm
     theta = y = None
     sel = None
@@ -40,9 +41,9 @@ def shift_invert_arnoldi(apply_op, n, num=5, target=0.0, tol=1e-7, max_dim=60, v
     for j in range(m):
         w = apply_op(V[:, j])
         # classical Gram-Schmidt, two sweeps
-        h = V[:, :j + 1].T @ w
+        h = V[:, :j + 1].conj().T @ w
         w = w - V[:, :j + 1] @ h
-        h2 = V[:, :j + 1].T @ w
+        h2 = V[:, :j + 1].conj().T @ w
         w = w - V[:, :j + 1] @ h2
         H[:j + 1, j] = h + h2
         hn = numpy.linalg.norm(w)

@@ -96,8 +96,13 @@ class DeviceMatrix:
         from scipy import sparse
         interface._require_whole_grid('DeviceMatrix.from_scipy')
         A = sparse.csr_matrix(A)
-        if A.shape != (interface.n, interface.n) or numpy.iscomplexobj(A.data):
-            raise NotImplementedError('only real matrices of the Interface size can be uploaded')
+        if A.shape != (interface.n, interface.n):
+            raise NotImplementedError('only matrices of the Interface size can be uploaded')
+        if numpy.iscomplexobj(A.data):
+            if not numpy.any(A.imag.data):
+                A = A.real
+            else:
+                return ComplexDeviceMatrix(cls.from_scipy(interface, A.real), cls.from_scipy(interface, A.imag))
         A.sum_duplicates()
         A.sort_indices()
         row_ptr, col = interface.pattern()
@@ -207,6 +212,22 @@ class DeviceMatrix:
 
 def _host_matrix(m):
     return m.tocsc() if isinstance(m, DeviceMatrix) else m
+
+
+class ComplexDeviceMatrix:
+    '''A complex matrix on the structural pattern, e.g. the shifted matrix ``beta * J - alpha * M`` of the eigen-solver
+    glue with a complex shift (JaDa.py:90,187): real and imaginary parts as two DeviceMatrix handles.  ``solve`` treats
+    it with a complex Krylov iteration whose products and preconditioner applications run on the device.'''
+
+    def __init__(self, real, imag):
+        self.real, self.imag = real, imag
+        self.shape = real.shape
+        self.dtype = numpy.dtype(numpy.complex128)
+
+    def __matmul__(self, x):
+        x = numpy.asarray(x)
+        xr, xi = numpy.ascontiguousarray(x.real, dtype=float), numpy.ascontiguousarray(x.imag, dtype=float)
+        return (self.real @ xr - self.imag @ xi) + 1j * (self.imag @ xr + self.real @ xi)
 
 
 class Interface:
@@ -466,7 +487,7 @@ class Interface:
         '''Solve ``J y = rhs`` (pressure pinned at row ``dim`` when dof > dim, SciPy.py:212-216)
         with the preconditioned Krylov solver on the device (IDR(s) / FGMRES / BiCGStab, see ``_solve_pinned``).  With a border (``rhs2, V, W, C``) the
         bordered system is reduced to two solves with J and a 1x1 Schur complement.'''
-        if not isinstance(jac, DeviceMatrix):
+        if not isinstance(jac, (DeviceMatrix, ComplexDeviceMatrix)):
             # host matrices built from ours (TimeIntegration's J - M/(theta dt), real shifts):
             # re-upload onto the structural pattern, cached on the matrix object like `jac.lu`
             dev = getattr(jac, '_tfb_device', None)
@@ -479,6 +500,8 @@ class Interface:
             jac = dev
         if V is not None:
             return self._bordered_solve(jac, rhs, rhs2, V, W, C)
+        if isinstance(jac, ComplexDeviceMatrix):
+            return self._solve_complex(jac, rhs)
         return self._solve1(jac, rhs)
 
     def _solve1(self, jac, rhs):
@@ -618,6 +641,87 @@ class Interface:
         self._debug_print('%s: %d iterations, relres %.3e' % (self.last_solve['method'], info.iters, info.relres))
         return y
 
+    def _solve_complex(self, mat, rhs):
+        '''(A_r + i A_i) y = rhs with the pressure pinned like the real solve: right-preconditioned flexible GMRES in
+        complex arithmetic on the host, every operator product (four real device SpMVs) and every preconditioner
+        application (the block preconditioner of A_r on the real and imaginary parts) on the device.  The counterpart of
+        SuperLU on a complex matrix in the reference (SciPy.py:131-162,194-202).'''
+        self._sync_solver()
+        its = self.parameters.get('Iterative Solver', {})
+        tol = its.get('Convergence Tolerance', 1e-10)
+        maxit = int(its.get('Maximum Iterations', 1000))
+        restart = int(min(its.get('Restart', 100), 200))
+        b = numpy.array(rhs, dtype=numpy.complex128)
+        prow = self.pressure_row if self.dof > self.dim else -1
+        if prow >= 0:
+            b[prow] = 0
+        o = _lib.TfbSolveOpts()
+        o.pressure_row = prow
+        o.precond_flags = 0 if getattr(self, '_joint', False) else _lib.PREC_NO_JOINT
+        L = _lib.lib()
+
+        def op(z):
+            z = z.copy()
+            zp = z[prow] if prow >= 0 else 0.0
+            if prow >= 0:
+                z[prow] = 0                     # dropped column
+            y = mat @ z
+            if prow >= 0:
+                y[prow] = -zp                   # pinned row: -1 on the diagonal
+            return y
+
+        def prec(r):
+            out = numpy.empty(self.n_local, dtype=numpy.complex128)
+            for part in ('real', 'imag'):
+                src = numpy.ascontiguousarray(getattr(r, part))
+                dst = numpy.empty(self.n_local)
+                check(L.tfb_precond_apply_opts(mat.real._h, ptr(src), ptr(dst), ctypes.byref(o)))
+                setattr(out, part, dst)
+            return out
+
+        bnorm = numpy.linalg.norm(b)
+        y = numpy.zeros(self.n_local, dtype=numpy.complex128)
+        total, relres = 0, 1.0
+        if bnorm == 0.0:
+            relres = 0.0
+        while total < maxit and relres > tol:
+            r = b - op(y) if total else b.copy()
+            beta = numpy.linalg.norm(r)
+            relres = beta / bnorm
+            if relres <= tol:
+                break
+            m = min(restart, maxit - total)
+            V = numpy.zeros((m + 1, self.n_local), dtype=numpy.complex128)
+            Z = numpy.zeros((m, self.n_local), dtype=numpy.complex128)
+            H = numpy.zeros((m + 1, m), dtype=numpy.complex128)
+            V[0] = r / beta
+            k = 0
+            for j in range(m):
+                Z[j] = prec(V[j])
+                w = op(Z[j])
+                for _ in range(2):                      # classical Gram-Schmidt, two sweeps
+                    h = V[:j + 1].conj() @ w
+                    w = w - h @ V[:j + 1]
+                    H[:j + 1, j] += h
+                H[j + 1, j] = numpy.linalg.norm(w)
+                total += 1
+                k = j + 1
+                e1 = numpy.zeros(k + 1, dtype=numpy.complex128)
+                e1[0] = beta
+                coef, res, _, _ = numpy.linalg.lstsq(H[:k + 1, :k], e1, rcond=None)
+                est = numpy.linalg.norm(H[:k + 1, :k] @ coef - e1) / bnorm
+                if est <= tol or H[j + 1, j] == 0 or total >= maxit:
+                    break
+                V[j + 1] = w / H[j + 1, j]
+            y = y + coef @ Z[:k]
+            relres = numpy.linalg.norm(b - op(y)) / bnorm
+        self.last_solve = {'iterations': total, 'relres': float(relres), 'converged': bool(relres <= tol * 1.0001), 'setup_ms': 0.0,
+                           'solve_ms': 0.0, 'method': 'complex FGMRES', 'schur': 'LSC', 'precond_precision': 'double'}
+        if not self.last_solve['converged']:
+            import warnings
+            warnings.warn('B200 complex solve stopped at relative residual %.3e after %d iterations' % (relres, total), RuntimeWarning)
+        return y
+
     def _direct_solve(self, jac, b, prow):
         info = _lib.TfbSolveInfo()
         y = self._result_vector()
@@ -653,21 +757,23 @@ class Interface:
         -- the contract of BaseInterface.eigs / _eigs (BaseInterface.py:294-386).  The reference
         runs jadapy's JDQZ there; this backend runs a shift-and-invert Arnoldi process whose
         operator ``(J - sigma M)^-1 M`` is one device Krylov solve per step (transiflow_b200/eigs.py).
-        Real targets only.'''
+        Complex targets use the complex solve of ``_solve_complex``.'''
         from .eigs import shift_invert_arnoldi
         self._require_whole_grid('eigs')
         prm = self.parameters.get('Eigenvalue Solver', {})
         target = prm.get('Target', 0.0)
-        if numpy.iscomplexobj(target) and complex(target).imag != 0.0:
-            raise NotImplementedError('complex eigenvalue targets are not supported by the B200 backend')
-        target = float(numpy.real(target))
+        target = complex(target) if (numpy.iscomplexobj(target) and complex(target).imag != 0.0) else float(numpy.real(target))
         num = int(prm.get('Number of Eigenvalues', 5))
         tol = float(prm.get('Tolerance', 1e-7))
         max_dim = int(prm.get('Maximum Subspace Dimension', 60))
         recycle = prm.get('Recycle Subspaces', enable_recycling)
         jac = self.jacobian(state)
         mass = self.mass_matrix()
-        shifted = jac if target == 0.0 else jac - target * mass
+        if isinstance(target, complex):
+            # complex shift: J - sigma M as real and imaginary parts on the device (ComplexDeviceMatrix)
+            shifted = DeviceMatrix.from_scipy(self, jac.tocsc() - target * mass)
+        else:
+            shifted = jac if target == 0.0 else jac - target * mass
         failures = []
 
         def apply_op(v):
