@@ -18,7 +18,7 @@ COMMON = ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler',
 # (source, extra flags).  The assembly kernels must not contract a*b+c into FMA: bit-parity
 # with the reference's numpy arithmetic depends on it.
 UNITS = [
-    ('tfb_core.cu', ['-fmad=false']),
+    ('tfb_core.cu', ['-fmad=false'] + (['-DTFB_ASM_EXPERIMENTS'] if os.environ.get('TFB_ASM_EXPERIMENTS') else [])),
     ('tfb_solver.cu', []),
     ('tfb_comm.cu', []),
     ('tfb_direct.cu', []),

@@ -244,7 +244,29 @@ struct RingState {
     }
 };
 
-template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB>
+// Which (equation d1, line jl) the warp `w` of a marching CTA works on.  Warp w issues on scheduler w % 4, and with the
+// plain (jl * DOF + d1) order every short pressure row of a dof-4 CTA lands on scheduler 3.  item = jl * DOF + d1, one
+// nibble per warp.  Two lines, dof 4: schedulers get {u0,u1} {v0,v1} {w0,p0} {w1,p1} in even CTAs and the mirrored deal
+// in odd ones; dof 5 (one CTA per SM): {v0,T0,p0} {v1,T1,p1} {w0,u0} {w1,u1}.  One line, dof 5: {p,T} {u} {v} {w};
+// dof 4: one equation per scheduler, rotated with the CTA index.  Other shapes keep the plain order.
+template <int DOF, int TJ>
+__device__ __forceinline__ void tfb_deal_item(int w, int& d1, int& jl) {
+    if constexpr ((TJ == 2 || TJ == 1) && (DOF == 4 || DOF == 5)) {
+        const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        unsigned long long table;
+        if (TJ == 2) table = DOF == 4 ? (((lin ^ (lin / 148u)) & 1u) ? 0x54731062ull : 0x73546210ull) : 0x8350947261ull;
+        else table = DOF == 4 ? (0x3210321032103210ull >> (4 * (lin & 3u))) : 0x42103ull;
+        const int item = (int)((table >> (4 * w)) & 15ull);
+        jl = item / DOF;
+        d1 = item - jl * DOF;
+    }
+}
+
+// OPT bit 0: warps are dealt to (equation, line) items through a table that spreads the short pressure rows over the
+//            four warp schedulers (warp w issues on scheduler w % 4) instead of parking them all on one;
+// (Measured and dropped: a third instantiation with only the x-face boundary code (BCM = 1) for the warps on the x walls,
+// wall lanes compacted from a scratch row -- 0.238 -> 0.310 ms at 128^3: 40 % more code and spills under the 128-register cap.)
+template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB, int EXP = 0, int OPT = 0>
 __global__ void __launch_bounds__(32 * Cfg::DOF * TJ, MINB)
 tfb_assemble_march_kernel(const TfbAsmArgs a) {
     using M = TfbMarch<Cfg, TJ>;
@@ -260,8 +282,10 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     __shared__ int sm_pstart[KCH + 1];   // first CSR offset of every plane of the chunk
 
     const TfbGrid& g = a.g;
-    const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
+    const int il = threadIdx.x;
+    int d1 = threadIdx.y, jl = threadIdx.z;
     const int tid = (jl * DOF + d1) * 32 + il;
+    if constexpr (OPT & 1) tfb_deal_item<DOF, TJ>(tid >> 5, d1, jl);
     const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
     const int kbeg = a.kofs0 + (blockIdx.z + a.kc0) * a.kstep, kend = min(kbeg + a.kstep, a.klim);   // local planes
     const int kofs = 1 - a.k0;
@@ -349,7 +373,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
     // The choice between the BC-free and the boundary instantiation is made per WARP: a warp that
     // holds even one wall cell (lanes 0 / 30 / 31 of the x-edge warps) runs the boundary code for all
     // its lanes instead of running both instantiations under divergence.
-    const bool xy_interior = __all_sync(0xffffffffu, xy_interior_lane || !valid);
+    const bool xy_interior = (EXP & 1) ? true : __all_sync(0xffffffffu, xy_interior_lane || !valid);
     const int kfar2 = tfb_far2_index(g.nz);
     const int cell_off = (jl + 1) * W + (il + 1);
     int s0 = 0;   // ring slot of plane k-1
@@ -404,7 +428,9 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
             P.pl[1] = ring + s1 * SLOT + cell_off;
             P.pl[2] = ring + s2 * SLOT + cell_off;
             double f = 0.0;
-            if (xy_interior && !(c.near[2] | c.far[2] | c.far2[2])) {
+            if (EXP & 4) {
+                f = P.pl[1][d1 * DSTR];
+            } else if (xy_interior && ((EXP & 1) || !(c.near[2] | c.far[2] | c.far2[2]))) {
                 TfbSmemSink sink{out + (rp - galign) + padl};
                 Cfg::template row<DO_J, DO_F, 0>(d1, a.prm, c, P, sink, f);
             } else {
@@ -459,7 +485,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
             // one TMA bulk store per line (smem -> global), double-buffered staging
             const int head = gbase - galign, cnt = gend - galign;
             const int body0 = head ? 2 : 0, body1 = cnt & ~1;
-            if (body1 > body0) {
+            if (body1 > body0 && !(EXP & 2)) {
                 const unsigned src = (unsigned)__cvta_generic_to_shared(out + body0);
                 double* dstp = a.vals + galign + body0;
                 const unsigned bytes = (unsigned)(body1 - body0) * 8u;

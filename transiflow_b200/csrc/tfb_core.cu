@@ -313,7 +313,7 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
 
 #define TFB_KCH 16   // planes per z-chunk of the marching kernel (also the host pipeline granularity)
 
-template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB>
+template <class Cfg, bool DO_J, bool DO_F, int TJ, int KCH, int MINB, int EXP = 0, int OPT = 0>
 static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     TfbAsmArgs a;
     a.g = c->grid();
@@ -332,7 +332,7 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     a.kc0 = c->chunk0 >= 0 ? c->chunk0 : 0;
     const int nlaunch = c->chunk0 >= 0 ? std::min(c->chunkn, nchunks - a.kc0) : nchunks;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
-    auto kern = tfb_assemble_march_kernel<Cfg, DO_J, DO_F, TJ, KCH, MINB>;
+    auto kern = tfb_assemble_march_kernel<Cfg, DO_J, DO_F, TJ, KCH, MINB, EXP, OPT>;
     static unsigned configured_devices = 0;       // the attribute is per device
     if (!((configured_devices >> (c->desc.device & 31)) & 1u)) {
         TFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -366,6 +366,15 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
         case 21: return launch_march_v<Cfg, DO_J, DO_F, 4, 32, 1>(c, m);
         case 22: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 4>(c, m);
         case 23: return launch_march_v<Cfg, DO_J, DO_F, 1, 32, 4>(c, m);
+#ifdef TFB_ASM_EXPERIMENTS
+        case 41: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 1>(c, m);   // every warp on the BC-free path (timing only)
+        case 42: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 2>(c, m);   // no bulk stores
+        case 44: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 4>(c, m);   // no row arithmetic
+        case 43: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 3>(c, m);
+        case 51: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 0, 1>(c, m);
+        case 52: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 4, 0, 1>(c, m);
+        case 53: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 3, 0, 1>(c, m);
+#endif
         default: break;
         }
     }
@@ -379,10 +388,17 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
                 if (variant == 34) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3>(c, m);
                 if (variant == 35) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 4>(c, m);
                 if (variant == 36) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2>(c, m);
+                if (variant == 37) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 0, 1>(c, m);
+                if (variant == 38) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2, 0, 1>(c, m);
+                if (variant == 39) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3, 0, 1>(c, m);
             }
-            return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);   // dof 5: 160 registers, no spills
+            // dof 5: 168 registers, no spills, one CTA of ten warps per SM; the warp -> (equation, line) table evens the
+            // four schedulers out (0.477 -> 0.453 ms at 128^3)
+            return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 0, 1>(c, m);
         }
-        else return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 2>(c, m);
+        // dof 4: one line per CTA, four CTAs per SM, equations rotated over the schedulers with the CTA index
+        // (two lines x two CTAs: 0.238 ms, one line x four CTAs: 0.246 ms, with the rotation: 0.231 ms at 128^3)
+        else return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 4, 0, 1>(c, m);
     } else {
         return launch_assemble_v<Cfg, DO_J, DO_F, (Cfg::DOF >= 5 ? 3 : 4), 1>(c, m);
     }
