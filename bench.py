@@ -468,16 +468,21 @@ def main():
         if nwarm % 50 == 0:
             check(L.tfb_sync(it._ctx))
     barrier()
+    # one (start, stop) event pair per iteration, read after the loop: a host synchronisation inside the loop would put
+    # the launch jitter of the slowest rank into every z-slab iteration (each one meets its neighbours in the halo exchange)
     kern_ms = []
     t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        check(L.tfb_flush_l2(it._ctx))
-        check(L.tfb_event_record(it._ctx, 0))
-        check(L.tfb_assemble_resident(it._ctx, mat._h, 1, 1))
-        check(L.tfb_event_record(it._ctx, 1))
-        ms = ctypes.c_float()
-        check(L.tfb_event_elapsed_ms(it._ctx, 0, 1, ctypes.byref(ms)))
-        kern_ms.append(ms.value)
+    for s0 in range(0, args.steps, 512):
+        block = range(s0, min(s0 + 512, args.steps))
+        for s in block:
+            check(L.tfb_flush_l2(it._ctx))
+            check(L.tfb_event_record(it._ctx, 16 + 2 * (s - s0)))
+            check(L.tfb_assemble_resident(it._ctx, mat._h, 1, 1))
+            check(L.tfb_event_record(it._ctx, 17 + 2 * (s - s0)))
+        for s in block:
+            ms = ctypes.c_float()
+            check(L.tfb_event_elapsed_ms(it._ctx, 16 + 2 * (s - s0), 17 + 2 * (s - s0), ctypes.byref(ms)))
+            kern_ms.append(ms.value)
     barrier()
     launches = L.tfb_launch_count() - launches0
     step_ms = max_over_ranks(sum(kern_ms) / len(kern_ms))

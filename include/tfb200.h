@@ -102,7 +102,8 @@ int tfb_host_checksum(const double* p, int64_t n, uint64_t out[2]);
 int64_t tfb_upload_count(tfb_ctx* ctx);
 int tfb_sync(tfb_ctx* ctx);
 
-/* CUDA-event timers on the ctx's stream. slot in [0,16). */
+/* CUDA-event timers on the ctx's stream. slot in [0,1040): a timing loop can record a (start, stop) pair per iteration
+ * and read them all after the loop, so that no host synchronisation sits between the iterations. */
 int tfb_event_record(tfb_ctx* ctx, int slot);
 int tfb_event_elapsed_ms(tfb_ctx* ctx, int slot_a, int slot_b, float* ms);
 /* write `bytes` of device memory (> L2) to evict the L2 between timed iterations */

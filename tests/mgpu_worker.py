@@ -103,6 +103,20 @@ def main():
         ok &= solve_parity(it, jac, -f, want, r0, r1, rank, world, 'LDC', opts)
     del it, jac
 
+    # ---- taller slabs (>= 4 planes on every rank, ragged): every rank takes the path that exchanges the halo on a side
+    # stream next to the interior planes when TFB_OVERLAP is set; RHS-only and Jacobian-only launches as well ----
+    nzt = 5 * world + 1
+    for prm, (nxt, nyt), name in ((LDC, (34, 5), 'LDC'), (RB, (7, 6), 'Rayleigh-Benard')):
+        it, orc, r0, r1 = make(prm, nxt, nyt, nzt, rank, world, local)
+        ok &= assembly_parity(it, orc, r0, r1, rank, world, '%s %dx%dx%d' % (name, nxt, nyt, nzt))
+        state = numpy.random.default_rng(4).uniform(-0.5, 0.5, orc.n)
+        good = numpy.array_equal(it.rhs(state[r0:r1].copy()), orc.rhs(state)[r0:r1])
+        jonly = it.jacobian(state[r0:r1].copy())
+        both, _ = it.jacobian_rhs(state[r0:r1].copy())
+        good = good and numpy.array_equal(jonly.values(), both.values())
+        ok &= say(rank, world, '%s tall slabs: rhs() and jacobian() alone equal the fused launch / the oracle' % name, good)
+        del it, jonly, both
+
     # ---- Rayleigh-Benard: assembly, and the coupled (w, T) line solve on pencils (all z, a chunk of y) ----
     nx, ny = 9, 10
     it, orc, r0, r1 = make(RB, nx, ny, nz, rank, world, local)

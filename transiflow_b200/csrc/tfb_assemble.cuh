@@ -89,7 +89,8 @@ tfb_assemble_kernel(const TfbAsmArgs a) {
     const int il = threadIdx.x, d1 = threadIdx.y, jl = threadIdx.z;
     const int tid = (jl * DOF + d1) * 32 + il;
     const int i0 = blockIdx.x * TFB_TI, j0 = blockIdx.y * TJ;
-    const int kl = blockIdx.z;           // local plane
+    const int kl = a.kofs0 + blockIdx.z * a.kstep;   // local plane (whole slab: kofs0 = 0, kstep = 1; the two planes next
+                                                     // to the halo of a z-slab: kofs0 = 0, kstep = nzl - 1)
     const int k = a.k0 + kl;             // global plane
     const int kofs = 1 - a.k0;           // global k -> plane index of the slab storage
 

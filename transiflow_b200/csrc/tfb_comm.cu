@@ -1,6 +1,8 @@
 // NCCL plumbing for z-slab partitioned runs (one process per GPU).  libnccl is loaded with
 // dlopen so that single-GPU use has no NCCL dependency at all.
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "tfb_internal.h"
@@ -36,6 +38,31 @@ static int load_nccl() {
 #undef SYM
     return 0;
 }
+
+// TFB_TRACE=1: every NCCL operation is announced on stderr when it is enqueued (which stream, how much); TFB_TRACE=2
+// also waits for it.  For chasing ordering problems between ranks; off by default.
+static int trace_level() {
+    static int lvl = -1;
+    if (lvl < 0) { const char* e = getenv("TFB_TRACE"); lvl = e ? atoi(e) : 0; }
+    return lvl;
+}
+static long g_trace_seq = 0;
+#define TFB_TRACE_OP(ctx_, what, count, str_)                                                                  \
+    do {                                                                                                       \
+        if (trace_level() > 0) {                                                                               \
+            fprintf(stderr, "[tfb r%d] #%ld %s count %lld on %s\n", (ctx_)->rank, g_trace_seq++, what,          \
+                    (long long)(count), (str_) == (ctx_)->stream ? "main" : "side");                           \
+            fflush(stderr);                                                                                    \
+        }                                                                                                      \
+    } while (0)
+#define TFB_TRACE_DONE(ctx_, str_)                                                                             \
+    do {                                                                                                       \
+        if (trace_level() > 1) {                                                                               \
+            TFB_CUDA(cudaStreamSynchronize(str_));                                                             \
+            fprintf(stderr, "[tfb r%d] #%ld done\n", (ctx_)->rank, g_trace_seq - 1);                           \
+            fflush(stderr);                                                                                    \
+        }                                                                                                      \
+    } while (0)
 
 #define TFB_NCCL(call)                                                                     \
     do {                                                                                   \
@@ -90,6 +117,7 @@ int tfb_alltoallv_bytes(tfb_ctx* c, const void* send, const long long* scount, c
     const int dt = elem_bytes == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32;
     const char* sp = (const char*)send;
     char* rp = (char*)recv;
+    TFB_TRACE_OP(c, "alltoallv", scount[c->rank], c->stream);
     TFB_NCCL(nccl.GroupStart());
     for (int r = 0; r < c->nranks; r++) {
         if (r == c->rank) continue;
@@ -113,6 +141,19 @@ int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const
 // Rank r owns planes directly above rank r-1 (z-slab order = rank order).
 int tfb_halo_exchange(tfb_ctx* c, double* v) { return tfb_halo_exchange_on(c, v, c->stream); }
 
+// OPT-IN ONLY.  Measured on 2 x B200 at 128^3 per rank (round 2): the side stream buys nothing -- the exchange kernel finds
+// no free SM while the interior-plane kernel keeps refilling them and runs in its tail (assembly 0.249 ms with, 0.250 ms
+// without, 0.231 ms on one GPU) -- and bench.py hung intermittently with it (3 of 11 runs, with and without a
+// high-priority side stream, never with the trace of TFB_TRACE on), so the default exchanges the halo in front of the kernel.
+bool tfb_overlap_enabled(int which) {
+    static int mode = -1;     // bit 0: assembly, bit 1: operator products
+    if (mode < 0) {
+        const char* e = getenv("TFB_OVERLAP");
+        mode = !e ? 0 : !strcmp(e, "asm") ? 1 : !strcmp(e, "spmv") ? 2 : !strcmp(e, "0") ? 0 : 3;
+    }
+    return (mode >> which) & 1;
+}
+
 // side stream + events for exchanges that run next to the interior part of a kernel
 int tfb_comm_stream(tfb_ctx* c) {
     if (c->s_comm) return 0;
@@ -130,6 +171,7 @@ int tfb_halo_exchange_on(tfb_ctx* c, double* v, cudaStream_t stream) {
     double* last_owned = v + pl * c->nzl;
     double* ghost_lo = v;
     double* ghost_hi = v + pl * (c->nzl + 1);
+    TFB_TRACE_OP(c, "halo exchange", pl, stream);
     TFB_NCCL(nccl.GroupStart());
     if (c->rank > 0) {
         TFB_NCCL(nccl.Send(first_owned, pl, NCCL_FLOAT64, c->rank - 1, comm, stream));
@@ -141,14 +183,17 @@ int tfb_halo_exchange_on(tfb_ctx* c, double* v, cudaStream_t stream) {
     }
     TFB_NCCL(nccl.GroupEnd());
     TFB_LAUNCHED();
+    TFB_TRACE_DONE(c, stream);
     return 0;
 }
 
 int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count) {
     if (c->nranks <= 1) return 0;
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    TFB_TRACE_OP(c, "allreduce", count, c->stream);
     TFB_NCCL(nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, (ncclComm_t_)c->nccl_comm, c->stream));
     TFB_LAUNCHED();
+    TFB_TRACE_DONE(c, c->stream);
     return 0;
 }
 
@@ -159,8 +204,10 @@ int tfb_allgather_f32(tfb_ctx* c, const float* send, float* recv, size_t count) 
         return 0;
     }
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
+    TFB_TRACE_OP(c, "allgather", count, c->stream);
     TFB_NCCL(nccl.AllGather(send, recv, count, NCCL_FLOAT32, (ncclComm_t_)c->nccl_comm, c->stream));
     TFB_LAUNCHED();
+    TFB_TRACE_DONE(c, c->stream);
     return 0;
 }
 
@@ -170,6 +217,7 @@ int tfb_halo_up_f32(tfb_ctx* c, const float* first_plane, float* ghost_above, si
     if (c->nranks <= 1) return 0;
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
     ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    TFB_TRACE_OP(c, "halo up f32", count, c->stream);
     TFB_NCCL(nccl.GroupStart());
     if (c->rank > 0) TFB_NCCL(nccl.Send(first_plane, count, NCCL_FLOAT32, c->rank - 1, comm, c->stream));
     if (c->rank < c->nranks - 1) TFB_NCCL(nccl.Recv(ghost_above, count, NCCL_FLOAT32, c->rank + 1, comm, c->stream));
@@ -183,6 +231,7 @@ int tfb_halo_up_f64(tfb_ctx* c, const double* first_plane, double* ghost_above, 
     if (c->nranks <= 1) return 0;
     TFB_CHECK(c->nccl_comm, "tfb_comm_init has not been called");
     ncclComm_t_ comm = (ncclComm_t_)c->nccl_comm;
+    TFB_TRACE_OP(c, "halo up f64", count, c->stream);
     TFB_NCCL(nccl.GroupStart());
     if (c->rank > 0) TFB_NCCL(nccl.Send(first_plane, count, NCCL_FLOAT64, c->rank - 1, comm, c->stream));
     if (c->rank < c->nranks - 1) TFB_NCCL(nccl.Recv(ghost_above, count, NCCL_FLOAT64, c->rank + 1, comm, c->stream));

@@ -82,7 +82,7 @@ extern "C" int tfb_create(const tfb_desc* d, tfb_ctx** out) {
     TFB_CUDA(cudaMemset(c->d_state, 0, sizeof(double) * c->plane_rows * (c->nzl + 2)));
     TFB_CUDA(cudaMalloc(&c->d_rhs, sizeof(double) * c->n_local));
     TFB_CUDA(cudaMalloc(&c->d_frc_static, sizeof(double) * c->n_local));
-    for (int e = 0; e < 16; e++) TFB_CUDA(cudaEventCreate(&c->ev[e]));
+    for (int e = 0; e < 16; e++) TFB_CUDA(cudaEventCreate(&c->ev[e]));     // the others are created on first use
     memset(&c->prm, 0, sizeof c->prm);
     c->desc.met[0] = c->desc.met[1] = c->desc.met[2] = nullptr;
     c->desc.cor = nullptr;
@@ -107,7 +107,7 @@ extern "C" void tfb_destroy(tfb_ctx* c) {
     cudaFree(c->d_massdiag);
     for (double* p : c->vals_pool) cudaFree(p);
     tfb_solver_free(c->solver);
-    for (int e = 0; e < 16; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
+    for (int e = 0; e < TFB_EVENT_SLOTS; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
     for (auto e : c->ev_comm) if (e) cudaEventDestroy(e);
     if (c->s_comm) cudaStreamDestroy(c->s_comm);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -295,6 +295,8 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
     a.kc0 = 0;
     a.kstep = 1;
     a.kofs0 = 0; a.klim = c->nzl;
+    const bool ends_only = c->win1 == -2;     // the first and the last plane of the slab (the ones that read the halo)
+    if (ends_only) a.kstep = c->nzl - 1;
     constexpr int LINE_CAP = TFB_TI * TfbTile<Cfg>::cell_slots() + 2;
     size_t smem = sizeof(double) * (((TfbTile<Cfg>::template state_doubles<TJ>() + 1) & ~1) + (DO_J ? TJ * LINE_CAP : 0));
     auto kern = tfb_assemble_kernel<Cfg, DO_J, DO_F, TJ, MINB>;
@@ -304,7 +306,7 @@ static int launch_assemble_v(tfb_ctx* c, tfb_mat* m) {
         configured_devices |= 1u << (c->desc.device & 31);
     }
     dim3 block(32, Cfg::DOF, TJ);
-    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, c->nzl);
+    dim3 grid((c->desc.nx + TFB_TI - 1) / TFB_TI, (c->desc.ny + TJ - 1) / TJ, ends_only ? 2 : c->nzl);
     kern<<<grid, block, smem, c->stream>>>(a);
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
@@ -379,6 +381,9 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
         }
     }
     if constexpr (!Cfg::FLAT) {
+        // the two planes of a z-slab that read the halo, after the exchange that ran next to the interior planes: one launch
+        // of the plane-tile kernel (a marching CTA would fill its ring for a single plane)
+        if (c->win1 == -2) return launch_assemble_v<Cfg, DO_J, DO_F, 2, 2>(c, m);
         // true 3-D grids: z-marching kernel (ring of state planes, software prefetch)
         if constexpr (Cfg::DOF >= 5) {
             if constexpr (DO_J && DO_F) {
@@ -455,10 +460,9 @@ extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f)
     if (do_j) { m->version = tfb_next_version(); m->shift = 0.0; }
     if (c->nranks > 1) {
         const bool marching = c->desc.dim == 3 && c->desc.nz > 1;
-        if (marching && c->nzl >= 4 && getenv("TFB_OVERLAP")) {
+        if (marching && c->nzl >= 4 && tfb_overlap_enabled(0)) {
             // the interior planes do not read the halo: exchange it on a side stream while they are assembled, then the
-            // two planes next to it.  OPT-IN (TFB_OVERLAP=1): green in the 2-rank parity test, but the 128^3 bench on
-            // 2 GPUs hung with it (unresolved), so the default exchanges the halo in front of the kernel
+            // two planes next to it (one launch of the plane-tile kernel).  OPT-IN, see tfb_overlap_enabled (tfb_comm.cu)
             if (tfb_comm_stream(c)) return -1;
             TFB_CUDA(cudaEventRecord(c->ev_comm[0], c->stream));
             TFB_CUDA(cudaStreamWaitEvent(c->s_comm, c->ev_comm[0], 0));
@@ -467,9 +471,7 @@ extern "C" int tfb_assemble_resident(tfb_ctx* c, tfb_mat* m, int do_j, int do_f)
             c->win0 = 1; c->win1 = c->nzl - 1;
             int rc = dispatch_assemble(c, m, do_j, do_f);
             TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_comm[1], 0));
-            c->win0 = 0; c->win1 = 1;
-            if (!rc) rc = dispatch_assemble(c, m, do_j, do_f);
-            c->win0 = c->nzl - 1; c->win1 = c->nzl;
+            c->win0 = 0; c->win1 = -2;      // both end planes, one launch
             if (!rc) rc = dispatch_assemble(c, m, do_j, do_f);
             c->win0 = 0; c->win1 = -1;
             return rc;
@@ -592,13 +594,14 @@ extern "C" int tfb_mass_diag(tfb_ctx* c, double* diag_out) {
 
 // ------------------------------- timing helpers -------------------------------
 extern "C" int tfb_event_record(tfb_ctx* c, int slot) {
-    TFB_CHECK(c && slot >= 0 && slot < 16, "bad slot");
+    TFB_CHECK(c && slot >= 0 && slot < TFB_EVENT_SLOTS, "bad slot");
+    if (!c->ev[slot]) TFB_CUDA(cudaEventCreate(&c->ev[slot]));
     TFB_CUDA(cudaEventRecord(c->ev[slot], c->stream));
     return 0;
 }
 
 extern "C" int tfb_event_elapsed_ms(tfb_ctx* c, int a, int b, float* ms) {
-    TFB_CHECK(c && ms && a >= 0 && a < 16 && b >= 0 && b < 16, "bad slot");
+    TFB_CHECK(c && ms && a >= 0 && a < TFB_EVENT_SLOTS && b >= 0 && b < TFB_EVENT_SLOTS && c->ev[a] && c->ev[b], "bad slot");
     TFB_CUDA(cudaEventSynchronize(c->ev[b]));
     TFB_CUDA(cudaEventElapsedTime(ms, c->ev[a], c->ev[b]));
     return 0;

@@ -28,6 +28,7 @@ int tfb_fail(const char* file, int line, const char* what, const char* detail);
 #define TFB_MAX_CHUNKS 80
 struct tfb_solver_state;  // tfb_solver.cu
 
+#define TFB_EVENT_SLOTS 1040   // 16 general-purpose timers + 512 (start, stop) pairs for un-synchronised timing loops
 struct tfb_ctx {
     tfb_desc desc;
     int nzl;                    // owned planes
@@ -57,7 +58,7 @@ struct tfb_ctx {
     double* d_massdiag = nullptr;   // tfb_mass_diag result buffer
     void* d_flush = nullptr;
     size_t flush_bytes = 0;
-    cudaEvent_t ev[16] = {};
+    cudaEvent_t ev[TFB_EVENT_SLOTS] = {};
     // pipelined host path of tfb_jacobian: copy streams, per-chunk events, z-chunk window of a launch
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[TFB_MAX_CHUNKS] = {}, ev_k[TFB_MAX_CHUNKS] = {};
@@ -92,6 +93,9 @@ int tfb_spmv_structured(tfb_ctx* c, const tfb_mat* m, const double* x_global_bas
 int tfb_halo_exchange(tfb_ctx* ctx, double* d_vec_with_ghosts);
 int tfb_halo_exchange_on(tfb_ctx* ctx, double* d_vec_with_ghosts, cudaStream_t stream);
 int tfb_comm_stream(tfb_ctx* c);
+// TFB_OVERLAP: "1" = the halo exchange of the assembly (which = 0) and of the operator products (which = 1) runs on a side
+// stream next to the interior planes; "asm" / "spmv" select one of the two
+bool tfb_overlap_enabled(int which);
 int tfb_allreduce_sum(tfb_ctx* c, double* d_buf, int count);
 int tfb_alltoallv(tfb_ctx* c, const double* send, const long long* scount, const long long* sdispl,
                   double* recv, const long long* rcount, const long long* rdispl);

@@ -255,7 +255,7 @@ static int spmv(tfb_ctx* c, tfb_mat* m, const double* x, double* y, int prow, un
     // planes of x that exist: the slab plus one halo plane on either side, clipped to the domain
     const int kv0 = std::max(0, c->desc.k0 - 1), kv1 = std::min(c->desc.nz, c->desc.k1 + 1);
     const bool marching = use_structured && c->desc.dim == 3 && c->desc.nz > 1;
-    if (c->nranks > 1 && marching && c->nzl >= 4 && ghost_capable(c, x) && getenv("TFB_OVERLAP")) {
+    if (c->nranks > 1 && marching && c->nzl >= 4 && ghost_capable(c, x) && tfb_overlap_enabled(1)) {
         // z-slabs: the halo planes of x travel on a side stream while the interior planes are multiplied; the two planes
         // next to the halo follow when it has landed
         if (dist_setup(c) || tfb_comm_stream(c)) return -1;
