@@ -234,6 +234,30 @@ def test_direct_solve_on_2d_grids_matches_superlu(name):
     assert numpy.abs(yk - g['y']).max() <= 1e-8 * scale
 
 
+@pytest.mark.parametrize('problem,nx,ny', [('ldc', 64, 12), ('ldc', 55, 9), ('dhc', 52, 10), ('ldc', 40, 7)])
+def test_direct_solve_with_line_blocks_beyond_one_panel(problem, nx, ny):
+    """Line blocks that do not fit in shared memory whole are eliminated panel by panel (k_gj_blocked: NB columns on one
+    CTA, one rank-NB update of the other columns by all CTAs); the last panel may be ragged (55 * 3 = 165 rows).  Against
+    SuperLU on the pinned host matrix, as SciPy.py:204-258 solves it."""
+    import scipy.sparse.linalg
+    params = {'ldc': {'Reynolds Number': 200, 'Grid Stretching Factor': 1.5},
+              'dhc': {'Problem Type': 'Differentially Heated Cavity', 'Rayleigh Number': 1e4, 'Prandtl Number': 1000,
+                      'Reynolds Number': 1}}[problem]
+    it = _iface(params, nx, ny, 1)
+    x = numpy.random.default_rng(7).uniform(-0.2, 0.2, it.n)
+    jac = it.jacobian(x)
+    b = numpy.random.default_rng(8).uniform(-1, 1, it.n)
+    b[it.dim] = 0
+    y = it.solve(jac, b)
+    assert it.last_solve['method'] == 'Direct' and it.last_solve['converged'], it.last_solve
+    A = jac.tocsr().tolil()
+    A[it.dim, :] = 0
+    A[:, it.dim] = 0
+    A[it.dim, it.dim] = -1
+    want = scipy.sparse.linalg.spsolve(A.tocsc(), b)
+    assert numpy.abs(y - want).max() <= 1e-9 * numpy.abs(want).max()
+
+
 @pytest.mark.parametrize('grid', [(8, 8, 8), (24, 24, 1)])
 def test_mass_shifted_matrices_carry_the_shift_into_the_preconditioner(grid):
     """J - M / (theta dt) with a small time step (and J - sigma M with a large shift) are dominated by the mass term; the

@@ -107,6 +107,7 @@ extern "C" void tfb_destroy(tfb_ctx* c) {
     cudaFree(c->d_massdiag);
     for (double* p : c->vals_pool) cudaFree(p);
     tfb_solver_free(c->solver);
+    tfb_direct_pool_free(c);
     for (int e = 0; e < TFB_EVENT_SLOTS; e++) if (c->ev[e]) cudaEventDestroy(c->ev[e]);
     for (auto e : c->ev_comm) if (e) cudaEventDestroy(e);
     if (c->s_comm) cudaStreamDestroy(c->s_comm);

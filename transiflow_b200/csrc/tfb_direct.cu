@@ -26,20 +26,43 @@ struct tfb_direct_factor {
     double* rowbuf = nullptr;   // m
     int* piv = nullptr;         // m
     int* colsrc = nullptr;      // m
+    int* swp = nullptr;         // 160: rows touched by the swaps of a panel (k_gj_blocked)
     unsigned* bar = nullptr;    // grid barrier counter + status word
     double* y = nullptr;        // n work vectors
     double* z = nullptr;
     double* rr = nullptr;
+    double* vb = nullptr;       // n: right-hand side, solution and correction of a solve
+    double* vx = nullptr;
+    double* vdx = nullptr;
     float factor_ms = 0.f;
 };
 
+static void direct_release(tfb_direct_factor* f) {
+    cudaFree(f->Sinv); cudaFree(f->S); cudaFree(f->W); cudaFree(f->colbuf); cudaFree(f->rowbuf); cudaFree(f->piv);
+    cudaFree(f->colsrc); cudaFree(f->swp); cudaFree(f->bar); cudaFree(f->y); cudaFree(f->z); cudaFree(f->rr);
+    cudaFree(f->vb); cudaFree(f->vx); cudaFree(f->vdx);
+    delete f;
+}
+
+// A Newton loop factors one Jacobian per step: the work space (the ny line inverses above all) is parked on the context
+// when its matrix goes away and taken over by the next one instead of being freed and allocated again.
 void tfb_direct_free(tfb_mat* mat) {
     tfb_direct_factor* f = (tfb_direct_factor*)mat->direct;
     if (!f) return;
-    cudaFree(f->Sinv); cudaFree(f->S); cudaFree(f->W); cudaFree(f->colbuf); cudaFree(f->rowbuf); cudaFree(f->piv);
-    cudaFree(f->colsrc); cudaFree(f->bar); cudaFree(f->y); cudaFree(f->z); cudaFree(f->rr);
-    delete f;
     mat->direct = nullptr;
+    tfb_ctx* c = mat->ctx;
+    if (c && !c->direct_pool) {
+        cudaStreamSynchronize(c->stream);     // nothing of this matrix is in flight any more
+        f->version = ~0ull;
+        c->direct_pool = f;
+        return;
+    }
+    direct_release(f);
+}
+
+void tfb_direct_pool_free(tfb_ctx* c) {
+    if (c->direct_pool) direct_release((tfb_direct_factor*)c->direct_pool);
+    c->direct_pool = nullptr;
 }
 
 // ---- blocks of line j out of the CSR matrix (pinned: row prow is -1 on the diagonal, column prow dropped) ----
@@ -92,7 +115,8 @@ __global__ void k_dense_times_sparse_sub(int m, int line, const int* __restrict_
     }
 }
 
-// ---- in-place Gauss-Jordan inversion with partial pivoting, persistent multi-CTA kernel ----
+// ---- in-place Gauss-Jordan inversion with partial pivoting, one column at a time, persistent multi-CTA kernel ----
+// (the fallback for blocks too large for the blocked kernel below, and TFB_DIRECT_UNBLOCKED=1)
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& epoch) {
     __syncthreads();
     if (nblocks == 1) return;
@@ -186,81 +210,214 @@ __global__ void __launch_bounds__(NT) k_gauss_jordan(int m, double* __restrict__
     (void)mm;
 }
 
-// the same elimination for a block that fits in shared memory (m <= 160): one CTA, no global round trips per column
-__global__ void __launch_bounds__(1024) k_gauss_jordan_smem(int m, const double* __restrict__ Ain, int* __restrict__ piv_g, unsigned* __restrict__ bar,
-                                                            double* __restrict__ out, double tiny) {
+// ---- blocked in-place Gauss-Jordan inversion (default) ----
+// The column-at-a-time kernel above pays two grid barriers per column: 2 m barriers per line block, 330 000 for the AMOC
+// configuration (m = 1280, 128 lines), which is where its 2.1 s went.  Here NB columns at a time form a PANEL that CTA 0
+// eliminates on its own in shared memory (all m rows of those columns; pivot search among the rows not used yet, barriers
+// are __syncthreads), and the rest of the matrix receives one rank-NB update per panel from all CTAs:
+//     A_J  <-  [rows outside the panel's pivot rows] A_J  +  P_new * A_K,J     (after the panel's row swaps; J: all other columns)
+// with P_new the eliminated panel (A_KK^-1 in the pivot rows, -A_OK A_KK^-1 elsewhere) -- two grid barriers per PANEL.
+// A block that fits in shared memory whole (m <= ~150: the 32 x 32 cavity) is a single panel and a single CTA.
+// tools/proto/blocked_gauss_jordan.py is the numpy model of the algebra.
+//   swp: [0] = number of touched rows nt, [1..64] = touched rows T (the pivot rows first), [65..128] = sigma: after the
+//   swaps row T[a] holds what row T[sigma[a]] held before.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_gj_blocked(int m, int NB, double* __restrict__ A, int* __restrict__ piv, int* __restrict__ swp,
+                                                   int* __restrict__ colsrc, unsigned* __restrict__ bar, double* __restrict__ out, double tiny) {
     extern __shared__ double sm[];
-    double* A = sm;                       // m x (m + 1): padded rows, column accesses are conflict-free
-    const int ld = m + 1;
-    double* colbuf = A + (size_t)m * ld;
-    double* rowbuf = colbuf + m;
-    int* piv = reinterpret_cast<int*>(rowbuf + m);
-    int* colsrc = piv + m;
-    __shared__ double s_val[32];
-    __shared__ int s_row[32];
-    __shared__ int s_p;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < m * m; e += nt) A[(e / m) * ld + (e % m)] = Ain[e];
-    __syncthreads();
-    for (int k = 0; k < m; k++) {
-        double best = -1.0;
-        int brow = k;
-        for (int i = k + tid; i < m; i += nt) {
-            const double v = fabs(A[i * ld + k]);
-            if (v > best) { best = v; brow = i; }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const double v = __shfl_xor_sync(0xffffffffu, best, o);
-            const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
-            if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
-        }
-        if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_row[tid >> 5] = brow; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < (nt >> 5); w++)
-                if (s_val[w] > s_val[0] || (s_val[w] == s_val[0] && s_row[w] < s_row[0])) { s_val[0] = s_val[w]; s_row[0] = s_row[w]; }
-            s_p = s_row[0];
-            piv[k] = s_row[0];
-            if (!(s_val[0] > tiny)) bar[1] = 1u;
-        }
-        __syncthreads();
-        const int p = s_p;
-        for (int j = tid; j < m; j += nt) {
-            const double ap = A[p * ld + j];
-            rowbuf[j] = ap;
-            double cv = A[j * ld + k];
-            if (j == k) cv = A[p * ld + k];
-            else if (j == p) cv = A[k * ld + k];
-            colbuf[j] = cv;
-        }
-        __syncthreads();
-        if (p != k)
-            for (int j = tid; j < m; j += nt)
-                if (j != k) A[p * ld + j] = A[k * ld + j];
-        __syncthreads();
-        const double pivinv = 1.0 / colbuf[k];
-        for (int i = tid >> 5; i < m; i += (nt >> 5)) {        // one warp per row, lanes along the row
-            double* arow = A + i * ld;
-            if (i == k) {
-                for (int j = tid & 31; j < m; j += 32) arow[j] = j == k ? pivinv : rowbuf[j] * pivinv;
-            } else {
-                const double f = colbuf[i] * pivinv;
-                for (int j = tid & 31; j < m; j += 32) arow[j] = j == k ? -f : arow[j] - f * rowbuf[j];
+    const int ld = NB | 1;                       // odd row pitch: column accesses are conflict-free
+    double* P = sm;                              // m x ld panel (CTA 0); afterwards tmp / AK of the update
+    const size_t psz = (size_t)m * ld + 2048;    // + tmp [64][32] of the update (which keeps the panel behind it)
+    double* colbuf = sm + psz;                   // m
+    double* rowbuf = colbuf + m;                 // NB
+    double* rowold = rowbuf + NB;                // NB
+    int* posof = reinterpret_cast<int*>(rowold + NB);   // m: index of a row in T, -1 if untouched
+    int* spiv = posof + m;                       // NB
+    __shared__ double s_val[NT / 32];
+    __shared__ int s_row[NT / 32];
+    __shared__ int s_T[64], s_sig[64], s_nt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    unsigned epoch = 0;
+    const unsigned nblk = gridDim.x;
+    for (int k0 = 0; k0 < m; k0 += NB) {
+        const int nb = min(NB, m - k0);
+        const bool whole = nb == m;              // no other columns: nothing to update
+        if (blockIdx.x == 0) {
+            // ---- panel into shared memory ----
+            // thread <-> (column, row group): JW lanes along a row (the power of two that covers nb, at most 32), rows
+            // strided by NT / JW; no index divisions, eight independent loads in flight per thread
+            const int JW = nb <= 8 ? 8 : nb <= 16 ? 16 : 32;
+            const int jl = tid & (JW - 1), rg = tid / JW, nrg = NT / JW;
+            for (int j = jl; j < nb; j += JW)
+                for (int i0 = rg; i0 < m; i0 += 8 * nrg) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; v[u] = i < m ? A[(size_t)i * m + k0 + j] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; if (i < m) P[i * ld + j] = v[u]; }
+                }
+            if (!whole) for (int i = tid; i < m; i += NT) posof[i] = (i >= k0 && i < k0 + nb) ? i - k0 : -1;
+            __syncthreads();
+            for (int s = 0; s < nb; s++) {
+                const int k = k0 + s;
+                // pivot of column s among the rows k..m-1 (smallest row on ties)
+                double best = -1.0;
+                int brow = k;
+                for (int i = k + tid; i < m; i += NT) {
+                    const double v = fabs(P[i * ld + s]);
+                    if (v > best) { best = v; brow = i; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double v = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
+                    if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
+                }
+                if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
+                __syncthreads();
+                // every warp reduces the NW warp results again with shuffles (no second barrier, no serial loop)
+                best = lane < NW ? s_val[lane] : -1.0;
+                brow = lane < NW ? s_row[lane] : m;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double v = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
+                    if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
+                }
+                const int p = brow;
+                if (tid == 0) {
+                    piv[k] = p;
+                    spiv[s] = p;
+                    if (!(best > tiny)) bar[1] = 1u;     // numerically singular block
+                }
+                // The row that becomes the pivot row (rowbuf), the row it displaces (rowold), and the multiplier of every
+                // row: column s as it stands after the swap, times 1 / pivot.  The pivot row itself carries -1 / pivot and
+                // starts from zero, so that one formula,  new = base - f * rowbuf  (and -f in column s), serves all rows.
+                const double pivinv = 1.0 / P[p * ld + s];
+                for (int j = tid; j < nb; j += NT) { rowbuf[j] = P[p * ld + j]; rowold[j] = P[k * ld + j]; }
+                for (int i = tid; i < m; i += NT) {
+                    double cv = P[i * ld + s];
+                    if (i == p) cv = P[k * ld + s];
+                    colbuf[i] = i == k ? -pivinv : cv * pivinv;
+                }
+                __syncthreads();
+                const bool swapped = p != k;
+                for (int j = jl; j < nb; j += JW) {
+                    const double rb = rowbuf[j], ro = rowold[j];
+                    const bool js = j == s;
+                    double* col = P + j;
+                    // every row by the same formula (the values it leaves in rows k and p are wrong) ...
+#pragma unroll 4
+                    for (int i = rg; i < m; i += nrg) {
+                        const double f = colbuf[i];
+                        const double v = col[i * ld] - f * rb;
+                        col[i * ld] = js ? -f : v;
+                    }
+                    // ... then the owner of rows k and p in this column (the thread that just wrote them) sets them right:
+                    // the pivot row starts from zero, the row that received the displaced row k from that row
+                    if (rg == k % nrg) { const double f = colbuf[k]; col[k * ld] = js ? -f : 0.0 - f * rb; }
+                    if (swapped && rg == p % nrg) { const double f = colbuf[p]; col[p * ld] = js ? -f : ro - f * rb; }
+                }
+                __syncthreads();
+            }
+            // ---- panel back to the matrix; which rows the swaps touched and where their contents went ----
+            for (int j = jl; j < nb; j += JW)
+                for (int i = rg; i < m; i += nrg) A[(size_t)i * m + k0 + j] = P[i * ld + j];
+            if (!whole && tid == 0) {
+                int nt = nb;
+                for (int a = 0; a < nb; a++) { s_T[a] = k0 + a; s_sig[a] = a; }
+                for (int s2 = 0; s2 < nb; s2++) {
+                    const int p = spiv[s2];
+                    int b = posof[p];
+                    if (b < 0) { b = nt; posof[p] = nt; s_T[nt] = p; s_sig[nt] = nt; nt++; }
+                    const int t = s_sig[s2]; s_sig[s2] = s_sig[b]; s_sig[b] = t;
+                }
+                swp[0] = nt;
+                for (int a = 0; a < nt; a++) { swp[1 + a] = s_T[a]; swp[65 + a] = s_sig[a]; }
             }
         }
-        __syncthreads();
+        if (whole) break;
+        grid_barrier(bar, nblk, epoch);
+        // ---- all CTAs: the other columns.  A CTA owns a contiguous range of W columns for the whole elimination (no hazards
+        // between CTAs), keeps the eliminated panel in shared memory and streams its columns with eight rows in flight.
+        if (tid == 0) s_nt = swp[0];
+        if (tid < 64) { s_T[tid] = swp[1 + tid]; s_sig[tid] = swp[65 + tid]; }
+        const int W = (m + (int)gridDim.x - 1) / (int)gridDim.x;          // columns per CTA
+        const int WP = W <= 8 ? 8 : W <= 16 ? 16 : 32;                      // lanes per row (power of two)
+        const int c0 = blockIdx.x * W, c1 = min(m, c0 + W);
+        if (c0 < c1) {
+            // P_new: the panel columns of every row (the K rows hold A_KK^-1), pitch ld as in CTA 0
+            double* Ps = P + 2048;           // behind tmp [64][32]
+            const int nb8 = (nb + 7) & ~7;   // columns nb..nb8 are zero: the update below runs in blocks of eight
+            {
+                const int JW = nb8 <= 8 ? 8 : nb8 <= 16 ? 16 : 32;
+                const int jl = tid & (JW - 1), rg = tid / JW, nrg = NT / JW;
+                if (jl < nb8)
+                    for (int i0 = rg; i0 < m; i0 += 8 * nrg) {
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; v[u] = (i < m && jl < nb) ? A[(size_t)i * m + k0 + jl] : 0.0; }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; if (i < m) Ps[i * ld + jl] = v[u]; }
+                    }
+            }
+            __syncthreads();
+            const int nt = s_nt;
+            double* tmp = sm;              // [64][WP]: rows touched by the swaps, already permuted
+            for (int cb = c0; cb < c1; cb += 32) {                         // (W > 32 only on small grids with few CTAs)
+                const int jc = tid & (WP - 1), rg = tid / WP, nrg = NT / WP;
+                const int j = cb + jc;
+                const bool jok = jc < W && j < c1 && !(j >= k0 && j < k0 + nb);
+                for (int a = rg; a < nt; a += nrg) tmp[a * WP + jc] = jok ? A[(size_t)s_T[s_sig[a]] * m + j] : 0.0;
+                __syncthreads();
+                // swapped rows outside the panel's pivot rows go back first (they are ordinary rows of the update below)
+                for (int a = nb + rg; a < nt; a += nrg) if (jok) A[(size_t)s_T[a] * m + j] = tmp[a * WP + jc];
+                __syncthreads();
+                if (jok) {
+                    double ak[32];
+#pragma unroll
+                    for (int s2 = 0; s2 < 32; s2++) ak[s2] = s2 < nb ? tmp[s2 * WP + jc] : 0.0;    // A_K,j after the swaps
+                    for (int i0 = rg; i0 < m; i0 += 8 * nrg) {
+                        double acc[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int i = i0 + u * nrg;
+                            acc[u] = (i < m && !(i >= k0 && i < k0 + nb)) ? A[(size_t)i * m + j] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int i = i0 + u * nrg;
+                            if (i < m) {
+                                const double* pr = Ps + (size_t)i * ld;
+                                double a2 = acc[u];
+#pragma unroll
+                                for (int blk = 0; blk < 4; blk++)
+                                    if (nb > 8 * blk) {
+#pragma unroll
+                                        for (int t2 = 0; t2 < 8; t2++) a2 += pr[8 * blk + t2] * ak[8 * blk + t2];
+                                    }
+                                A[(size_t)i * m + j] = a2;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        grid_barrier(bar, nblk, epoch);
     }
-    if (tid == 0) {
+    // inverse of the row-permuted matrix -> inverse: undo the swaps on the columns, composed into one gather
+    grid_barrier(bar, nblk, epoch);
+    if (blockIdx.x == 0 && tid == 0) {
         for (int c = 0; c < m; c++) colsrc[c] = c;
         for (int k = m - 1; k >= 0; k--) {
             const int p = piv[k];
             if (p != k) { const int t = colsrc[k]; colsrc[k] = colsrc[p]; colsrc[p] = t; }
         }
     }
-    __syncthreads();
-    for (int i = tid >> 5; i < m; i += (nt >> 5))
-        for (int j = tid & 31; j < m; j += 32) out[i * m + j] = A[i * ld + colsrc[j]];
-    (void)piv_g;
+    grid_barrier(bar, nblk, epoch);
+    for (int i = blockIdx.x; i < m; i += gridDim.x)
+        for (int j = tid; j < m; j += NT) out[(size_t)i * m + j] = A[(size_t)i * m + colsrc[j]];
 }
 
 // ---- substitution ----
@@ -319,6 +476,12 @@ static int direct_factor(tfb_mat* mat, int prow) {
     const int m = dof * nx, nl = ny * c->desc.nz;
     tfb_direct_factor* f = (tfb_direct_factor*)mat->direct;
     if (f && f->version == mat->version && f->prow == prow) return 0;
+    if (!f && c->direct_pool) {
+        tfb_direct_factor* parked = (tfb_direct_factor*)c->direct_pool;
+        c->direct_pool = nullptr;
+        if (parked->m == m && parked->nl == nl) { f = parked; mat->direct = f; }
+        else direct_release(parked);
+    }
     if (!f) {
         f = new tfb_direct_factor();
         mat->direct = f;
@@ -334,7 +497,11 @@ static int direct_factor(tfb_mat* mat, int prow) {
         TFB_CUDA(cudaMalloc(&f->rowbuf, sizeof(double) * m));
         TFB_CUDA(cudaMalloc(&f->piv, sizeof(int) * m));
         TFB_CUDA(cudaMalloc(&f->colsrc, sizeof(int) * m));
+        TFB_CUDA(cudaMalloc(&f->swp, sizeof(int) * 160));
         TFB_CUDA(cudaMalloc(&f->bar, sizeof(unsigned) * 2));
+        TFB_CUDA(cudaMalloc(&f->vb, sizeof(double) * c->n_local));
+        TFB_CUDA(cudaMalloc(&f->vx, sizeof(double) * c->n_local));
+        TFB_CUDA(cudaMalloc(&f->vdx, sizeof(double) * c->n_local));
         TFB_CUDA(cudaMalloc(&f->y, sizeof(double) * c->n_local));
         TFB_CUDA(cudaMalloc(&f->z, sizeof(double) * c->n_local));
         TFB_CUDA(cudaMalloc(&f->rr, sizeof(double) * (c->n_local + 2)));
@@ -343,19 +510,33 @@ static int direct_factor(tfb_mat* mat, int prow) {
     TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
     TFB_CUDA(cudaEventRecord(e0, c->stream));
     const size_t mm = (size_t)m * m;
-    // the persistent elimination kernel needs all its CTAs resident at once
+    // the persistent elimination kernels need all their CTAs resident at once
     int per_sm = 0, sms = 0;
-    TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gauss_jordan<256>, 256, 0));
     TFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->desc.device));
-    // tiny blocks: one CTA (barriers are __syncthreads); otherwise ~8 elements per thread, at most two CTAs per SM
-    static int single_max = -1;        // largest line block handled by ONE 1024-thread CTA (barriers are __syncthreads)
-    if (single_max < 0) { const char* e = getenv("TFB_DIRECT_SINGLE_MAX"); single_max = e ? atoi(e) : 128; }
-    const bool single = m <= single_max;
-    const size_t gj_smem = sizeof(double) * ((size_t)m * (m + 1) + 2 * (size_t)m) + sizeof(int) * 2 * (size_t)m;
-    const bool in_smem = gj_smem <= 200 * 1024;
-    if (in_smem) TFB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_smem));
-    const int gj_grid = single ? 1
-                               : (int)std::max<long long>(1, std::min<long long>((long long)sms * std::min(per_sm, 2), ((long long)mm + 256 * 8 - 1) / (256 * 8)));
+    // blocked elimination (k_gj_blocked): the panel width is what fits in shared memory next to the column buffers; a block
+    // that fits whole is one panel on one CTA.  TFB_DIRECT_UNBLOCKED=1 keeps the column-at-a-time kernel.
+    constexpr int GJ_NT = 512;
+    auto gj_bytes = [&](int nb) {
+        const size_t pan = (size_t)m * (nb | 1) + 2048;
+        return sizeof(double) * (pan + (size_t)m + 2 * (size_t)nb) + sizeof(int) * ((size_t)m + nb + 16);
+    };
+    const size_t smem_cap = 224 * 1024;
+    int NB = 0;
+    static int unblocked = -1;
+    if (unblocked < 0) { const char* e = getenv("TFB_DIRECT_UNBLOCKED"); unblocked = (e && e[0] == '1') ? 1 : 0; }
+    if (!unblocked) {
+        if (gj_bytes(m) <= smem_cap) NB = m;
+        else for (int nb = 32; nb >= 8; nb -= 8) if (gj_bytes(nb) <= smem_cap) { NB = nb; break; }
+    }
+    int gjb_grid = 1;
+    if (NB > 0) {
+        TFB_CUDA(cudaFuncSetAttribute(k_gj_blocked<GJ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_bytes(NB)));
+        TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gj_blocked<GJ_NT>, GJ_NT, gj_bytes(NB)));
+        TFB_CHECK(per_sm >= 1, "the elimination kernel does not fit on an SM");
+        gjb_grid = NB >= m ? 1 : (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (m + 7) / 8));
+    }
+    TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gauss_jordan<256>, 256, 0));
+    const int gj_grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * std::min(per_sm, 2), ((long long)mm + 256 * 8 - 1) / (256 * 8)));
     double amax = 0.0;   // scale for the singularity test: largest |value| of the matrix
     {
         std::vector<double> probe(std::min<size_t>((size_t)c->nnz, 4096));
@@ -376,8 +557,7 @@ static int direct_factor(tfb_mat* mat, int prow) {
             TFB_LAUNCHED(); TFB_LAUNCHED();
         }
         TFB_CUDA(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * 2, c->stream));
-        if (in_smem) k_gauss_jordan_smem<<<1, 1024, gj_smem, c->stream>>>(m, f->S, f->piv, f->bar, f->Sinv + (size_t)j * mm, tiny);
-        else if (single) k_gauss_jordan<1024><<<1, 1024, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        if (NB > 0) k_gj_blocked<GJ_NT><<<gjb_grid, GJ_NT, gj_bytes(NB), c->stream>>>(m, NB, f->S, f->piv, f->swp, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
         else k_gauss_jordan<256><<<gj_grid, 256, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
         TFB_LAUNCHED();
         TFB_CUDA(cudaGetLastError());
@@ -440,10 +620,7 @@ extern "C" int tfb_direct_solve(tfb_mat* mat, const double* b, double* x, int pr
     cudaEvent_t e0, e1;
     TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
     TFB_CUDA(cudaEventRecord(e0, c->stream));
-    double *d_b = nullptr, *d_x = nullptr, *d_dx = nullptr;
-    TFB_CUDA(cudaMalloc(&d_b, sizeof(double) * n));
-    TFB_CUDA(cudaMalloc(&d_x, sizeof(double) * n));
-    TFB_CUDA(cudaMalloc(&d_dx, sizeof(double) * n));
+    double *d_b = f->vb, *d_x = f->vx, *d_dx = f->vdx;
     TFB_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     if (direct_substitute(mat, prow, d_b, d_x)) return -1;
     const unsigned nb = (unsigned)((n + 255) / 256);
@@ -467,7 +644,6 @@ extern "C" int tfb_direct_solve(tfb_mat* mat, const double* b, double* x, int pr
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_b); cudaFree(d_x); cudaFree(d_dx);
     const double relres = norms[1] > 0.0 ? sqrt(norms[0] / norms[1]) : sqrt(norms[0]);
     if (info) {
         info->iters = 1; info->relres = relres; info->converged = relres <= 1e-10;

@@ -65,6 +65,7 @@ struct tfb_ctx {
     int chunk0 = -1, chunkn = 0, chunk_planes = 0;
     int win0 = 0, win1 = -1;    // plane window [win0, win1) of the next assembly launch (win1 < 0: the whole slab)
     // z-slabs: the halo exchange runs on its own stream next to the interior planes of the kernel that needs it
+    void* direct_pool = nullptr;   // parked work space of the 2-D direct solve (tfb_direct.cu)
     cudaStream_t s_comm = nullptr;
     cudaEvent_t ev_comm[2] = {nullptr, nullptr};
     tfb_solver_state* solver = nullptr;   // FDM operators, Krylov work space (tfb_solver.cu)
@@ -104,3 +105,4 @@ int tfb_halo_up_f64(tfb_ctx* c, const double* first_plane, double* ghost_above, 
 int tfb_allgather_f32(tfb_ctx* c, const float* send, float* recv, size_t count);
 void tfb_solver_free(tfb_solver_state* s);
 void tfb_direct_free(tfb_mat* mat);
+void tfb_direct_pool_free(tfb_ctx* c);
