@@ -513,14 +513,42 @@ static int dispatch_assemble_impl(tfb_ctx* c, tfb_mat* m, int do_j, int do_f) {
 }
 static int dispatch_assemble(tfb_ctx* c, tfb_mat* m, int do_j, int do_f) { return dispatch_assemble_impl(c, m, do_j, do_f); }
 
+// Pieces of the pipelined host path, as plane boundaries b[0] = 0 < b[1] < ... = nzl.  Every piece costs a fixed ~40 us
+// (copy set-up on both engines, event hand-overs), the first upload and the last download are not overlapped with
+// anything, so the pieces are small at both ends and large in the middle: 4, 12, 16, 32, ..., 32, 16, 12, 4 planes
+// (measured at 128^3, uniform pieces: 2 planes 2.40 ms, 4: 2.21, 8: 1.95, 16: 1.83, 32: 1.83, 64: 2.08 per call).
+// TFB_PIPE_PLANES=n forces uniform pieces of n planes.
+static std::vector<int> tfb_pipe_pieces(int nzl) {
+    static int uniform = -1;
+    if (uniform < 0) { const char* e = getenv("TFB_PIPE_PLANES"); uniform = e ? std::max(1, atoi(e)) : 0; }
+    std::vector<int> b{0};
+    if (uniform > 0 || nzl < 64) {
+        const int step = uniform > 0 ? uniform : 8;
+        for (int k = step; k < nzl; k += step) b.push_back(k);
+        b.push_back(nzl);
+        return b;
+    }
+    const int ramp[3] = {4, 12, 16};
+    std::vector<int> tail;
+    int lo = 0, hi = nzl;
+    for (int r = 0; r < 3 && hi - lo >= 2 * ramp[r]; r++) {
+        lo += ramp[r]; b.push_back(lo);
+        hi -= ramp[r]; tail.push_back(hi);
+    }
+    while (hi - lo > 32) { lo += 32; b.push_back(lo); }
+    if (hi > lo) b.push_back(hi);
+    for (int t = (int)tail.size() - 2; t >= 0; t--) b.push_back(tail[t]);
+    b.push_back(nzl);
+    b.erase(std::unique(b.begin(), b.end()), b.end());
+    return b;
+}
+
 // Host-buffer path for 3-D grids on one GPU: the upload of the state, the assembly and the download
-// of F(x) are pipelined over z-chunks on three streams (PCIe is full duplex), so the call costs
+// of F(x) are pipelined over z-pieces on three streams (PCIe is full duplex), so the call costs
 // about max(H2D, D2H) instead of H2D + kernel + D2H.
 static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, double* rhs_out) {
-    // pipeline granularity: half a marching chunk.  Finer pieces shorten the fill (first kernel waits for one
-    // piece) and the drain (last download) of the pipeline; the kernel time is hidden behind PCIe either way.
-    const int PCH = TFB_KCH / 2;
-    const int nch = (c->nzl + PCH - 1) / PCH;
+    const std::vector<int> b = tfb_pipe_pieces(c->nzl);
+    const int nch = (int)b.size() - 1;
     if (!c->s_h2d) {
         TFB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         TFB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
@@ -533,10 +561,10 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
     TFB_CUDA(cudaEventRecord(c->ev_k[TFB_MAX_CHUNKS - 1], c->stream));
     TFB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[TFB_MAX_CHUNKS - 1], 0));
     const size_t pr = (size_t)c->plane_rows;
-    // upload pieces are shifted by one plane: piece ch ends with the first plane of chunk ch+1, which is the
-    // only plane of the next chunk the kernel of chunk ch reads
+    // upload pieces are shifted by one plane: piece ch ends with the first plane of piece ch+1, which is the
+    // only plane of the next piece the kernel of piece ch reads
     for (int ch = 0; ch < nch; ch++) {
-        const int u0 = ch == 0 ? 0 : ch * PCH + 1, u1 = std::min((ch + 1) * PCH + 1, c->nzl);
+        const int u0 = ch == 0 ? 0 : b[ch] + 1, u1 = std::min(b[ch + 1] + 1, c->nzl);
         if (u1 > u0)
             TFB_CUDA(cudaMemcpyAsync(c->d_state + pr * (u0 + 1), state + pr * u0, sizeof(double) * pr * (u1 - u0),
                                      cudaMemcpyHostToDevice, c->s_h2d));
@@ -546,11 +574,11 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
     m->shift = 0.0;
     c->state_uploads++;
     for (int ch = 0; ch < nch; ch++) {
-        const int p0 = ch * PCH, p1 = std::min(p0 + PCH, c->nzl);
+        const int p0 = b[ch], p1 = b[ch + 1];
         TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[ch], 0));
-        c->chunk0 = ch; c->chunkn = 1; c->chunk_planes = PCH;
+        c->win0 = p0; c->win1 = p1;                 // plane window of this launch (marching chunks inside it)
         int rc = dispatch_assemble(c, m, 1, rhs_out != nullptr);
-        c->chunk0 = -1; c->chunk_planes = 0;
+        c->win0 = 0; c->win1 = -1;
         if (rc) return rc;
         if (rhs_out) {
             TFB_CUDA(cudaEventRecord(c->ev_k[ch], c->stream));
@@ -568,8 +596,8 @@ extern "C" int tfb_jacobian(tfb_ctx* c, const double* state, tfb_mat* m, double*
     TFB_CHECK(c && state && m && m->ctx == c, "bad arguments");
     TFB_CHECK(c->have_params, "tfb_set_params has not been called");
     TFB_CUDA(cudaSetDevice(c->desc.device));
-    const int nch = (c->nzl + TFB_KCH / 2 - 1) / (TFB_KCH / 2);
-    if (c->nranks == 1 && c->desc.nz > 1 && c->desc.dim == 3 && nch >= 2 && nch < TFB_MAX_CHUNKS - 1 && !getenv("TFB_NO_PIPELINE"))
+    const int nch = c->nranks == 1 && c->desc.nz > 1 && c->desc.dim == 3 ? (int)tfb_pipe_pieces(c->nzl).size() - 1 : 0;
+    if (nch >= 2 && nch < TFB_MAX_CHUNKS - 1 && !getenv("TFB_NO_PIPELINE"))
         return jacobian_pipelined(c, state, m, rhs_out);
     int rc = tfb_state_upload(c, state);
     if (rc) return rc;
