@@ -258,6 +258,34 @@ def test_direct_solve_with_line_blocks_beyond_one_panel(problem, nx, ny):
     assert numpy.abs(y - want).max() <= 1e-9 * numpy.abs(want).max()
 
 
+@pytest.mark.parametrize('name', ['ldc2d', 'dhc2d', 'qg', 'amoc'])
+def test_direct_solve_at_the_baseline_sizes(name):
+    """The 2-D BASELINE configurations at their full sizes (32 x 32 stretched cavity, 64 x 64 heated cavity, 256 x 128
+    double gyre and AMOC: line blocks of 96 to 1280 rows, the larger ones eliminated in panels over all SMs): the Newton
+    update of the device solve against SuperLU on the pinned host matrix (SciPy.py:204-258), 1e-8 as SURVEY section 8(d)
+    asks.  SuperLU needs ~10 s for the AMOC matrix on the box's host."""
+    import scipy.sparse.linalg
+    from bench import PROBLEMS_2D
+    params, nx, ny, _ = PROBLEMS_2D[name]
+    it = _iface(dict(params), nx, ny, 1)
+    x = numpy.random.default_rng(11).uniform(-0.01, 0.01, it.n)
+    jac, f = it.jacobian_rhs(x)
+    b = -f
+    y = it.solve(jac, b)
+    assert it.last_solve['method'] == 'Direct' and it.last_solve['converged'], it.last_solve
+    import scipy.sparse
+    prow = it.pressure_row
+    keep = numpy.ones(it.n)
+    keep[prow] = 0.0
+    D = scipy.sparse.diags(keep)
+    pin = scipy.sparse.csr_matrix(([-1.0], ([prow], [prow])), shape=(it.n, it.n))
+    A = (D @ jac.tocsr() @ D + pin).tocsc()           # row and column of the pinned pressure removed, -1 on the diagonal
+    bb = b.copy()
+    bb[prow] = 0
+    want = scipy.sparse.linalg.spsolve(A, bb)
+    assert numpy.abs(y - want).max() <= 1e-8 * numpy.abs(want).max()
+
+
 @pytest.mark.parametrize('grid', [(8, 8, 8), (24, 24, 1)])
 def test_mass_shifted_matrices_carry_the_shift_into_the_preconditioner(grid):
     """J - M / (theta dt) with a small time step (and J - sigma M with a large shift) are dominated by the mass term; the
