@@ -252,10 +252,11 @@ struct RingState {
 // dof 4: one equation per scheduler, rotated with the CTA index.  Other shapes keep the plain order.
 template <int DOF, int TJ>
 __device__ __forceinline__ void tfb_deal_item(int w, int& d1, int& jl) {
-    if constexpr ((TJ == 2 || TJ == 1) && (DOF == 4 || DOF == 5)) {
+    if constexpr (((TJ == 2 || TJ == 1) && (DOF == 4 || DOF == 5)) || (TJ == 3 && DOF == 5)) {
         const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
         unsigned long long table;
-        if (TJ == 2) table = DOF == 4 ? (((lin ^ (lin / 148u)) & 1u) ? 0x54731062ull : 0x73546210ull) : 0x8350947261ull;
+        if (TJ == 3) table = 0xD83CE947B652A10ull;      // {u0,u1,T0,p0} {v0,v1,T1,p1} {u2,v2,T2,p2} {w0,w1,w2}
+        else if (TJ == 2) table = DOF == 4 ? (((lin ^ (lin / 148u)) & 1u) ? 0x54731062ull : 0x73546210ull) : 0x8350947261ull;
         else table = DOF == 4 ? (0x3210321032103210ull >> (4 * (lin & 3u))) : 0x42103ull;
         const int item = (int)((table >> (4 * w)) & 15ull);
         jl = item / DOF;
@@ -470,7 +471,7 @@ tfb_assemble_march_kernel(const TfbAsmArgs a) {
                 if (!(il & 1) && il < ncl) {
                     const int rel0 = rp - galign, rel1 = (il + 2 < ncl ? rp2 : gend) - galign;
                     const int head = rel0 & 1, b0 = rel0 + head, b1 = rel1 & ~1;
-                    if (b1 > b0) {
+                    if (b1 > b0 && !(EXP & 2)) {
                         const unsigned src = (unsigned)__cvta_generic_to_shared(out + b0 + il);
                         double* dstp = a.vals + galign + b0;
                         const unsigned bytes = (unsigned)(b1 - b0) * 8u;

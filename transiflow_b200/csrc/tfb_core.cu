@@ -395,6 +395,12 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
                 if (variant == 35) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 4>(c, m);
                 if (variant == 36) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2>(c, m);
                 if (variant == 37) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 0, 1>(c, m);
+                if (variant == 40) return launch_march_v<Cfg, DO_J, DO_F, 3, TFB_KCH, 1, 0, 1>(c, m);
+#ifdef TFB_ASM_EXPERIMENTS
+                if (variant == 45) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 2, 1>(c, m);   // no bulk stores
+                if (variant == 46) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 4, 1>(c, m);   // no row arithmetic
+                if (variant == 47) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 1, 1>(c, m);   // all warps BC-free
+#endif
                 if (variant == 38) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2, 0, 1>(c, m);
                 if (variant == 39) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3, 0, 1>(c, m);
             }
@@ -667,10 +673,10 @@ extern "C" int tfb_pinned_free(void* p) {
 }
 
 // ------------------------------- structured SpMV (tfb_spmv_march.cuh) -------------------------------
-template <class Cfg>
-static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
-                             int prow, unsigned rowmask, unsigned colmask, const double* rowscale) {
-    constexpr int TJ = 2;     // two lines per CTA (dof 5 with three measured slower: 514 us against 441 us at 128^3)
+template <class Cfg, int TJ>
+static int launch_spmv_march_t(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
+                               int prow, unsigned rowmask, unsigned colmask, const double* rowscale) {
+    // TJ: lines per CTA.  Two by default (dof 5 with three measured slower: 514 us against 441 us at 128^3)
     TfbSpmvArgs a;
     a.g = c->grid();
     a.x = x_global_base;
@@ -723,6 +729,20 @@ static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_globa
     TFB_LAUNCHED();
     TFB_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <class Cfg>
+static int launch_spmv_march(tfb_ctx* c, const tfb_mat* m, const double* x_global_base, int kvalid0, int kvalid1, double* y,
+                             int prow, unsigned rowmask, unsigned colmask, const double* rowscale) {
+#ifdef TFB_ASM_EXPERIMENTS
+    static int tj = -1;
+    if (tj < 0) { const char* e = getenv("TFB_SPMV_TJ"); tj = e ? atoi(e) : 2; }
+    if constexpr (Cfg::DOF == 4) {
+        if (tj == 3) return launch_spmv_march_t<Cfg, 3>(c, m, x_global_base, kvalid0, kvalid1, y, prow, rowmask, colmask, rowscale);
+        if (tj == 1) return launch_spmv_march_t<Cfg, 1>(c, m, x_global_base, kvalid0, kvalid1, y, prow, rowmask, colmask, rowscale);
+    }
+#endif
+    return launch_spmv_march_t<Cfg, 2>(c, m, x_global_base, kvalid0, kvalid1, y, prow, rowmask, colmask, rowscale);
 }
 
 // returns 1 when the configuration has no structured kernel (2-D / folded grids): caller uses the CSR kernel

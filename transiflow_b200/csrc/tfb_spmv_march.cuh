@@ -93,7 +93,7 @@ __device__ __forceinline__ double tfb_row_dot_any(int d1, const double* __restri
 // (The scheduler-balancing deal of the assembly kernel, tfb_deal_item, was measured here too: 244 -> 250 us at dof 4,
 // 422 -> 419 us at dof 5 -- this kernel waits on memory, not on issue slots; it keeps the plain order.)
 template <class Cfg, int TJ, int KCH, bool MASKED>
-__global__ void __launch_bounds__(32 * Cfg::DOF * TJ, (Cfg::DOF <= 4 ? 3 : 2))
+__global__ void __launch_bounds__(32 * Cfg::DOF * TJ, (Cfg::DOF <= 4 && TJ <= 2 ? 3 : 2))
 tfb_spmv_march_kernel(const TfbSpmvArgs a) {
     using M = TfbMarch<Cfg, TJ>;
     constexpr int DOF = Cfg::DOF, W = M::W, H = M::H, DSTR = M::DSTR, SLOT = M::SLOT, LINE_CAP = M::LINE_CAP;
