@@ -49,3 +49,84 @@ def make_state(kind, n):
     if kind == 'zero':
         return numpy.zeros(n)
     return numpy.random.default_rng(kind).uniform(-0.5, 0.5, n)
+
+
+# ---- user-supplied boundary conditions (Discretization.py:62-66; reference test: tests/test_interface.py:117-150) ----
+# name: (parameters, nx, ny, nz, dim, dof, state-kind, callback).  The callbacks only use the public methods of the
+# reference's BoundaryConditions class; the same functions drive the reference (make_golden.py) and the B200 Interface.
+def _bc_reference_test(bc, atom):
+    '''The callback of the reference's own test_custom_bc.'''
+    bc.heat_flux_east(atom, 0)
+    bc.heat_flux_west(atom, 0)
+    bc.no_slip_east(atom)
+    bc.no_slip_west(atom)
+    bc.heat_flux_north(atom, 0)
+    bc.heat_flux_south(atom, 0)
+    bc.no_slip_north(atom)
+    bc.no_slip_south(atom)
+    Bi = 0
+    bc.heat_flux_top(atom, 0, Bi)
+    bc.temperature_bottom(atom, 0)
+    bc.free_slip_top(atom)
+    bc.no_slip_bottom(atom)
+    return bc.get_forcing()
+
+
+def _bc_heated_box(bc, atom):
+    '''Same order of ops, every constant non-trivial: side-wall heat fluxes, a Robin lid, a hot bottom.'''
+    bc.heat_flux_east(atom, 0.25)
+    bc.heat_flux_west(atom, -0.5, 0.2)
+    bc.no_slip_east(atom)
+    bc.no_slip_west(atom)
+    bc.heat_flux_north(atom, 0.1, 0.3)
+    bc.heat_flux_south(atom, 0)
+    bc.no_slip_north(atom)
+    bc.no_slip_south(atom)
+    bc.heat_flux_top(atom, 0.4, 1.5)
+    bc.temperature_bottom(atom, 2.0)
+    bc.free_slip_top(atom)
+    bc.no_slip_bottom(atom)
+    return bc.get_forcing()
+
+
+def _bc_fast_lid(bc, atom):
+    '''Lid-driven cavity with the lid velocity given by the callback instead of the parameter list.'''
+    bc.no_slip_east(atom)
+    bc.no_slip_west(atom)
+    bc.no_slip_south(atom)
+    bc.no_slip_north(atom)
+    bc.no_slip_bottom(atom)
+    bc.moving_lid_top(atom, 3.5)
+    return bc.get_forcing()
+
+
+def _bc_walls_2d(bc, atom):
+    '''2-D box with wall temperatures of the callback's choosing (order of ops of the heated cavity).'''
+    bc.temperature_east(atom, -0.75)
+    bc.temperature_west(atom, 1.25)
+    bc.no_slip_east(atom)
+    bc.no_slip_west(atom)
+    bc.heat_flux_north(atom, 0.2)
+    bc.heat_flux_south(atom, 0, 0.5)
+    bc.no_slip_north(atom)
+    bc.no_slip_south(atom)
+    return bc.get_forcing()
+
+
+def _bc_unsupported(bc, atom):
+    '''An order of ops no kernel family is generated for (free-slip side walls under a moving lid).'''
+    bc.free_slip_east(atom)
+    bc.free_slip_west(atom)
+    bc.no_slip_south(atom)
+    bc.moving_lid_north(atom, 1.0)
+    return bc.get_forcing()
+
+
+CUSTOM_BC_CASES = {
+    'custom_reference_test': ({'Rayleigh Number': 100, 'Prandtl Number': 100}, 4, 4, 4, 3, 5, 20, _bc_reference_test),
+    'custom_heated_box': ({'Rayleigh Number': 800.0, 'Prandtl Number': 7.0, 'Reynolds Number': 1, **STR}, 5, 4, 6, 3, 5, 21,
+                          _bc_heated_box),
+    'custom_fast_lid': ({'Reynolds Number': 40}, 5, 6, 4, 3, 4, 22, _bc_fast_lid),
+    'custom_walls_2d': ({'Rayleigh Number': 1e3, 'Prandtl Number': 10.0, 'Reynolds Number': 1}, 7, 6, 1, 2, 4, 23,
+                        _bc_walls_2d),
+}

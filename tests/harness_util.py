@@ -37,11 +37,16 @@ def lib():
     return _LIB
 
 
-def assemble(parameters, nx, ny, nz, dim, dof, state, x=None, y=None, z=None):
-    '''Returns (vals, cols, row_ptr, rhs) of the fixed structural pattern (explicit zeros kept).'''
+def assemble(parameters, nx, ny, nz, dim, dof, state, x=None, y=None, z=None, boundary_conditions=None):
+    '''Returns (vals, cols, row_ptr, rhs) of the fixed structural pattern (explicit zeros kept).  With a user
+    ``boundary_conditions`` callback the kernel family is the one whose recipe has the structure of the recorded ops
+    (recipes.match_recorded), exactly as Interface.__init__ chooses it.'''
     p = parameters
     problem = recipes.PROBLEM_IDS[p.get('Problem Type', 'Lid-driven Cavity').lower()]
-    cfg = recipes.find_config(problem, dim, nz, dof)
+    if boundary_conditions is not None:
+        cfg = recipes.match_recorded(recipes.record_boundary_conditions(boundary_conditions), dim, nz, dof)
+    else:
+        cfg = recipes.find_config(problem, dim, nz, dof)
     assert cfg is not None, 'no generated config'
     x = hostprep.coordinate_vector(p, p.get('X-min', 0.0), p.get('X-max', 1.0), nx) if x is None else x
     y = hostprep.coordinate_vector(p, p.get('Y-min', 0.0), p.get('Y-max', 1.0), ny) if y is None else y

@@ -6,7 +6,7 @@ operation order).'''
 import numpy
 import pytest
 
-from cases import CASES, make_state
+from cases import CASES, CUSTOM_BC_CASES, _bc_unsupported, make_state
 from golden_io import assert_csr_equal, compress, load_case, read_ref_matrix, read_ref_vector
 
 pytestmark = pytest.mark.gpu
@@ -146,12 +146,44 @@ def test_matvec_matches_scipy():
     assert numpy.iscomplexobj(gotc) and numpy.allclose(gotc, wantc, rtol=1e-13, atol=1e-13 * numpy.abs(wantc).max())
 
 
+@pytest.mark.parametrize('name', sorted(CUSTOM_BC_CASES))
+def test_user_boundary_conditions_on_the_device(name):
+    """``Interface(..., boundary_conditions=callback)`` (Discretization.py:62-66,719; 'custom_reference_test' is the callback
+    of the reference's tests/test_interface.py:117-150): the callback is recorded once, its op sequence picks a generated
+    kernel family and its constants become kernel arguments.  CSR and RHS bit-identical to the reference run with the same
+    callback; the Newton-update solve works on such a matrix like on any other."""
+    from transiflow_b200 import Interface
+    params, nx, ny, nz, dim, dof, kind, callback = CUSTOM_BC_CASES[name]
+    g = load_case(name)
+    it = Interface(dict(params), nx, ny, nz, dim, dof, g['x'], g['y'], g['z'], boundary_conditions=callback)
+    jac, f = it.jacobian_rhs(g['state'])
+    row_ptr, col = it.pattern()
+    assert_csr_equal(compress(jac.values(), col, row_ptr), (g['coA'], g['jcoA'], g['begA']), 0.0, name)
+    assert numpy.array_equal(f, g['rhs'])
+    assert numpy.array_equal(it.rhs(g['state']), g['rhs'])
+    # the reference's test only asks for rhs(zero state) to run
+    it.rhs(it.vector())
+    it.parameters['Iterative Solver'] = {'Maximum Iterations': 2000, 'Restart': 2000}
+    dx = it.solve(jac, -f)
+    assert it.last_solve['converged'], it.last_solve
+    A = jac.tocsr().tolil()
+    A[it.dim, :] = 0
+    A[:, it.dim] = 0
+    A[it.dim, it.dim] = -1
+    b = -f.copy()
+    b[it.dim] = 0
+    r = A.tocsr() @ dx - b
+    assert numpy.linalg.norm(r) <= 1e-8 * numpy.linalg.norm(b)
+
+
 def test_unsupported_configurations_fail_loudly():
     from transiflow_b200 import Interface
     with pytest.raises(NotImplementedError):
         Interface({'Problem Type': 'Double Gyre'}, 4, 4, 1, 2, 4)      # QG with an extra scalar
     with pytest.raises(NotImplementedError):
-        Interface({}, 4, 4, 4, boundary_conditions=lambda bc, atom: None)
+        Interface({}, 4, 4, 4, boundary_conditions=lambda bc, atom: None)       # applies nothing: no such kernel family
+    with pytest.raises(NotImplementedError, match='no kernel family'):
+        Interface({}, 6, 6, 1, boundary_conditions=_bc_unsupported)             # free-slip side walls under a moving lid
     with pytest.raises(Exception):
         Interface({'Problem Type': 'nonsense'}, 4, 4, 4)
 

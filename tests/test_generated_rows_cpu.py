@@ -3,7 +3,7 @@ compiled for the host, against the oracle and the committed golden vectors.  CPU
 import numpy
 import pytest
 
-from cases import CASES, make_state
+from cases import CASES, CUSTOM_BC_CASES, _bc_unsupported, make_state
 from golden_io import assert_csr_equal, compress, load_case
 from harness_util import assemble
 from oracle.tf_oracle import Oracle
@@ -37,3 +37,28 @@ def test_pattern_is_state_independent_superset(name):
         assert numpy.array_equal(rhs, orc.rhs(state)) or numpy.allclose(rhs, orc.rhs(state), rtol=1e-13, atol=1e-13)
     if params.get('Problem Type') not in ('AMOC',):
         assert numpy.all(numpy.abs(val) > 1e-14), 'generic state should populate the full structural pattern'
+
+
+@pytest.mark.parametrize('name', sorted(CUSTOM_BC_CASES))
+def test_user_boundary_conditions_match_golden(name):
+    '''User-supplied ``boundary_conditions(bc, atom)`` callbacks (Discretization.py:62-66,719; the first case is the
+    callback of the reference's own tests/test_interface.py:117-150): the recorded ops select a generated kernel family,
+    the callback's constants become run-time arguments -- CSR and RHS bit-identical to the reference run with the same
+    callback (fixtures: tests/golden/make_golden.py).'''
+    params, nx, ny, nz, dim, dof, kind, callback = CUSTOM_BC_CASES[name]
+    g = load_case(name)
+    val, col, ptr, rhs = assemble(dict(params), nx, ny, nz, dim, dof, g['state'], g['x'], g['y'], g['z'],
+                                  boundary_conditions=callback)
+    assert_csr_equal(compress(val, col, ptr), (g['coA'], g['jcoA'], g['begA']), 0.0, name)
+    assert numpy.array_equal(rhs, g['rhs'])
+
+
+def test_boundary_recorder_and_matcher():
+    from transiflow_b200 import recipes
+    ops = recipes.record_boundary_conditions(CUSTOM_BC_CASES['custom_fast_lid'][-1])
+    assert ops[-2:] == [('force', 2, 1, 'u', 'lidv', 3.5), ('wall', 2, 1, -1)]          # moving lid = forcing + no-slip fold
+    cfg = recipes.match_recorded(ops, 3, 4, 4)
+    assert cfg is not None and cfg.name == 'ldc3d' and cfg.recipe == ops
+    assert recipes.find_config(recipes.LDC, 3, 4, 4).recipe != ops                      # the generated config is untouched
+    assert recipes.match_recorded(ops, 3, 4, 5) is None                                 # other unknowns: other family
+    assert recipes.match_recorded(recipes.record_boundary_conditions(_bc_unsupported), 2, 1, 3) is None

@@ -180,12 +180,14 @@ def make_params(cfg, problem, parameters, nx, ny, nz, x, y, z):
         _, axis, far, var, kind, arg = op
         if kind == 'lid':
             cf, ca = 2 * _get(parameters, 'Lid Velocity', 1), -1
+        elif kind == 'lidv':                                  # a user callback's moving lid: literal velocity
+            cf, ca = 2 * arg, -1
         elif kind == 'temp':
             Tb = (1 if problem == recipes.RB else 0) if arg == 'bottom' else arg
             cf, ca = 2 * Tb, -1
         elif kind == 'hflux':
             Q = _get(parameters, 'Asymmetry Parameter') if arg[0] == 'asym' else arg[0]
-            b = Bi if arg[1] == 'Bi' else 0.0
+            b = Bi if arg[1] == 'Bi' else float(arg[1])
             cf, ca = _robin_constants(X[axis], m[axis], far, Q, b)
         elif kind == 'sflux':
             Xa = X[axis]

@@ -238,8 +238,6 @@ class Interface:
 
     def __init__(self, parameters, nx, ny, nz=1, dim=None, dof=None,
                  x=None, y=None, z=None, boundary_conditions=None, device=0, slab=None):
-        if boundary_conditions is not None:
-            raise NotImplementedError('user-supplied boundary_conditions callbacks cannot run on the device')
         self.parameters = parameters
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dim = dim if dim is not None else (3 if nz > 1 else 2)       # Discretization.py:115-117
@@ -254,7 +252,17 @@ class Interface:
             elif self.problem == recipes.AMOC:
                 dof = self.dim + 3
         self.dof = dof
-        self.config = recipes.find_config(self.problem, self.dim, nz, dof)
+        if boundary_conditions is not None:
+            # Discretization.py:62-66,719: the callback is recorded once; it runs on the device if its sequence of ops has
+            # the structure of a generated recipe (its constants are run-time arguments of the kernels), see recipes.py
+            ops = recipes.record_boundary_conditions(boundary_conditions)
+            self.config = recipes.match_recorded(ops, self.dim, nz, dof)
+            if self.config is None:
+                raise NotImplementedError(
+                    'this boundary_conditions callback applies a sequence of ops for which no kernel family is generated '
+                    '(dim=%d nz=%d dof=%d): %r' % (self.dim, nz, dof, [op[:4] for op in ops]))
+        else:
+            self.config = recipes.find_config(self.problem, self.dim, nz, dof)
         if self.config is None:
             raise NotImplementedError('no B200 kernel family for problem=%r dim=%d nz=%d dof=%d'
                                       % (ptype, self.dim, nz, dof))

@@ -130,3 +130,83 @@ def find_config(problem, dim, nz, dof):
         if c.problem == base and c.dim == dim and c.flat == flat and c.dof == dof:
             return c
     return None
+
+
+# ---------------------------------------------------------------------------------------
+# User-supplied boundary conditions (Discretization.py:62-66,719: ``boundary_conditions(bc, atom)``).
+# The callback is run once against a recorder that has the public methods of the reference's
+# BoundaryConditions class (BoundaryConditions.py:55-469) and notes which op each call is -- every
+# one of them is a wall fold or a `_constant_forcing_<face>` with two constants.  The generated
+# kernels depend on the ORDER and KIND of the ops (face, variable, no-slip / free-slip) only; the
+# constants are run-time arguments.  So a callback whose op sequence has the structure of one of the
+# generated recipes runs on the device with its own constants; anything else raises.
+# ---------------------------------------------------------------------------------------
+_FACES = {'east': E, 'west': W, 'north': N, 'south': S, 'top': T, 'bottom': B}
+
+
+class BoundaryRecorder:
+    '''Stand-in for ``transiflow.BoundaryConditions`` that records the ops a callback applies.'''
+
+    def __init__(self):
+        self.ops = []
+
+    def get_forcing(self):
+        return None
+
+
+def _recorder_method(kind, face):
+    axis, far = _FACES[face]
+    if kind == 'no_slip':
+        return lambda self, atom: self.ops.append(('wall', axis, far, NOSLIP))
+    if kind == 'free_slip':
+        return lambda self, atom: self.ops.append(('wall', axis, far, FREESLIP))
+    if kind == 'moving_lid':
+        # the tangential velocity that is prescribed: v on the x faces, u elsewhere (BoundaryConditions.py:235-295);
+        # the reference applies the no-slip fold right after the forcing
+        var = 'v' if axis == 0 else 'u'
+
+        def lid(self, atom, velocity):
+            self.ops.append(('force', axis, far, var, 'lidv', velocity))
+            self.ops.append(('wall', axis, far, NOSLIP))
+        return lid
+    if kind == 'temperature':
+        return lambda self, atom, temperature: self.ops.append(('force', axis, far, 'T', 'temp', temperature))
+    if kind == 'heat_flux':
+        return lambda self, atom, heat_flux, biot=0.0: self.ops.append(('force', axis, far, 'T', 'hflux', (heat_flux, biot)))
+    if kind == 'salinity_flux':
+        return lambda self, atom, salinity_flux: self.ops.append(('force', axis, far, 'S', 'sflux', salinity_flux))
+    raise ValueError(kind)
+
+
+for _kind in ('no_slip', 'free_slip', 'moving_lid', 'temperature', 'heat_flux', 'salinity_flux'):
+    for _face in _FACES:
+        setattr(BoundaryRecorder, '%s_%s' % (_kind, _face), _recorder_method(_kind, _face))
+
+
+def _structure(op):
+    if op[0] == 'wall':
+        return op
+    if op[0] == 'force':
+        return op[:4] + (op[4] in ('tarr', 'sarr'),)     # constants vs per-face value arrays
+    return op
+
+
+def record_boundary_conditions(callback):
+    '''Ops (in our tuple format, constants as literals) that ``callback(bc, atom)`` applies.'''
+    rec = BoundaryRecorder()
+    callback(rec, None)
+    return rec.ops
+
+
+def match_recorded(ops, dim, nz, dof):
+    '''A copy of the generated Config whose recipe has the structure of ``ops`` (same grid family: dim, flat, dof),
+    carrying ``ops`` -- i.e. the callback's own constants -- as its recipe; None if no kernel family has that structure.'''
+    import copy
+    flat = dim == 2 or nz <= 1
+    want = [_structure(op) for op in ops]
+    for c in CONFIGS:
+        if c.dim == dim and c.flat == flat and c.dof == dof and [_structure(op) for op in c.recipe] == want:
+            c2 = copy.copy(c)
+            c2.recipe = list(ops)
+            return c2
+    return None
