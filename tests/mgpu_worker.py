@@ -117,6 +117,12 @@ def main():
         ok &= say(rank, world, '%s tall slabs: rhs() and jacobian() alone equal the fused launch / the oracle' % name, good)
         del it, jonly, both
 
+    # ---- slabs of 17-18 planes: the host path of jacobian_rhs is pipelined over z-pieces (edge planes first, halo exchange
+    # while the rest of the slab is uploaded) -- same bits ----
+    it, orc, r0, r1 = make(LDC, 7, 5, 17 * world + 1, rank, world, local)
+    ok &= assembly_parity(it, orc, r0, r1, rank, world, 'LDC 7x5x%d (pipelined host path)' % (17 * world + 1))
+    del it
+
     # ---- Rayleigh-Benard: assembly, and the coupled (w, T) line solve on pencils (all z, a chunk of y) ----
     nx, ny = 9, 10
     it, orc, r0, r1 = make(RB, nx, ny, nz, rank, world, local)

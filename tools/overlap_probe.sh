@@ -1,10 +1,12 @@
-# Two-GPU check of the side-stream halo exchange of the assembly (TFB_OVERLAP=asm): bench timings with and without.
+# Two-GPU check: parity worker, then the bench line (e2e on z-slabs now goes through the pipelined host path).
 python -c "import torch"
-run() { timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 200 --warmup 5 --no-cpu-baseline --newton-steps $2 --rb-strong $1 2>&1 | grep '^{' | python -c "
-import sys, json
-for l in sys.stdin:
-    d = json.loads(l)
-    print('asm %.4f ms  e2e %.3f ms  spmv %.4f  rb_strong %s newton %s' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['spmv']['ms'], (d.get('rb_strong') or {}).get('assembly_ms'), (d.get('newton') or {}).get('ms_per_step')))
-"; echo "rc=${PIPESTATUS[0]}"; }
-echo "== bench, overlap asm"; TFB_OVERLAP=asm run 1 0
-echo "== bench, overlap both"; TFB_OVERLAP=1 run 0 3
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/mgpu_worker.py 2>&1 | grep -i "pipelined\|tall\|ALL OK\|FAILED\|MISMATCH\|Error" | head -12
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 --no-cpu-baseline --newton-steps 3 --rb-strong 1 2>&1 | grep '^{' > gpurun_out/bench_final_2gpu.json; echo "rc=$?"
+python - <<'P'
+import json
+for l in open('gpurun_out/bench_final_2gpu.json'):
+    d = json.loads(l); n = d['newton']; r = d.get('rb_strong') or {}
+    print('asm %.4f ms  e2e %.3f ms  spmv %.4f  newton %.1f ms %s  rb_strong asm %s newton %s  parity_slabs %s' % (
+        d['ms_per_step'], d['e2e']['ms_per_step'], d['spmv']['ms'], n['ms_per_step'], n['krylov_iterations'],
+        r.get('assembly_ms'), r.get('newton_ms_per_step'), d.get('parity_slabs')))
+P

@@ -549,7 +549,7 @@ static std::vector<int> tfb_pipe_pieces(int nzl) {
     return b;
 }
 
-// Host-buffer path for 3-D grids on one GPU: the upload of the state, the assembly and the download
+// Host-buffer path for 3-D grids (one GPU or a z-slab): the upload of the state, the assembly and the download
 // of F(x) are pipelined over z-pieces on three streams (PCIe is full duplex), so the call costs
 // about max(H2D, D2H) instead of H2D + kernel + D2H.
 static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, double* rhs_out) {
@@ -567,10 +567,22 @@ static int jacobian_pipelined(tfb_ctx* c, const double* state, tfb_mat* m, doubl
     TFB_CUDA(cudaEventRecord(c->ev_k[TFB_MAX_CHUNKS - 1], c->stream));
     TFB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[TFB_MAX_CHUNKS - 1], 0));
     const size_t pr = (size_t)c->plane_rows;
+    int lo = 0, hi = c->nzl;      // planes the pieces still have to upload
+    if (c->nranks > 1) {
+        // z-slab: the first and the last owned plane go up first and are exchanged with the neighbours on the compute
+        // stream (NCCL) while the bulk of the slab is still on its way
+        TFB_CUDA(cudaMemcpyAsync(c->d_state + pr, state, sizeof(double) * pr, cudaMemcpyHostToDevice, c->s_h2d));
+        TFB_CUDA(cudaMemcpyAsync(c->d_state + pr * c->nzl, state + pr * (c->nzl - 1), sizeof(double) * pr,
+                                 cudaMemcpyHostToDevice, c->s_h2d));
+        TFB_CUDA(cudaEventRecord(c->ev_up[TFB_MAX_CHUNKS - 2], c->s_h2d));
+        TFB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[TFB_MAX_CHUNKS - 2], 0));
+        if (tfb_halo_exchange(c, c->d_state)) return -1;
+        lo = 1; hi = c->nzl - 1;
+    }
     // upload pieces are shifted by one plane: piece ch ends with the first plane of piece ch+1, which is the
     // only plane of the next piece the kernel of piece ch reads
     for (int ch = 0; ch < nch; ch++) {
-        const int u0 = ch == 0 ? 0 : b[ch] + 1, u1 = std::min(b[ch + 1] + 1, c->nzl);
+        const int u0 = std::max(lo, ch == 0 ? 0 : b[ch] + 1), u1 = std::min(hi, std::min(b[ch + 1] + 1, c->nzl));
         if (u1 > u0)
             TFB_CUDA(cudaMemcpyAsync(c->d_state + pr * (u0 + 1), state + pr * u0, sizeof(double) * pr * (u1 - u0),
                                      cudaMemcpyHostToDevice, c->s_h2d));
@@ -602,7 +614,7 @@ extern "C" int tfb_jacobian(tfb_ctx* c, const double* state, tfb_mat* m, double*
     TFB_CHECK(c && state && m && m->ctx == c, "bad arguments");
     TFB_CHECK(c->have_params, "tfb_set_params has not been called");
     TFB_CUDA(cudaSetDevice(c->desc.device));
-    const int nch = c->nranks == 1 && c->desc.nz > 1 && c->desc.dim == 3 ? (int)tfb_pipe_pieces(c->nzl).size() - 1 : 0;
+    const int nch = c->desc.nz > 1 && c->desc.dim == 3 && c->nzl >= 4 ? (int)tfb_pipe_pieces(c->nzl).size() - 1 : 0;
     if (nch >= 2 && nch < TFB_MAX_CHUNKS - 1 && !getenv("TFB_NO_PIPELINE"))
         return jacobian_pipelined(c, state, m, rhs_out);
     int rc = tfb_state_upload(c, state);
