@@ -328,12 +328,11 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     a.rhs = c->d_rhs;
     a.k0 = c->desc.k0;
     a.nzl = c->nzl;
-    a.kstep = (c->chunk0 >= 0 && c->chunk_planes > 0) ? std::min(c->chunk_planes, KCH) : KCH;
-    a.kofs0 = c->win1 >= 0 ? c->win0 : 0;
-    a.klim = c->win1 >= 0 ? c->win1 : c->nzl;
-    const int nchunks = (a.klim - a.kofs0 + a.kstep - 1) / a.kstep;
-    a.kc0 = c->chunk0 >= 0 ? c->chunk0 : 0;
-    const int nlaunch = c->chunk0 >= 0 ? std::min(c->chunkn, nchunks - a.kc0) : nchunks;
+    a.kstep = KCH;
+    a.kofs0 = c->win1 >= 0 ? c->win0 : 0;        // plane window [win0, win1) of this launch (pieces of the host pipeline,
+    a.klim = c->win1 >= 0 ? c->win1 : c->nzl;    // interior planes of a z-slab); the whole slab otherwise
+    a.kc0 = 0;
+    const int nlaunch = (a.klim - a.kofs0 + a.kstep - 1) / a.kstep;
     size_t smem = sizeof(double) * TfbMarch<Cfg, TJ>::smem_doubles(DO_J);
     auto kern = tfb_assemble_march_kernel<Cfg, DO_J, DO_F, TJ, KCH, MINB, EXP, OPT>;
     static unsigned configured_devices = 0;       // the attribute is per device
@@ -349,10 +348,12 @@ static int launch_march_v(tfb_ctx* c, tfb_mat* m) {
     return 0;
 }
 
-// Tile shape / occupancy variant.  Default: TJ lines per CTA, MINB CTAs per SM (register cap).
-// TFB_ASM_VARIANT (env) selects alternatives for the headline 3D LDC kernel while tuning.
+// Kernel shape per configuration.  The alternatives that were measured against the defaults (tile shapes, occupancy caps,
+// ablations) are only compiled with -DTFB_ASM_EXPERIMENTS (TFB_ASM_EXPERIMENTS=1 python -m transiflow_b200.build) and
+// selected with TFB_ASM_VARIANT; tools/asm_time.py times them.
 template <class Cfg, bool DO_J, bool DO_F>
 static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
+#ifdef TFB_ASM_EXPERIMENTS
     static int variant = -1;
     if (variant < 0) {
         const char* e = getenv("TFB_ASM_VARIANT");
@@ -360,50 +361,42 @@ static int launch_assemble_t(tfb_ctx* c, tfb_mat* m) {
     }
     if constexpr (Cfg::ID == 1 && DO_J && DO_F) {   // Cfg_ldc3d
         switch (variant) {
-        case 16: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);
+        case 16: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2>(c, m);      // round-1 default
         case 17: return launch_march_v<Cfg, DO_J, DO_F, 4, 16, 1>(c, m);
         case 24: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 3>(c, m);
         case 18: return launch_march_v<Cfg, DO_J, DO_F, 2, 32, 2>(c, m);
         case 19: return launch_march_v<Cfg, DO_J, DO_F, 2, 8, 2>(c, m);
         case 20: return launch_march_v<Cfg, DO_J, DO_F, 3, 16, 1>(c, m);
-        case 21: return launch_march_v<Cfg, DO_J, DO_F, 4, 32, 1>(c, m);
         case 22: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 4>(c, m);
-        case 23: return launch_march_v<Cfg, DO_J, DO_F, 1, 32, 4>(c, m);
-#ifdef TFB_ASM_EXPERIMENTS
         case 41: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 1>(c, m);   // every warp on the BC-free path (timing only)
         case 42: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 2>(c, m);   // no bulk stores
         case 44: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 4>(c, m);   // no row arithmetic
         case 43: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 3>(c, m);
         case 51: return launch_march_v<Cfg, DO_J, DO_F, 2, 16, 2, 0, 1>(c, m);
-        case 52: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 4, 0, 1>(c, m);
         case 53: return launch_march_v<Cfg, DO_J, DO_F, 1, 16, 3, 0, 1>(c, m);
-#endif
         default: break;
         }
     }
+    if constexpr (!Cfg::FLAT && Cfg::DOF >= 5 && DO_J && DO_F) {
+        if (c->win1 != -2) {
+            if (variant == 31) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 2>(c, m);
+            if (variant == 32) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);      // round-1 default
+            if (variant == 34) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3>(c, m);
+            if (variant == 36) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2>(c, m);
+            if (variant == 38) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2, 0, 1>(c, m);
+            if (variant == 40) return launch_march_v<Cfg, DO_J, DO_F, 3, TFB_KCH, 1, 0, 1>(c, m);
+            if (variant == 45) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 2, 1>(c, m);   // no bulk stores
+            if (variant == 46) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 4, 1>(c, m);   // no row arithmetic
+            if (variant == 47) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 1, 1>(c, m);   // all warps BC-free
+        }
+    }
+#endif
     if constexpr (!Cfg::FLAT) {
         // the two planes of a z-slab that read the halo, after the exchange that ran next to the interior planes: one launch
         // of the plane-tile kernel (a marching CTA would fill its ring for a single plane)
         if (c->win1 == -2) return launch_assemble_v<Cfg, DO_J, DO_F, 2, 2>(c, m);
         // true 3-D grids: z-marching kernel (ring of state planes, software prefetch)
         if constexpr (Cfg::DOF >= 5) {
-            if constexpr (DO_J && DO_F) {
-                if (variant == 31) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 2>(c, m);
-                if (variant == 32) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1>(c, m);
-                if (variant == 33) return launch_march_v<Cfg, DO_J, DO_F, 4, TFB_KCH, 1>(c, m);
-                if (variant == 34) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3>(c, m);
-                if (variant == 35) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 4>(c, m);
-                if (variant == 36) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2>(c, m);
-                if (variant == 37) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 0, 1>(c, m);
-                if (variant == 40) return launch_march_v<Cfg, DO_J, DO_F, 3, TFB_KCH, 1, 0, 1>(c, m);
-#ifdef TFB_ASM_EXPERIMENTS
-                if (variant == 45) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 2, 1>(c, m);   // no bulk stores
-                if (variant == 46) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 4, 1>(c, m);   // no row arithmetic
-                if (variant == 47) return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 1, 1>(c, m);   // all warps BC-free
-#endif
-                if (variant == 38) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 2, 0, 1>(c, m);
-                if (variant == 39) return launch_march_v<Cfg, DO_J, DO_F, 1, TFB_KCH, 3, 0, 1>(c, m);
-            }
             // dof 5: 168 registers, no spills, one CTA of ten warps per SM; the warp -> (equation, line) table evens the
             // four schedulers out (0.477 -> 0.453 ms at 128^3)
             return launch_march_v<Cfg, DO_J, DO_F, 2, TFB_KCH, 1, 0, 1>(c, m);

@@ -62,7 +62,6 @@ struct tfb_ctx {
     // pipelined host path of tfb_jacobian: copy streams, per-chunk events, z-chunk window of a launch
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[TFB_MAX_CHUNKS] = {}, ev_k[TFB_MAX_CHUNKS] = {};
-    int chunk0 = -1, chunkn = 0, chunk_planes = 0;
     int win0 = 0, win1 = -1;    // plane window [win0, win1) of the next assembly launch (win1 < 0: the whole slab)
     // z-slabs: the halo exchange runs on its own stream next to the interior planes of the kernel that needs it
     void* direct_pool = nullptr;   // parked work space of the 2-D direct solve (tfb_direct.cu)
