@@ -521,6 +521,17 @@ static std::vector<int> tfb_pipe_pieces(int nzl) {
     static int uniform = -1;
     if (uniform < 0) { const char* e = getenv("TFB_PIPE_PLANES"); uniform = e ? std::max(1, atoi(e)) : 0; }
     std::vector<int> b{0};
+    if (const char* e = getenv("TFB_PIPE_PIECES")) {          // explicit piece sizes "4,12,16,...": tuning only
+        int k = 0;
+        for (const char* q = e; *q && k < nzl;) {
+            k = std::min(nzl, k + std::max(1, atoi(q)));
+            b.push_back(k);
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        if (b.back() != nzl) b.push_back(nzl);
+        return b;
+    }
     if (uniform > 0 || nzl < 64) {
         const int step = uniform > 0 ? uniform : 8;
         for (int k = step; k < nzl; k += step) b.push_back(k);
