@@ -7,11 +7,11 @@ cd "$(dirname "$0")/.."
 SO=transiflow_b200/lib/libtfb200.so
 OUT=profiles/sass
 mkdir -p $OUT
-cuobjdump -res-usage $SO 2>/dev/null | grep -A1 "Function" | grep -v "^--" | paste - - | sed 's/^ *//' | grep -E "assemble_march_kernelI9Cfg_(ldc3d|rb3d)Lb1ELb1E|spmv_march_kernelI9Cfg_(ldc3d|rb3d)|tfb_fdm_plane_kernel|tfb_thomas_kernel|k_idr_sweep|k_shadow_dots|k_all_axpy|tfb_tc_pre4|tfb_tc_post4" > $OUT/r2_resource_usage.txt
-for pat in "tfb_fdm_plane_kernelILi32ELi3E" "tfb_assemble_march_kernelI9Cfg_ldc3dLb1ELb1ELi2ELi16ELi2E" "tfb_spmv_march_kernelI9Cfg_ldc3dLi2ELi16ELb0E"; do
+cuobjdump -res-usage $SO 2>/dev/null | grep -A1 "Function" | grep -v "^--" | paste - - | sed 's/^ *//' | grep -E "assemble_march_kernelI[0-9]Cfg_(ldc3d|rb3d)Lb1ELb1E|spmv_march_kernelI9Cfg_(ldc3d|rb3d)|tfb_fdm_plane_kernel|tfb_thomas_kernel|k_idr_sweep|k_shadow_dots|k_all_axpy|tfb_tc_pre4|tfb_tc_post4|k_gj_blocked" > $OUT/r2_resource_usage.txt
+for pat in "tfb_fdm_plane_kernelILi32ELi3E" "tfb_assemble_march_kernelI9Cfg_ldc3dLb1ELb1ELi1ELi16ELi4ELi0ELi1E" "tfb_assemble_march_kernelI8Cfg_rb3dLb1ELb1ELi2ELi16ELi1ELi0ELi1E" "k_gj_blockedILi512E" "tfb_spmv_march_kernelI9Cfg_ldc3dLi2ELi16ELb0E"; do
     fn=$(cuobjdump -res-usage $SO 2>/dev/null | grep -o "Function [^:]*" | awk '{print $2}' | grep "$pat" | head -1)
     [ -z "$fn" ] && continue
-    short=$(echo $pat | sed 's/I9Cfg_/_/; s/[^A-Za-z0-9_]/_/g')
+    short=$(echo $pat | sed 's/I[0-9]Cfg_/_/; s/[^A-Za-z0-9_]/_/g')
     {
         echo "# cuobjdump -sass -fun $fn $SO  (filtered to the async-proxy / tensor-core / barrier instructions)"
         echo "# mnemonic histogram:"
