@@ -26,7 +26,7 @@ struct tfb_direct_factor {
     double* rowbuf = nullptr;   // m
     int* piv = nullptr;         // m
     int* colsrc = nullptr;      // m
-    int* swp = nullptr;         // 160: rows touched by the swaps of a panel (k_gj_blocked)
+    int* swp = nullptr;         // 2 x 160: rows touched by the swaps of a panel (k_gj_blocked / k_gj_lookahead)
     unsigned* bar = nullptr;    // grid barrier counter + status word
     double* y = nullptr;        // n work vectors
     double* z = nullptr;
@@ -420,6 +420,249 @@ __global__ void __launch_bounds__(NT) k_gj_blocked(int m, int NB, double* __rest
         for (int j = tid; j < m; j += NT) out[(size_t)i * m + j] = A[(size_t)i * m + colsrc[j]];
 }
 
+
+// ---- the same elimination with LOOK-AHEAD (opt-in: TFB_DIRECT_LOOKAHEAD=1, see direct_factor) ----
+// In k_gj_blocked every CTA but one waits while the panel is eliminated, and that one waits while the others update.  Here
+// CTA 0 owns no columns of its own: while the other CTAs apply panel n to their columns, CTA 0 applies it to the columns of
+// panel n+1 only (straight into its shared-memory copy), eliminates that panel and publishes it -- one grid barrier per
+// panel, and the update hides behind the elimination (which is the longer of the two).  The swap lists are double-buffered.
+template <int NT>
+__global__ void __launch_bounds__(NT) k_gj_lookahead(int m, int NB, double* __restrict__ A, int* __restrict__ piv, int* __restrict__ swp,
+                                                     int* __restrict__ colsrc, unsigned* __restrict__ bar, double* __restrict__ out, double tiny) {
+    extern __shared__ double sm[];
+    const int ld = NB | 1;
+    double* tmp = sm;                            // [64][32]: rows touched by the swaps of the current panel, permuted
+    double* P = sm + 2048;                       // CTA 0: the panel being eliminated; others: the eliminated panel
+    double* colbuf = sm + (size_t)m * ld + 2048; // m
+    double* rowbuf = colbuf + m;                 // NB
+    double* rowold = rowbuf + NB;                // NB
+    int* posof = reinterpret_cast<int*>(rowold + NB);
+    int* spiv = posof + m;
+    __shared__ double s_val[NT / 32];
+    __shared__ int s_row[NT / 32];
+    __shared__ int s_T[64], s_sig[64], s_nt;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    unsigned epoch = 0;
+    const unsigned nblk = gridDim.x;
+    const int np = (m + NB - 1) / NB;
+
+    // columns k0..k0+nb of all rows -> P (thread <-> (column, row group), eight loads in flight)
+    auto load_plain = [&](int k0, int nb) {
+        const int JW = nb <= 8 ? 8 : nb <= 16 ? 16 : 32;
+        const int jl = tid & (JW - 1), rg = tid / JW, nrg = NT / JW;
+        for (int j = jl; j < nb; j += JW)
+            for (int i0 = rg; i0 < m; i0 += 8 * nrg) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; v[u] = i < m ? A[(size_t)i * m + k0 + j] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; if (i < m) P[i * ld + j] = v[u]; }
+            }
+    };
+    // Gauss-Jordan steps on the panel in P (see k_gj_blocked), panel back to the matrix, swap list to swp_out
+    auto eliminate = [&](int k0, int nb, int* swp_out) {
+        const int JW = nb <= 8 ? 8 : nb <= 16 ? 16 : 32;
+        const int jl = tid & (JW - 1), rg = tid / JW, nrg = NT / JW;
+        for (int i = tid; i < m; i += NT) posof[i] = (i >= k0 && i < k0 + nb) ? i - k0 : -1;
+        __syncthreads();
+        for (int s = 0; s < nb; s++) {
+            const int k = k0 + s;
+            // pivot of column s among the rows k..m-1 (smallest row on ties)
+            double best = -1.0;
+            int brow = k;
+            for (int i = k + tid; i < m; i += NT) {
+                const double v = fabs(P[i * ld + s]);
+                if (v > best) { best = v; brow = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double v = __shfl_xor_sync(0xffffffffu, best, o);
+                const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
+                if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
+            }
+            if (lane == 0) { s_val[warp] = best; s_row[warp] = brow; }
+            __syncthreads();
+            // every warp reduces the NW warp results again with shuffles (no second barrier, no serial loop)
+            best = lane < NW ? s_val[lane] : -1.0;
+            brow = lane < NW ? s_row[lane] : m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double v = __shfl_xor_sync(0xffffffffu, best, o);
+                const int rw = __shfl_xor_sync(0xffffffffu, brow, o);
+                if (v > best || (v == best && rw < brow)) { best = v; brow = rw; }
+            }
+            const int p = brow;
+            if (tid == 0) {
+                piv[k] = p;
+                spiv[s] = p;
+                if (!(best > tiny)) bar[1] = 1u;     // numerically singular block
+            }
+            // The row that becomes the pivot row (rowbuf), the row it displaces (rowold), and the multiplier of every
+            // row: column s as it stands after the swap, times 1 / pivot.  The pivot row itself carries -1 / pivot and
+            // starts from zero, so that one formula,  new = base - f * rowbuf  (and -f in column s), serves all rows.
+            const double pivinv = 1.0 / P[p * ld + s];
+            for (int j = tid; j < nb; j += NT) { rowbuf[j] = P[p * ld + j]; rowold[j] = P[k * ld + j]; }
+            for (int i = tid; i < m; i += NT) {
+                double cv = P[i * ld + s];
+                if (i == p) cv = P[k * ld + s];
+                colbuf[i] = i == k ? -pivinv : cv * pivinv;
+            }
+            __syncthreads();
+            const bool swapped = p != k;
+            for (int j = jl; j < nb; j += JW) {
+                const double rb = rowbuf[j], ro = rowold[j];
+                const bool js = j == s;
+                double* col = P + j;
+                // every row by the same formula (the values it leaves in rows k and p are wrong) ...
+#pragma unroll 4
+                for (int i = rg; i < m; i += nrg) {
+                    const double f = colbuf[i];
+                    const double v = col[i * ld] - f * rb;
+                    col[i * ld] = js ? -f : v;
+                }
+                // ... then the owner of rows k and p in this column (the thread that just wrote them) sets them right:
+                // the pivot row starts from zero, the row that received the displaced row k from that row
+                if (rg == k % nrg) { const double f = colbuf[k]; col[k * ld] = js ? -f : 0.0 - f * rb; }
+                if (swapped && rg == p % nrg) { const double f = colbuf[p]; col[p * ld] = js ? -f : ro - f * rb; }
+            }
+            __syncthreads();
+        }
+        for (int j = jl; j < nb; j += JW)
+            for (int i = rg; i < m; i += nrg) A[(size_t)i * m + k0 + j] = P[i * ld + j];
+        if (tid == 0) {
+            int nt = nb;
+            for (int a = 0; a < nb; a++) { s_T[a] = k0 + a; s_sig[a] = a; }
+            for (int s2 = 0; s2 < nb; s2++) {
+                const int p = spiv[s2];
+                int b = posof[p];
+                if (b < 0) { b = nt; posof[p] = nt; s_T[nt] = p; s_sig[nt] = nt; nt++; }
+                const int t = s_sig[s2]; s_sig[s2] = s_sig[b]; s_sig[b] = t;
+            }
+            swp_out[0] = nt;
+            for (int a = 0; a < nt; a++) { swp_out[1 + a] = s_T[a]; swp_out[65 + a] = s_sig[a]; }
+        }
+    };
+
+    if (blockIdx.x == 0) {
+        load_plain(0, min(NB, m));
+        __syncthreads();
+        eliminate(0, min(NB, m), swp);
+    }
+    grid_barrier(bar, nblk, epoch);
+    const int owners = (int)gridDim.x - 1;
+    const int W = (m + owners - 1) / owners;                                // columns per owner CTA
+    const int WP = W <= 8 ? 8 : W <= 16 ? 16 : 32;
+    for (int n = 0; n < np; n++) {
+        const int k0 = n * NB, nb = min(NB, m - k0);
+        const int k1 = k0 + NB, nb1 = n + 1 < np ? min(NB, m - k1) : 0;     // the next panel (none after the last)
+        const int* sw = swp + 160 * (n & 1);
+        __syncthreads();
+        if (tid == 0) s_nt = sw[0];
+        if (tid < 64) { s_T[tid] = sw[1 + tid]; s_sig[tid] = sw[65 + tid]; }
+        __syncthreads();
+        const int nt = s_nt;
+        if (blockIdx.x == 0) {
+            if (nb1 > 0) {
+                // ---- panel n applied to the columns of panel n+1, in shared memory; then that panel is eliminated ----
+                load_plain(k1, nb1);
+                __syncthreads();
+                const int JW = nb1 <= 8 ? 8 : nb1 <= 16 ? 16 : 32;
+                const int jl = tid & (JW - 1), rg = tid / JW, nrg = NT / JW;
+                if (jl < nb1) for (int a = rg; a < nt; a += nrg) tmp[a * 32 + jl] = P[s_T[s_sig[a]] * ld + jl];
+                __syncthreads();
+                if (jl < nb1) for (int a = nb + rg; a < nt; a += nrg) P[s_T[a] * ld + jl] = tmp[a * 32 + jl];
+                __syncthreads();
+                if (jl < nb1) {
+                    double ak[32];
+#pragma unroll
+                    for (int s2 = 0; s2 < 32; s2++) ak[s2] = s2 < nb ? tmp[s2 * 32 + jl] : 0.0;   // rows K_n of these columns
+                    for (int i = rg; i < m; i += nrg) {
+                        double a2 = (i >= k0 && i < k0 + nb) ? 0.0 : P[i * ld + jl];
+                        const double* pr = A + (size_t)i * m + k0;     // P_new(n): panel n is never the last one here, nb = NB
+#pragma unroll
+                        for (int blk = 0; blk < 4; blk++)
+                            if (nb > 8 * blk) {
+#pragma unroll
+                                for (int t2 = 0; t2 < 8; t2++) a2 += pr[8 * blk + t2] * ak[8 * blk + t2];
+                            }
+                        P[i * ld + jl] = a2;
+                    }
+                }
+                __syncthreads();
+                eliminate(k1, nb1, swp + 160 * ((n + 1) & 1));
+            }
+        } else {
+            // ---- owner CTAs: panel n applied to their columns, the columns of panels n and n+1 excepted ----
+            const int c0 = ((int)blockIdx.x - 1) * W, c1 = min(m, c0 + W);
+            if (c0 < c1) {
+                const int nb8 = (nb + 7) & ~7;
+                {
+                    const int JW = nb8 <= 8 ? 8 : nb8 <= 16 ? 16 : 32;
+                    const int jl = tid & (JW - 1), rg = tid / JW, nrg = NT / JW;
+                    if (jl < nb8)
+                        for (int i0 = rg; i0 < m; i0 += 8 * nrg) {
+                            double v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; v[u] = (i < m && jl < nb) ? A[(size_t)i * m + k0 + jl] : 0.0; }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { const int i = i0 + u * nrg; if (i < m) P[i * ld + jl] = v[u]; }
+                        }
+                }
+                __syncthreads();
+                for (int cb = c0; cb < c1; cb += 32) {
+                    const int jc = tid & (WP - 1), rg = tid / WP, nrg = NT / WP;
+                    const int j = cb + jc;
+                    const bool jok = jc < W && j < c1 && !(j >= k0 && j < k0 + nb) && !(j >= k1 && j < k1 + nb1);
+                    for (int a = rg; a < nt; a += nrg) tmp[a * WP + jc] = jok ? A[(size_t)s_T[s_sig[a]] * m + j] : 0.0;
+                    __syncthreads();
+                    for (int a = nb + rg; a < nt; a += nrg) if (jok) A[(size_t)s_T[a] * m + j] = tmp[a * WP + jc];
+                    __syncthreads();
+                    if (jok) {
+                        double ak[32];
+#pragma unroll
+                        for (int s2 = 0; s2 < 32; s2++) ak[s2] = s2 < nb ? tmp[s2 * WP + jc] : 0.0;
+                        for (int i0 = rg; i0 < m; i0 += 8 * nrg) {
+                            double acc[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int i = i0 + u * nrg;
+                                acc[u] = (i < m && !(i >= k0 && i < k0 + nb)) ? A[(size_t)i * m + j] : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int i = i0 + u * nrg;
+                                if (i < m) {
+                                    const double* pr = P + (size_t)i * ld;
+                                    double a2 = acc[u];
+#pragma unroll
+                                    for (int blk = 0; blk < 4; blk++)
+                                        if (nb > 8 * blk) {
+#pragma unroll
+                                            for (int t2 = 0; t2 < 8; t2++) a2 += pr[8 * blk + t2] * ak[8 * blk + t2];
+                                        }
+                                    A[(size_t)i * m + j] = a2;
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        grid_barrier(bar, nblk, epoch);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        for (int c = 0; c < m; c++) colsrc[c] = c;
+        for (int k = m - 1; k >= 0; k--) {
+            const int p = piv[k];
+            if (p != k) { const int t = colsrc[k]; colsrc[k] = colsrc[p]; colsrc[p] = t; }
+        }
+    }
+    grid_barrier(bar, nblk, epoch);
+    for (int i = blockIdx.x; i < m; i += gridDim.x)
+        for (int j = tid; j < m; j += NT) out[(size_t)i * m + j] = A[(size_t)i * m + colsrc[j]];
+}
+
 // ---- substitution ----
 // z = Sinv_j * y_j  (dense m x m times vector; one warp per row)
 __global__ void __launch_bounds__(256) k_dense_matvec(int m, const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y) {
@@ -497,7 +740,7 @@ static int direct_factor(tfb_mat* mat, int prow) {
         TFB_CUDA(cudaMalloc(&f->rowbuf, sizeof(double) * m));
         TFB_CUDA(cudaMalloc(&f->piv, sizeof(int) * m));
         TFB_CUDA(cudaMalloc(&f->colsrc, sizeof(int) * m));
-        TFB_CUDA(cudaMalloc(&f->swp, sizeof(int) * 160));
+        TFB_CUDA(cudaMalloc(&f->swp, sizeof(int) * 320));
         TFB_CUDA(cudaMalloc(&f->bar, sizeof(unsigned) * 2));
         TFB_CUDA(cudaMalloc(&f->vb, sizeof(double) * c->n_local));
         TFB_CUDA(cudaMalloc(&f->vx, sizeof(double) * c->n_local));
@@ -535,6 +778,19 @@ static int direct_factor(tfb_mat* mat, int prow) {
         TFB_CHECK(per_sm >= 1, "the elimination kernel does not fit on an SM");
         gjb_grid = NB >= m ? 1 : (int)std::max<long long>(1, std::min<long long>((long long)sms * per_sm, (m + 7) / 8));
     }
+    // TFB_DIRECT_LOOKAHEAD=1: the look-ahead kernel.  Correct (same tests), but not the default: measured against
+    // k_gj_blocked it gives AMOC 889 -> 847 ms, QG 454 -> 487 ms, heated cavity 46.1 -> 46.5 ms -- the panel elimination on
+    // its one CTA is the critical path either way (about 4 us per elimination step at m = 1280), and what the look-ahead
+    // hides (the update by the other CTAs, two barriers) it pays back as CTA 0's own update of the next panel's columns.
+    static int lookahead = -1;
+    if (lookahead < 0) { const char* e = getenv("TFB_DIRECT_LOOKAHEAD"); lookahead = (e && e[0] == '1') ? 1 : 0; }
+    int gjl_grid = 0;
+    if (NB > 0 && NB < m && lookahead) {
+        TFB_CUDA(cudaFuncSetAttribute(k_gj_lookahead<GJ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gj_bytes(NB)));
+        TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gj_lookahead<GJ_NT>, GJ_NT, gj_bytes(NB)));
+        if (per_sm >= 1) gjl_grid = (int)std::min<long long>((long long)sms * per_sm, (m + 7) / 8 + 1);
+        if (gjl_grid < 2) gjl_grid = 0;
+    }
     TFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gauss_jordan<256>, 256, 0));
     const int gj_grid = (int)std::max<long long>(1, std::min<long long>((long long)sms * std::min(per_sm, 2), ((long long)mm + 256 * 8 - 1) / (256 * 8)));
     double amax = 0.0;   // scale for the singularity test: largest |value| of the matrix
@@ -557,7 +813,8 @@ static int direct_factor(tfb_mat* mat, int prow) {
             TFB_LAUNCHED(); TFB_LAUNCHED();
         }
         TFB_CUDA(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * 2, c->stream));
-        if (NB > 0) k_gj_blocked<GJ_NT><<<gjb_grid, GJ_NT, gj_bytes(NB), c->stream>>>(m, NB, f->S, f->piv, f->swp, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        if (gjl_grid > 0) k_gj_lookahead<GJ_NT><<<gjl_grid, GJ_NT, gj_bytes(NB), c->stream>>>(m, NB, f->S, f->piv, f->swp, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
+        else if (NB > 0) k_gj_blocked<GJ_NT><<<gjb_grid, GJ_NT, gj_bytes(NB), c->stream>>>(m, NB, f->S, f->piv, f->swp, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
         else k_gauss_jordan<256><<<gj_grid, 256, 0, c->stream>>>(m, f->S, f->colbuf, f->rowbuf, f->piv, f->colsrc, f->bar, f->Sinv + (size_t)j * mm, tiny);
         TFB_LAUNCHED();
         TFB_CUDA(cudaGetLastError());
