@@ -758,6 +758,9 @@ static int direct_factor(tfb_mat* mat, int prow) {
     TFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->desc.device));
     // blocked elimination (k_gj_blocked): the panel width is what fits in shared memory next to the column buffers; a block
     // that fits whole is one panel on one CTA.  TFB_DIRECT_UNBLOCKED=1 keeps the column-at-a-time kernel.
+    // 512 threads: measured against 256 (AMOC 1122 ms, QG 559 ms) and 1024 with the update's operands in shared memory
+    // (977 ms, 484 ms); 512 gives 889 ms, 454 ms -- more warps make the three CTA barriers of a step dearer, fewer leave
+    // the LDS -> DFMA -> STS chains exposed
     constexpr int GJ_NT = 512;
     auto gj_bytes = [&](int nb) {
         const size_t pan = (size_t)m * (nb | 1) + 2048;
