@@ -106,6 +106,10 @@ int tfb_sync(tfb_ctx* ctx);
  * and read them all after the loop, so that no host synchronisation sits between the iterations. */
 int tfb_event_record(tfb_ctx* ctx, int slot);
 int tfb_event_elapsed_ms(tfb_ctx* ctx, int slot_a, int slot_b, float* ms);
+/* Plane boundaries 0 = b[0] < b[1] < ... = nzl of the z-pieces over which tfb_jacobian pipelines upload, assembly and
+ * download of a slab of nzl planes (small pieces at both ends, 32-plane pieces in the middle). Returns the number of
+ * boundaries written to `out` (< 0: bad arguments). Host-only: no device is touched. */
+int tfb_pipe_pieces_of(int nzl, int* out, int cap);
 /* write `bytes` of device memory (> L2) to evict the L2 between timed iterations */
 int tfb_flush_l2(tfb_ctx* ctx);
 /* page-locked host buffers for the host<->device legs of the e2e path */

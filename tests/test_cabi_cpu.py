@@ -51,3 +51,21 @@ def test_every_problem_type_has_a_kernel_family():
         cfg = recipes.find_config(problem, dim, nz, dof)
         assert cfg is not None
         assert _lib.lib().tfb_config_name(cfg.cid).decode() == cfg.name
+
+
+def test_host_pipeline_pieces_cover_the_slab():
+    '''The z-pieces over which tfb_jacobian pipelines upload, assembly and download (csrc/tfb_core.cu, tfb_pipe_pieces):
+    strictly increasing boundaries from 0 to nzl for every slab height, small pieces at both ends of tall slabs.'''
+    L = _lib.lib()
+    out = (ctypes.c_int * 128)()
+    for nzl in list(range(1, 200)) + [255, 256, 257, 512, 1000, 1024]:
+        n = L.tfb_pipe_pieces_of(nzl, out, 128)
+        b = list(out[:n])
+        assert n >= 2 and b[0] == 0 and b[-1] == nzl, (nzl, b)
+        assert all(y > x for x, y in zip(b, b[1:])), (nzl, b)
+        sizes = [y - x for x, y in zip(b, b[1:])]
+        assert max(sizes) <= 32 or nzl < 64, (nzl, sizes)
+        if nzl >= 96:
+            assert sizes[0] == 4 and sizes[-1] == 4, (nzl, sizes)       # short fill and drain of the pipeline
+    assert list(out[:L.tfb_pipe_pieces_of(128, out, 128)]) == [0, 4, 16, 32, 64, 96, 112, 124, 128]
+    assert L.tfb_pipe_pieces_of(0, out, 128) < 0

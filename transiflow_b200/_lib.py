@@ -50,7 +50,7 @@ EXPORTS = [
     'tfb_sizes', 'tfb_get_pattern', 'tfb_mat_create', 'tfb_mat_destroy', 'tfb_mat_get_values',
     'tfb_mat_set_values', 'tfb_mat_add_diag', 'tfb_mat_set_shift', 'tfb_rhs', 'tfb_jacobian', 'tfb_mass_diag', 'tfb_state_upload',
     'tfb_assemble_resident', 'tfb_rhs_download', 'tfb_host_checksum', 'tfb_upload_count', 'tfb_sync', 'tfb_event_record', 'tfb_event_elapsed_ms',
-    'tfb_flush_l2', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_spmv_bench', 'tfb_solve', 'tfb_direct_solve', 'tfb_fdm_set', 'tfb_fdm_set_pencil', 'tfb_fdm_pin', 'tfb_joint_set', 'tfb_joint_apply', 'tfb_precond_apply', 'tfb_precond_apply_opts', 'tfb_nccl_unique_id', 'tfb_comm_init',
+    'tfb_flush_l2', 'tfb_pipe_pieces_of', 'tfb_pinned_alloc', 'tfb_pinned_free', 'tfb_launch_count', 'tfb_spmv', 'tfb_spmv_bench', 'tfb_solve', 'tfb_direct_solve', 'tfb_fdm_set', 'tfb_fdm_set_pencil', 'tfb_fdm_pin', 'tfb_joint_set', 'tfb_joint_apply', 'tfb_precond_apply', 'tfb_precond_apply_opts', 'tfb_nccl_unique_id', 'tfb_comm_init',
 ]
 
 

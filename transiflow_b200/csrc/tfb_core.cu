@@ -553,6 +553,15 @@ static std::vector<int> tfb_pipe_pieces(int nzl) {
     return b;
 }
 
+// the piece boundaries for a slab of nzl planes (host-only; tests/test_cabi_cpu.py checks the grading without a device)
+extern "C" int tfb_pipe_pieces_of(int nzl, int* out, int cap) {
+    if (nzl < 1 || !out || cap < 2) return -1;
+    const std::vector<int> b = tfb_pipe_pieces(nzl);
+    if ((int)b.size() > cap) return -1;
+    for (size_t i = 0; i < b.size(); i++) out[i] = b[i];
+    return (int)b.size();
+}
+
 // Host-buffer path for 3-D grids (one GPU or a z-slab): the upload of the state, the assembly and the download
 // of F(x) are pipelined over z-pieces on three streams (PCIe is full duplex), so the call costs
 // about max(H2D, D2H) instead of H2D + kernel + D2H.
