@@ -514,10 +514,9 @@ def main():
                 'csr_equivalent_bytes': csr_bytes, 'csr_equivalent_gbs': csr_bytes / (sp_ms * 1e-3) / 1e9,
                 'kernel': 'tfb_spmv_march_kernel (values-only stream, TMA bulk loads, no column indices)'}
         if world > 1:
-            # every product of this loop meets both z-neighbours in its halo exchange and is followed by a host
-            # synchronisation: on many ranks the sample contains the launch skew of the slowest neighbour;
-            # the operator phase inside the Krylov solve (device timers under 'Verbose') is the figure to compare
-            spmv['includes'] = 'halo exchange (NCCL send/recv with both z-neighbours) + host synchronisation per product'
+            # every product of this loop meets both z-neighbours in its halo exchange: the figure is the median of 50
+            # device-timed products (a late rank lengthens single samples by milliseconds)
+            spmv['includes'] = 'halo exchange (NCCL send/recv with both z-neighbours); median of 50 device-timed products'
     except Exception as e:     # noqa: BLE001
         spmv = {'error': str(e)}
 

@@ -2693,24 +2693,24 @@ extern "C" int tfb_spmv_bench(tfb_mat* m, int reps, int masked, float* ms_out) {
     const int dim = c->desc.dim;
     const unsigned velmask = (1u << dim) - 1u;
     TFB_CUDA(cudaMemcpyAsync(s->vec[0], s->d_mass, sizeof(double) * c->n_local, cudaMemcpyDeviceToDevice, c->stream));   // any non-zero x
-    cudaEvent_t e0, e1;
-    TFB_CUDA(cudaEventCreate(&e0)); TFB_CUDA(cudaEventCreate(&e1));
     for (int w = 0; w < 3; w++)
         if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, masked ? velmask : 0u, nullptr)) return -1;
-    // one timed launch at a time: on z-slabs every product contains a halo exchange, and a Krylov solve synchronises
-    // with the host between products; 50 un-synchronised grouped send/recv pairs measured rank skew instead (round 1:
-    // 2.5 ms at 8 ranks against 0.31 ms at 4)
-    float ms = 0.f;
+    // One event pair per product, read after the loop; the result is the MEDIAN.  On z-slabs every product meets both
+    // neighbours in its halo exchange, so a single late rank (host launch skew at the start of the loop, a descheduled
+    // host thread) lengthens individual samples by milliseconds: the mean of such a loop measured the skew (round 1:
+    // 2.5 ms at 8 ranks against 0.31 ms at 4), a host synchronisation after every product made it worse (3.3 - 5.5 ms).
+    std::vector<cudaEvent_t> ev(2 * (size_t)reps);
+    for (auto& e : ev) TFB_CUDA(cudaEventCreate(&e));
     for (int r = 0; r < reps; r++) {
-        TFB_CUDA(cudaEventRecord(e0, c->stream));
+        TFB_CUDA(cudaEventRecord(ev[2 * r], c->stream));
         if (spmv(c, m, s->vec[0], s->vec[1], dim, masked ? velmask : 0u, masked ? velmask : 0u, nullptr)) return -1;
-        TFB_CUDA(cudaEventRecord(e1, c->stream));
-        TFB_CUDA(cudaEventSynchronize(e1));
-        float one = 0.f;
-        cudaEventElapsedTime(&one, e0, e1);
-        ms += one;
+        TFB_CUDA(cudaEventRecord(ev[2 * r + 1], c->stream));
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    *ms_out = ms / reps;
+    TFB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<float> t(reps, 0.f);
+    for (int r = 0; r < reps; r++) cudaEventElapsedTime(&t[r], ev[2 * r], ev[2 * r + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::sort(t.begin(), t.end());
+    *ms_out = t[reps / 2];
     return 0;
 }
