@@ -36,6 +36,7 @@ CASES = {
     'rb_semi2d_rand': (RB, 6, 5, 1, 3, 5, 11),
     'dhc2d_rand': (DHC, 8, 8, 1, None, None, 12),
     'dhc3d_rand': (DHC, 4, 5, 4, None, None, 13),
+    'dhc_semi2d_rand': (DHC, 6, 5, 1, 3, 5, 16),
     'qg_rand': (QG, 8, 6, 1, None, None, 14),
     'qg_zero': (QG, 6, 6, 1, None, None, 'zero'),
     'amoc_rand': (AMOC, 8, 6, 1, None, None, 15),

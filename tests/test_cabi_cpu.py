@@ -47,7 +47,8 @@ def test_coordinate_vectors_match_oracle_copy():
 def test_every_problem_type_has_a_kernel_family():
     for problem, dim, nz, dof in ((recipes.LDC, 2, 1, 3), (recipes.LDC, 3, 8, 4), (recipes.RB, 2, 1, 4),
                                   (recipes.RBP, 3, 8, 5), (recipes.DHC, 2, 1, 4), (recipes.DHC, 3, 4, 5),
-                                  (recipes.QG, 2, 1, 3), (recipes.AMOC, 2, 1, 5), (recipes.LDC, 3, 1, 4)):
+                                  (recipes.QG, 2, 1, 3), (recipes.AMOC, 2, 1, 5), (recipes.LDC, 3, 1, 4),
+                                  (recipes.RB, 3, 1, 5), (recipes.DHC, 3, 1, 5)):
         cfg = recipes.find_config(problem, dim, nz, dof)
         assert cfg is not None
         assert _lib.lib().tfb_config_name(cfg.cid).decode() == cfg.name

@@ -258,6 +258,29 @@ def test_direct_solve_with_line_blocks_beyond_one_panel(problem, nx, ny):
     assert numpy.abs(y - want).max() <= 1e-9 * numpy.abs(want).max()
 
 
+def test_semi_2d_heated_cavity_solve():
+    """dim = 3 on an nz = 1 grid (the z-offsets fold onto the cell, Discretization.py:127-128) for the heated cavity, dof 5:
+    the folded kernel family `dhc3d_flat` and the direct solve, against SuperLU on the pinned host matrix."""
+    import scipy.sparse.linalg
+    p = {'Problem Type': 'Differentially Heated Cavity', 'Rayleigh Number': 1e4, 'Prandtl Number': 1000.0,
+         'Reynolds Number': 1, 'X-max': 0.051, 'Y-max': 1}
+    from transiflow_b200 import Interface
+    it = Interface(dict(p), 12, 10, 1, 3, 5)
+    x = numpy.random.default_rng(1).uniform(-0.1, 0.1, it.n)
+    jac, f = it.jacobian_rhs(x)
+    dx = it.solve(jac, -f)
+    assert it.last_solve['converged'], it.last_solve
+    A = jac.tocsr().tolil()
+    pr = it.pressure_row
+    A[pr, :] = 0
+    A[:, pr] = 0
+    A[pr, pr] = -1
+    b = -f.copy()
+    b[pr] = 0
+    want = scipy.sparse.linalg.spsolve(A.tocsc(), b)
+    assert numpy.abs(dx - want).max() <= 1e-8 * numpy.abs(want).max()
+
+
 def test_full_size_128_cubed_newton_update_properties():
     """BASELINE headline size (3-D cavity 128^3, 8.4 M unknowns): SuperLU is out of reach there, so the Newton update of
     the solver that bench.py times (IDR(8), scaled-mass Schur complement, tensor-core sub-solves -- what 'auto' picks at

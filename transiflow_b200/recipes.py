@@ -109,6 +109,7 @@ CONFIGS = [
     Config('amoc2d', 7, AMOC, 2, True, 5, _amoc),
     Config('ldc3d_flat', 8, LDC, 3, True, 4, _ldc),
     Config('rb3d_flat', 9, RB, 3, True, 5, _rb),
+    Config('dhc3d_flat', 10, DHC, 3, True, 5, _dhc),
 ]
 
 PROBLEM_IDS = {
